@@ -1,0 +1,196 @@
+/*
+ * nas3d_b200.h — C-ABI of the B200-native compute path for nas_3d_unet.
+ *
+ * The reference (woodywff/nas_3d_unet) is pure PyTorch: its "FFI" for this path is the
+ * ATen dispatch underneath torch.nn (prim_ops.py:58,63,66,95-110,133-147,161-163;
+ * cell.py:30,32,81,82; loss.py:13-14).  Every entry point below replaces one of those
+ * dispatch sites (cited per function) with a hand-written sm_100a kernel.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless marked "host".
+ *  - activations are fp32 NDHWC ("channels-last 3-D"): element (n,d,h,w,c) of a tensor
+ *    with voxel pitch `ld` (floats) lives at  base[(((n*D+d)*H+h)*W+w)*ld + c].
+ *    `ld >= C` lets a tensor be a channel slice of a wider buffer (zero-copy concat,
+ *    cell.py:82).  C and ld are multiples of 4 except where stated.
+ *  - parameters keep the reference's state_dict layouts: Conv3d [Cout,Cin/g,k,k,k],
+ *    ConvTranspose3d [Cin,Cout/g,k,k,k], GroupNorm/Linear as in torch.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *    nothing, keeps no pointer after returning, and may be called from any host thread
+ *    (the autograd worker thread calls the *_bwd entry points).
+ *  - return value: 0 on success, negative nas3d_status on error; nas3d_last_error()
+ *    returns a thread-local message.
+ */
+#ifndef NAS3D_B200_H
+#define NAS3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NAS3D_OK = 0,
+  NAS3D_ERR_ARG = -1,      /* bad shape / alignment / unsupported combination */
+  NAS3D_ERR_CUDA = -2,     /* a CUDA runtime call or launch failed */
+  NAS3D_ERR_UNSUPPORTED = -3
+} nas3d_status;
+
+int nas3d_version(void);
+const char* nas3d_last_error(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+unsigned long long nas3d_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout: NCDHW (what search.py:212 hands over) -> NDHWC with pitch ld_dst.
+ * V = D*H*W.  C arbitrary.
+ * ------------------------------------------------------------------------------------- */
+int nas3d_ncdhw_to_ndhwc(const float* src, float* dst, int N, int C, long long V, int ld_dst,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Convolutions.  Replaces nn.Conv3d / nn.ConvTranspose3d forward and convolution_backward
+ * (prim_ops.py:95-110,142-147).
+ *
+ * One descriptor describes the CONV VIEW of the op: a "big" tensor (Db,Hb,Wb,Cb) that is
+ * gathered from and a "small" tensor (Ds,Hs,Ws,Cs) with
+ *       big_pos = small_pos*stride - pad + tap*dil            (per axis, tap in [0,k))
+ *   Conv3d:           big = module input,  small = module output
+ *   ConvTranspose3d:  big = module output, small = module input
+ * and a weight tensor W[Cs][Cb/groups][k][k][k] (exactly the torch layout in both cases).
+ * groups is 1 or Cb==Cs (depthwise).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int N;
+  int Db, Hb, Wb, Cb, ld_big;
+  int Ds, Hs, Ws, Cs, ld_small;
+  int k, stride, dil, pad;
+  int depthwise;            /* 0: groups=1, 1: groups=C */
+} nas3d_conv_desc;
+
+/* small[o,cs] = bias[cs] + sum_{tap,cb} f(big[o*s-p+t*d, cb]) * W[cs][cb][tap]
+ * f = optional prologue on the big tensor: relu (preprocess 'act_weight_norm', cell.py:47-50)
+ * and/or per-(n,cb) scale `big_scale` [N,Cb] (Dropout3d mask, nas.py:50; may be NULL).
+ * out_sigmoid: apply 1/(1+exp(-v)) in the epilogue (nn.Sigmoid of last_conv, nas.py:52).
+ * Used for: Conv3d forward, ConvTranspose3d dgrad. */
+int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const float* w,
+                              const float* bias, const float* big_scale, int big_relu,
+                              int out_sigmoid, float* small, int accumulate, void* stream);
+
+/* big[i,cb] (+)= bias[cb] + sum over (o,tap) with o*s-p+t*d == i of small[o,cs]*W[cs][cb][tap]
+ * Optional epilogue for the dgrad of a prologue'd Conv3d: result *= (mask_big>0) and
+ * *= big_scale[n,cb].  Used for: ConvTranspose3d forward, Conv3d dgrad. */
+int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, const float* w,
+                              const float* bias, const float* mask_big, int ld_mask,
+                              const float* big_scale, float* big, int accumulate, void* stream);
+
+/* dW[cs][cb][tap] += sum_{n,o} small[o,cs] * f(big[o*s-p+t*d, cb]);
+ * d_bias_small[cs] += sum small (if non-NULL);  d_bias_big[cb] += sum big (if non-NULL).
+ * dW / d_bias must be zero-initialised by the caller (they are accumulated with atomics so
+ * they can live directly in the flat gradient bucket that NCCL all-reduces). */
+int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,
+                     const float* big_scale, int big_relu, float* dW, float* d_bias_small,
+                     float* d_bias_big, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-(n,c) moments: S[n][c] = {sum x, sum x^2} in fp64 (zeroed inside the call).
+ * Serves GroupNorm statistics (prim_ops.py:56-58,77) and the SE squeeze
+ * (AdaptiveAvgPool3d, prim_ops.py:133,150).
+ * ------------------------------------------------------------------------------------- */
+int nas3d_moments_nc(const float* x, int N, long long V, int C, int ld, double* S, void* stream);
+
+/* GroupNorm coefficients: y = a[n,c]*x + b[n,c]  with a = rstd*gamma, b = beta - mean*a.
+ * G groups of C/G channels, biased variance, eps (nn.GroupNorm).  mean_rstd [N,G,2] fp32 out. */
+int nas3d_gn_coef(const double* S, const float* gamma, const float* beta, int N, int C, int G,
+                  long long V, float eps, float* a, float* b, float* mean_rstd, void* stream);
+
+/* SE excitation (prim_ops.py:134-139,151): s[n,c] = sigmoid(W2[c]*relu(W1.mean[n,:]+b1)+b2[c]).
+ * W1 [1,C], b1 [1], W2 [C,1], b2 [C].  hz [N,2] = {relu(z), z} saved for backward. */
+int nas3d_se_excite(const double* S, const float* W1, const float* b1, const float* W2,
+                    const float* b2, int N, int C, long long V, float* s, float* hz, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused affine-sum:  out = sum_k w_k * act_k(a_k[n,c]*x_k + b_k[n,c])
+ * This one kernel is MixedOp's softmax(alpha)-weighted sum (cell.py:30,32) fused with the
+ * GroupNorm-apply / ReLU / SE-scale epilogues of the candidate ops (prim_ops.py:75-80,152),
+ * the node sum (cell.py:81, searched.py:50) and the concat (cell.py:82: `out` may be a
+ * channel slice).  All arrays below are HOST arrays of length nterms (<= NAS3D_MAX_TERMS).
+ * a[k]/b[k] may be NULL (=1 / =0); w[k] is a DEVICE pointer to one float or NULL (=1).
+ * ------------------------------------------------------------------------------------- */
+#define NAS3D_MAX_TERMS 32
+int nas3d_affine_sum_fwd(int nterms, const float* const* x, const int* ld_x,
+                         const float* const* a, const float* const* b, const float* const* w,
+                         const int* relu, float* out, int ld_out, int N, long long V, int C,
+                         void* stream);
+
+/* Backward pass 1: per term k and (n,c):  R[k][n][c] = { sum m*dout, sum m*dout*x_k } (fp64),
+ * m = relu mask (a*x+b > 0) or 1.  R[k] are device pointers to [N,C,2] doubles (zeroed inside). */
+int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld_x,
+                                const float* const* a, const float* const* b, const int* relu,
+                                const float* dout, int ld_dout, double* const* R, int N,
+                                long long V, int C, void* stream);
+
+/* GroupNorm backward coefficients from R (one term):
+ *   dx = p*m*dout + q*x + r ;  dgamma[c] += .. ; dbeta[c] += .. ; dw += <dout, y>  (if dw!=NULL)
+ * w: device scalar weight of the term (NULL = 1).  p,q,r: [N,C] fp32 out. */
+int nas3d_gn_bwd_coef(const double* R, const float* mean_rstd, const float* gamma,
+                      const float* a, const float* b, const float* w, int N, int C, int G,
+                      long long V, float* p, float* q, float* r, float* dgamma, float* dbeta,
+                      float* dw, void* stream);
+
+/* SE backward coefficients from R (term x*s): p = w*s, q = 0, r = dmean/V; parameter grads of
+ * the two Linear layers are accumulated (atomics).  S = forward moments of x. */
+int nas3d_se_bwd_coef(const double* R, const double* S, const float* s, const float* hz,
+                      const float* W1, const float* W2, const float* w, int N, int C, long long V,
+                      float* p, float* r, float* dW1, float* db1, float* dW2, float* db2,
+                      float* dw, void* stream);
+
+/* Plain term (a=1,b=0, e.g. pooling outputs): only dw += sum_{n,c} R2 is needed. */
+int nas3d_plain_bwd_coef(const double* R, const float* w, int N, int C, float* dw, void* stream);
+
+/* Backward pass 2: dx_k (+)= p_k*m*dout + q_k*x_k + r_k.  p/q/r may be NULL (p: use w_k or 1;
+ * q,r: 0).  accumulate[k] != 0 adds into dx_k. Terms that share a dx buffer are handled in
+ * order by the same thread. */
+int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_x,
+                               const float* const* a, const float* const* b, const int* relu,
+                               const float* const* p, const float* const* q,
+                               const float* const* r, const float* const* w,
+                               float* const* dx, const int* ld_dx, const int* accumulate,
+                               const float* dout, int ld_dout, int N, long long V, int C,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * 2x2x2 stride-2 pooling (prim_ops.py:160-168).  kind 0 = avg, 1 = max.
+ * Backward of max re-derives the arg-max from x (first maximum in d,h,w scan order, as
+ * torch's max_pool3d_with_indices does).
+ * ------------------------------------------------------------------------------------- */
+int nas3d_pool2_fwd(int kind, const float* x, int ld_x, float* y, int ld_y, int N, int Do, int Ho,
+                    int Wo, int C, void* stream);
+int nas3d_pool2_bwd(int kind, const float* x, int ld_x, const float* dy, int ld_dy, float* dx,
+                    int ld_dx, int accumulate, int N, int Do, int Ho, int Wo, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Soft Dice (loss.py:12-14).  pred/truth are addressed as base[n*sn + c*sc + v*sv] so both
+ * NDHWC model outputs and NCDHW label tensors are read in place.
+ * sums [N,C,3] fp64 = {sum p*t, sum p, sum t} (zeroed inside); loss: 1 float.
+ * ------------------------------------------------------------------------------------- */
+int nas3d_dice_fwd(const float* pred, long long p_sn, long long p_sc, long long p_sv,
+                   const float* truth, long long t_sn, long long t_sc, long long t_sv, int N,
+                   int C, long long V, float smooth, double* sums, float* loss, void* stream);
+/* dpred[n,c,v] = gout * d loss / d pred, written with pred's addressing. */
+int nas3d_dice_bwd(const double* sums, const float* gout, const float* truth, long long t_sn,
+                   long long t_sc, long long t_sv, float* dpred, long long p_sn, long long p_sc,
+                   long long p_sv, int N, int C, long long V, float smooth, void* stream);
+
+/* dlogit = dprob * prob * (1-prob)   (backward of nn.Sigmoid, nas.py:52); n contiguous floats */
+int nas3d_sigmoid_bwd(const float* prob, const float* dprob, float* dlogit, long long n,
+                      void* stream);
+
+/* y (+)= x, n contiguous floats (gradient accumulation of multiply-used activations) */
+int nas3d_add_inplace(float* y, const float* x, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAS3D_B200_H */

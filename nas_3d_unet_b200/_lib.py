@@ -1,0 +1,112 @@
+"""ctypes binding of libnas3d_b200.so (the C-ABI declared in include/nas3d_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnas3d_b200.so")
+
+c_float_p = C.c_void_p   # device pointers travel as integers
+c_ll = C.c_longlong
+c_int = C.c_int
+c_vp = C.c_void_p
+
+
+class ConvDesc(C.Structure):
+    """mirror of nas3d_conv_desc"""
+    _fields_ = [(n, C.c_int) for n in (
+        "N", "Db", "Hb", "Wb", "Cb", "ld_big", "Ds", "Hs", "Ws", "Cs", "ld_small",
+        "k", "stride", "dil", "pad", "depthwise")]
+
+
+class Nas3dError(RuntimeError):
+    pass
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PP = C.POINTER(C.c_void_p)   # host array of device pointers
+_PI = C.POINTER(C.c_int)      # host array of ints
+_SIGNATURES = {
+    "nas3d_version": [],
+    "nas3d_last_error": [],
+    "nas3d_launch_count": [],
+    "nas3d_ncdhw_to_ndhwc": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp],
+    "nas3d_conv_small_from_big": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp,
+                                  c_int, c_vp],
+    "nas3d_conv_big_from_small": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
+                                  c_int, c_vp],
+    "nas3d_conv_wgrad": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_moments_nc": [c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp],
+    "nas3d_gn_coef": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, C.c_float, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_se_excite": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp],
+    "nas3d_affine_sum_fwd": [c_int, _PP, _PI, _PP, _PP, _PP, _PI, c_vp, c_int, c_int, c_ll, c_int,
+                             c_vp],
+    "nas3d_affine_sum_bwd_reduce": [c_int, _PP, _PI, _PP, _PP, _PI, c_vp, c_int, _PP, c_int, c_ll,
+                                    c_int, c_vp],
+    "nas3d_gn_bwd_coef": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, c_vp, c_vp,
+                          c_vp, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_se_bwd_coef": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp,
+                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_plain_bwd_coef": [c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    "nas3d_affine_sum_bwd_apply": [c_int, _PP, _PI, _PP, _PP, _PI, _PP, _PP, _PP, _PP, _PP, _PI,
+                                   _PI, c_vp, c_int, c_int, c_ll, c_int, c_vp],
+    "nas3d_pool2_fwd": [c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp],
+    "nas3d_pool2_bwd": [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int,
+                        c_int, c_int, c_vp],
+    "nas3d_dice_fwd": [c_vp, c_ll, c_ll, c_ll, c_vp, c_ll, c_ll, c_ll, c_int, c_int, c_ll, C.c_float,
+                       c_vp, c_vp, c_vp],
+    "nas3d_dice_bwd": [c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_vp, c_ll, c_ll, c_ll, c_int, c_int,
+                       c_ll, C.c_float, c_vp],
+    "nas3d_sigmoid_bwd": [c_vp, c_vp, c_vp, c_ll, c_vp],
+    "nas3d_add_inplace": [c_vp, c_vp, c_ll, c_vp],
+}
+_RESTYPES = {
+    "nas3d_last_error": C.c_char_p,
+    "nas3d_launch_count": C.c_ulonglong,
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """dlopen the library once; raises Nas3dError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Nas3dError(
+            "%s not found: build it with `python -m nas_3d_unet_b200.build` "
+            "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().nas3d_last_error()
+        raise Nas3dError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(load().nas3d_launch_count())
+
+
+def ptr_array(ptrs):
+    """host array of device pointers from a list of ints/None"""
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p if p else None
+    return arr
+
+
+def int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])

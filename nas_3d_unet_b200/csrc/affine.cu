@@ -1,0 +1,253 @@
+// Fused affine-sum kernels: the MixedOp / node-sum / GroupNorm-apply / ReLU / SE-scale /
+// concat hot loop of cell.py:30,32,81,82 and prim_ops.py:75-80,152 as ONE pass over memory.
+//
+//   fwd : out = sum_k w_k * act_k(a_k[n,c]*x_k + b_k[n,c])          reads K tensors, writes 1
+//   bwd : dx_k (+)= p_k*m_k*dout + q_k*x_k + r_k                    reads dout (+x_k), writes K
+//
+// HBM-bound: one float4 (4 channels of one voxel) per thread per iteration, grid-stride,
+// grid = 148 SMs x 8 CTAs.  Per-(n,c) coefficients are tiny and stay in L1.
+#include "common.cuh"
+
+namespace nas3d {
+
+struct FwdTerms {
+  const float* x[NAS3D_MAX_TERMS];
+  const float* a[NAS3D_MAX_TERMS];
+  const float* b[NAS3D_MAX_TERMS];
+  const float* w[NAS3D_MAX_TERMS];
+  int ld[NAS3D_MAX_TERMS];
+  int relu[NAS3D_MAX_TERMS];
+  int nterms;
+};
+
+__global__ void __launch_bounds__(256)
+    affine_sum_fwd_kernel(const __grid_constant__ FwdTerms T, float* __restrict__ out, int ld_out,
+                          long long V, int C, int C4, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long gv = i / C4;
+    const int c = (int)(i - gv * C4) * 4;
+    const long long nc = (gv / V) * C + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int k = 0; k < T.nterms; ++k) {
+      float4 v = ldg4(T.x[k] + gv * T.ld[k] + c);
+      if (T.a[k]) {
+        const float4 a = ldg4(T.a[k] + nc);
+        v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w;
+      }
+      if (T.b[k]) {
+        const float4 b = ldg4(T.b[k] + nc);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (T.relu[k]) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      const float w = T.w[k] ? __ldg(T.w[k]) : 1.f;
+      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+    st4(out + gv * ld_out + c, acc);
+  }
+}
+
+struct BwdTerms {
+  const float* x[NAS3D_MAX_TERMS];
+  const float* a[NAS3D_MAX_TERMS];
+  const float* b[NAS3D_MAX_TERMS];
+  const float* p[NAS3D_MAX_TERMS];
+  const float* q[NAS3D_MAX_TERMS];
+  const float* r[NAS3D_MAX_TERMS];
+  const float* w[NAS3D_MAX_TERMS];
+  float* dx[NAS3D_MAX_TERMS];
+  int ld[NAS3D_MAX_TERMS];
+  int ld_dx[NAS3D_MAX_TERMS];
+  int relu[NAS3D_MAX_TERMS];
+  int acc[NAS3D_MAX_TERMS];
+  int nterms;
+};
+
+__global__ void __launch_bounds__(256)
+    affine_sum_bwd_apply_kernel(const __grid_constant__ BwdTerms T, const float* __restrict__ dout,
+                                int ld_dout, long long V, int C, int C4, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long gv = i / C4;
+    const int c = (int)(i - gv * C4) * 4;
+    const long long nc = (gv / V) * C + c;
+    const float4 d = ldg4(dout + gv * ld_dout + c);
+    for (int k = 0; k < T.nterms; ++k) {
+      float4 g = d;
+      const bool need_x = T.relu[k] || T.q[k];
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (need_x) x = ldg4(T.x[k] + gv * T.ld[k] + c);
+      if (T.relu[k]) {
+        float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T.a[k]) a = ldg4(T.a[k] + nc);
+        if (T.b[k]) b = ldg4(T.b[k] + nc);
+        g.x = (a.x * x.x + b.x > 0.f) ? g.x : 0.f;
+        g.y = (a.y * x.y + b.y > 0.f) ? g.y : 0.f;
+        g.z = (a.z * x.z + b.z > 0.f) ? g.z : 0.f;
+        g.w = (a.w * x.w + b.w > 0.f) ? g.w : 0.f;
+      }
+      if (T.p[k]) {
+        const float4 p = ldg4(T.p[k] + nc);
+        g.x *= p.x; g.y *= p.y; g.z *= p.z; g.w *= p.w;
+      } else if (T.w[k]) {
+        const float w = __ldg(T.w[k]);
+        g.x *= w; g.y *= w; g.z *= w; g.w *= w;
+      }
+      if (T.q[k]) {
+        const float4 q = ldg4(T.q[k] + nc);
+        g.x += q.x * x.x; g.y += q.y * x.y; g.z += q.z * x.z; g.w += q.w * x.w;
+      }
+      if (T.r[k]) {
+        const float4 r = ldg4(T.r[k] + nc);
+        g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
+      }
+      float* dst = T.dx[k] + gv * T.ld_dx[k] + c;
+      if (T.acc[k]) {
+        // plain load (not the read-only path): an earlier term of this very launch may have
+        // written this location from this same thread
+        const float4 o = *reinterpret_cast<const float4*>(dst);
+        g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+      }
+      st4(dst, g);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n4,
+                       long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 a = *reinterpret_cast<float4*>(y + i * 4);
+    const float4 b = ldg4(x + i * 4);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    st4(y + i * 4, a);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[n4 * 4 + threadIdx.x] += x[n4 * 4 + threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256)
+    sigmoid_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob,
+                       float* __restrict__ dlogit, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float p = __ldg(prob + i);
+    dlogit[i] = __ldg(dprob + i) * p * (1.f - p);
+  }
+}
+
+// NCDHW -> NDHWC: one thread per voxel, coalesced plane reads, C-wide row writes
+__global__ void __launch_bounds__(256)
+    ncdhw_to_ndhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+                          long long V, int ld, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / V, v = i - n * V;
+    const float* s = src + n * C * V + v;
+    float* d = dst + i * ld;
+    if ((C & 3) == 0 && (ld & 3) == 0) {
+      for (int c = 0; c < C; c += 4) {
+        float4 t;
+        t.x = __ldg(s + (long long)(c + 0) * V);
+        t.y = __ldg(s + (long long)(c + 1) * V);
+        t.z = __ldg(s + (long long)(c + 2) * V);
+        t.w = __ldg(s + (long long)(c + 3) * V);
+        st4(d + c, t);
+      }
+    } else {
+      for (int c = 0; c < C; ++c) d[c] = __ldg(s + (long long)c * V);
+    }
+  }
+}
+
+static inline unsigned grid_for(long long total, int block) {
+  long long b = (total + block - 1) / block;
+  long long cap = (long long)kNumSMs * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace nas3d
+
+using namespace nas3d;
+
+extern "C" {
+
+int nas3d_affine_sum_fwd(int nterms, const float* const* x, const int* ld_x,
+                         const float* const* a, const float* const* b, const float* const* w,
+                         const int* relu, float* out, int ld_out, int N, long long V, int C,
+                         void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "affine_sum_fwd: nterms=%d", nterms);
+  NAS3D_REQUIRE(C % 4 == 0 && ld_out % 4 == 0 && aligned16(out),
+                "affine_sum_fwd: C=%d ld_out=%d must be multiples of 4, out 16B aligned", C, ld_out);
+  FwdTerms T;
+  T.nterms = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    NAS3D_REQUIRE(ld_x[k] % 4 == 0 && aligned16(x[k]), "affine_sum_fwd: term %d misaligned", k);
+    T.x[k] = x[k]; T.ld[k] = ld_x[k];
+    T.a[k] = a ? a[k] : nullptr; T.b[k] = b ? b[k] : nullptr; T.w[k] = w ? w[k] : nullptr;
+    T.relu[k] = relu ? relu[k] : 0;
+  }
+  const int C4 = C / 4;
+  const long long total = (long long)N * V * C4;
+  affine_sum_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(T, out, ld_out, V,
+                                                                                C, C4, total);
+  return launched("affine_sum_fwd");
+}
+
+int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_x,
+                               const float* const* a, const float* const* b, const int* relu,
+                               const float* const* p, const float* const* q,
+                               const float* const* r, const float* const* w,
+                               float* const* dx, const int* ld_dx, const int* accumulate,
+                               const float* dout, int ld_dout, int N, long long V, int C,
+                               void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "affine_sum_bwd_apply: nterms=%d", nterms);
+  NAS3D_REQUIRE(C % 4 == 0 && ld_dout % 4 == 0 && aligned16(dout),
+                "affine_sum_bwd_apply: C=%d ld_dout=%d", C, ld_dout);
+  BwdTerms T;
+  T.nterms = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    NAS3D_REQUIRE(ld_dx[k] % 4 == 0 && aligned16(dx[k]), "affine_sum_bwd_apply: dx %d misaligned", k);
+    T.x[k] = x ? x[k] : nullptr; T.ld[k] = ld_x ? ld_x[k] : 0;
+    T.a[k] = a ? a[k] : nullptr; T.b[k] = b ? b[k] : nullptr;
+    T.p[k] = p ? p[k] : nullptr; T.q[k] = q ? q[k] : nullptr; T.r[k] = r ? r[k] : nullptr;
+    T.w[k] = w ? w[k] : nullptr;
+    T.dx[k] = dx[k]; T.ld_dx[k] = ld_dx[k];
+    T.relu[k] = relu ? relu[k] : 0; T.acc[k] = accumulate ? accumulate[k] : 0;
+    NAS3D_REQUIRE(!(T.relu[k] || T.q[k]) || T.x[k], "affine_sum_bwd_apply: term %d needs x", k);
+  }
+  const int C4 = C / 4;
+  const long long total = (long long)N * V * C4;
+  affine_sum_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      T, dout, ld_dout, V, C, C4, total);
+  return launched("affine_sum_bwd_apply");
+}
+
+int nas3d_add_inplace(float* y, const float* x, long long n, void* stream) {
+  NAS3D_REQUIRE(aligned16(y) && aligned16(x), "add_inplace: pointers must be 16B aligned");
+  long long n4 = n / 4;
+  add_inplace_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, (cudaStream_t)stream>>>(y, x, n4, n);
+  return launched("add_inplace");
+}
+
+int nas3d_sigmoid_bwd(const float* prob, const float* dprob, float* dlogit, long long n,
+                      void* stream) {
+  sigmoid_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(prob, dprob, dlogit, n);
+  return launched("sigmoid_bwd");
+}
+
+int nas3d_ncdhw_to_ndhwc(const float* src, float* dst, int N, int C, long long V, int ld_dst,
+                         void* stream) {
+  NAS3D_REQUIRE(ld_dst >= C, "ncdhw_to_ndhwc: ld_dst < C");
+  const long long total = (long long)N * V;
+  ncdhw_to_ndhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, C, V,
+                                                                                ld_dst, total);
+  return launched("ncdhw_to_ndhwc");
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+// Per-(n,c) reductions and the tiny coefficient kernels that turn them into the per-(n,c)
+// affine coefficients consumed by the fused affine-sum kernels (affine.cu).
+//
+// Memory-bound family (HBM roofline): each activation tensor is read exactly once, with
+// 128-bit loads; fp32 partials over <=32 elements per thread, fp64 from there on
+// (GroupNorm statistics of inputs up to ~110 in magnitude cancel badly in fp32).
+#include "common.cuh"
+
+namespace nas3d {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+constexpr int RB = 256;     // threads per reduction block
+constexpr int RITER = 32;   // super-elements per thread
+
+// ---------------------------------------------------------------------------------------
+// moments: S[n][c] = {sum x, sum x^2}
+// channel float4-groups C4 = U*P (U odd, P power of two <= 256).  A thread owns the U groups
+// p*U..p*U+U-1 of the voxels j>>log2(P) for its fixed p = tid & (P-1).
+// ---------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(RB) moments_nc_kernel(const float* __restrict__ x, long long V,
+                                                         int C, int ld, int P, int logP,
+                                                         double* __restrict__ S) {
+  const int n = blockIdx.y;
+  const long long total = V << logP;  // super-elements in this sample
+  const long long j0 = (long long)blockIdx.x * (RB * RITER) + threadIdx.x;
+  const int p = threadIdx.x & (P - 1);
+  const float* xb = x + (long long)n * V * ld + (long long)p * U * 4;
+
+  float s[U][4], q[U][4];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[u][e] = q[u][e] = 0.f;
+
+#pragma unroll 4
+  for (int it = 0; it < RITER; ++it) {
+    long long j = j0 + (long long)it * RB;
+    if (j < total) {
+      const float* px = xb + (j >> logP) * ld;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float4 v = ldg4(px + u * 4);
+        s[u][0] += v.x; s[u][1] += v.y; s[u][2] += v.z; s[u][3] += v.w;
+        q[u][0] += v.x * v.x; q[u][1] += v.y * v.y; q[u][2] += v.z * v.z; q[u][3] += v.w * v.w;
+      }
+    }
+  }
+
+  __shared__ double sm[2 * 4 * 64 * 3 / 1];  // [C*2] (C <= 768)
+  for (int i = threadIdx.x; i < C * 2; i += RB) sm[i] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double a = s[u][e], b = q[u][e];
+      for (int o = 16; o >= P; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane < P || P > 32) {
+        int c = (p * U + u) * 4 + e;
+        atomicAdd(&sm[c * 2 + 0], a);
+        atomicAdd(&sm[c * 2 + 1], b);
+      }
+    }
+  __syncthreads();
+  double* Sn = S + (long long)n * C * 2;
+  for (int i = threadIdx.x; i < C * 2; i += RB) atomicAdd(&Sn[i], sm[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward reduce for up to TG terms per block (blockIdx.z selects the term group):
+//   R[k][n][c] = { sum m*dout, sum m*dout*x_k },  m = (a*x+b > 0) if relu else 1
+// ---------------------------------------------------------------------------------------
+struct ReduceTerms {
+  const float* x[NAS3D_MAX_TERMS];
+  const float* a[NAS3D_MAX_TERMS];
+  const float* b[NAS3D_MAX_TERMS];
+  double* R[NAS3D_MAX_TERMS];
+  int ld[NAS3D_MAX_TERMS];
+  int relu[NAS3D_MAX_TERMS];
+  int nterms;
+};
+
+template <int U, int TG>
+__global__ void __launch_bounds__(RB)
+    bwd_reduce_kernel(const __grid_constant__ ReduceTerms T, const float* __restrict__ dout,
+                      int ld_dout, long long V, int C, int P, int logP) {
+  const int n = blockIdx.y;
+  const int k0 = blockIdx.z * TG;
+  const long long total = V << logP;
+  const long long j0 = (long long)blockIdx.x * (RB * RITER) + threadIdx.x;
+  const int p = threadIdx.x & (P - 1);
+  const int cbase = p * U * 4;
+  const float* db = dout + (long long)n * V * ld_dout + cbase;
+
+  float r1[TG][U][4], r2[TG][U][4];
+#pragma unroll
+  for (int t = 0; t < TG; ++t)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r1[t][u][e] = r2[t][u][e] = 0.f;
+
+  for (int it = 0; it < RITER; ++it) {
+    long long j = j0 + (long long)it * RB;
+    if (j >= total) break;
+    const long long vox = j >> logP;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 d4 = ldg4(db + vox * ld_dout + u * 4);
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int t = 0; t < TG; ++t) {
+        const int k = k0 + t;
+        if (k < T.nterms) {
+          const float4 x4 = ldg4(T.x[k] + ((long long)n * V + vox) * T.ld[k] + cbase + u * 4);
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+          float m[4] = {1.f, 1.f, 1.f, 1.f};
+          if (T.relu[k]) {
+            float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (T.a[k]) a4 = ldg4(T.a[k] + (long long)n * C + cbase + u * 4);
+            if (T.b[k]) b4 = ldg4(T.b[k] + (long long)n * C + cbase + u * 4);
+            m[0] = (a4.x * xv[0] + b4.x > 0.f) ? 1.f : 0.f;
+            m[1] = (a4.y * xv[1] + b4.y > 0.f) ? 1.f : 0.f;
+            m[2] = (a4.z * xv[2] + b4.z > 0.f) ? 1.f : 0.f;
+            m[3] = (a4.w * xv[3] + b4.w > 0.f) ? 1.f : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float md = m[e] * d[e];
+            r1[t][u][e] += md;
+            r2[t][u][e] += md * xv[e];
+          }
+        }
+      }
+    }
+  }
+
+  __shared__ double sm[TG * 768 * 2];  // TG * C * 2, C <= 768 (TG=4 -> 48 KB is too much: see host)
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < TG * C * 2; i += RB) sm[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < TG; ++t)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        double a = r1[t][u][e], b = r2[t][u][e];
+        for (int o = 16; o >= P; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane < P || P > 32) {
+          int c = cbase + u * 4 + e;
+          atomicAdd(&sm[(t * C + c) * 2 + 0], a);
+          atomicAdd(&sm[(t * C + c) * 2 + 1], b);
+        }
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TG * C * 2; i += RB) {
+    int t = i / (C * 2);
+    int k = k0 + t;
+    if (k < T.nterms) atomicAdd(&T.R[k][(long long)n * C * 2 + (i - t * C * 2)], sm[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tiny per-sample coefficient kernels: grid = N, block = 128
+// ---------------------------------------------------------------------------------------
+constexpr int TB = 128;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < TB / 32; ++i) t += sh[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(TB)
+    gn_coef_kernel(const double* __restrict__ S, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int C, int G, double inv_m, float eps,
+                   float* __restrict__ a, float* __restrict__ b, float* __restrict__ mean_rstd) {
+  const int n = blockIdx.x;
+  const int cg = C / G;
+  __shared__ float sh_mean[64], sh_rstd[64];
+  const double* Sn = S + (long long)n * C * 2;
+  for (int g = threadIdx.x; g < G; g += TB) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { s += Sn[c * 2]; q += Sn[c * 2 + 1]; }
+    double mean = s * inv_m;
+    double var = q * inv_m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sh_mean[g] = (float)mean;
+    sh_rstd[g] = rstd;
+    mean_rstd[((long long)n * G + g) * 2 + 0] = (float)mean;
+    mean_rstd[((long long)n * G + g) * 2 + 1] = rstd;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TB) {
+    int g = c / cg;
+    float av = sh_rstd[g] * gamma[c];
+    a[(long long)n * C + c] = av;
+    b[(long long)n * C + c] = beta[c] - sh_mean[g] * av;
+  }
+}
+
+__global__ void __launch_bounds__(TB)
+    se_excite_kernel(const double* __restrict__ S, const float* __restrict__ W1,
+                     const float* __restrict__ b1, const float* __restrict__ W2,
+                     const float* __restrict__ b2, int C, double inv_v, float* __restrict__ s,
+                     float* __restrict__ hz) {
+  const int n = blockIdx.x;
+  __shared__ double sh[TB / 32];
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += TB)
+    part += (double)W1[c] * (double)(float)(S[((long long)n * C + c) * 2] * inv_v);
+  float z = (float)block_sum(part, sh) + b1[0];
+  float h = z > 0.f ? z : 0.f;
+  if (threadIdx.x == 0) { hz[n * 2 + 0] = h; hz[n * 2 + 1] = z; }
+  for (int c = threadIdx.x; c < C; c += TB) {
+    float e = W2[c] * h + b2[c];
+    s[(long long)n * C + c] = 1.f / (1.f + expf(-e));
+  }
+}
+
+__global__ void __launch_bounds__(TB)
+    gn_bwd_coef_kernel(const double* __restrict__ R, const float* __restrict__ mean_rstd,
+                       const float* __restrict__ gamma, const float* __restrict__ a,
+                       const float* __restrict__ b, const float* __restrict__ w, int C, int G,
+                       double inv_m, float* __restrict__ p, float* __restrict__ q,
+                       float* __restrict__ r, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dw) {
+  const int n = blockIdx.x;
+  const int cg = C / G;
+  const double wv = w ? (double)w[0] : 1.0;
+  __shared__ double shA[64], shB[64];
+  __shared__ double sh[TB / 32];
+  const double* Rn = R + (long long)n * C * 2;
+  for (int g = threadIdx.x; g < G; g += TB) {
+    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+    double A = 0.0, B = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
+      A += (double)gamma[c] * r1;
+      B += (double)gamma[c] * rho * (r2 - mu * r1);
+    }
+    shA[g] = A;
+    shB[g] = B;
+  }
+  __syncthreads();
+  double dwp = 0.0;
+  for (int c = threadIdx.x; c < C; c += TB) {
+    int g = c / cg;
+    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+    double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
+    double qq = -rho * rho * shB[g] * inv_m;
+    p[(long long)n * C + c] = (float)(wv * rho * (double)gamma[c]);
+    q[(long long)n * C + c] = (float)(wv * qq);
+    r[(long long)n * C + c] = (float)(wv * (-qq * mu - rho * shA[g] * inv_m));
+    atomicAdd(&dgamma[c], (float)(wv * rho * (r2 - mu * r1)));
+    atomicAdd(&dbeta[c], (float)(wv * r1));
+    dwp += (double)a[(long long)n * C + c] * r2 + (double)b[(long long)n * C + c] * r1;
+  }
+  if (dw) {
+    double tot = block_sum(dwp, sh);
+    if (threadIdx.x == 0) atomicAdd(dw, (float)tot);
+  }
+}
+
+__global__ void __launch_bounds__(TB)
+    se_bwd_coef_kernel(const double* __restrict__ R, const double* __restrict__ S,
+                       const float* __restrict__ s, const float* __restrict__ hz,
+                       const float* __restrict__ W1, const float* __restrict__ W2,
+                       const float* __restrict__ w, int C, double inv_v, float* __restrict__ p,
+                       float* __restrict__ r, float* __restrict__ dW1, float* __restrict__ db1,
+                       float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dw) {
+  const int n = blockIdx.x;
+  const double wv = w ? (double)w[0] : 1.0;
+  const float h = hz[n * 2 + 0], z = hz[n * 2 + 1];
+  __shared__ double sh[TB / 32];
+  double dh_part = 0.0, dw_part = 0.0;
+  for (int c = threadIdx.x; c < C; c += TB) {
+    double r2 = R[((long long)n * C + c) * 2 + 1];
+    double sv = s[(long long)n * C + c];
+    double de = wv * r2 * sv * (1.0 - sv);
+    atomicAdd(&dW2[c], (float)(de * h));
+    atomicAdd(&db2[c], (float)de);
+    dh_part += de * (double)W2[c];
+    dw_part += sv * r2;
+    p[(long long)n * C + c] = (float)(wv * sv);
+  }
+  double dh = block_sum(dh_part, sh);
+  double dz = z > 0.f ? dh : 0.0;
+  for (int c = threadIdx.x; c < C; c += TB) {
+    double mean = S[((long long)n * C + c) * 2] * inv_v;
+    atomicAdd(&dW1[c], (float)(dz * mean));
+    r[(long long)n * C + c] = (float)(dz * (double)W1[c] * inv_v);
+  }
+  if (threadIdx.x == 0) atomicAdd(db1, (float)dz);
+  if (dw) {
+    double tot = block_sum(dw_part, sh);
+    if (threadIdx.x == 0) atomicAdd(dw, (float)tot);
+  }
+}
+
+__global__ void __launch_bounds__(TB)
+    plain_bwd_coef_kernel(const double* __restrict__ R, int NC, float* __restrict__ dw) {
+  __shared__ double sh[TB / 32];
+  double part = 0.0;
+  for (int i = threadIdx.x; i < NC; i += TB) part += R[(long long)i * 2 + 1];
+  double tot = block_sum(part, sh);
+  if (threadIdx.x == 0) atomicAdd(dw, (float)tot);
+}
+
+static int check_channels(int C, int ld, int* U, int* P, int* logP) {
+  NAS3D_REQUIRE(C > 0 && C % 4 == 0 && ld % 4 == 0 && ld >= C,
+                "channel count %d / pitch %d must be multiples of 4", C, ld);
+  NAS3D_REQUIRE(C <= 768, "C=%d > 768 unsupported", C);
+  split_c4(C / 4, U, P);
+  NAS3D_REQUIRE(*U == 1 || *U == 3, "C=%d: odd factor %d of C/4 unsupported (1 or 3)", C, *U);
+  NAS3D_REQUIRE(*P <= 256, "C=%d too wide", C);
+  int l = 0;
+  while ((1 << l) < *P) ++l;
+  *logP = l;
+  return NAS3D_OK;
+}
+
+}  // namespace nas3d
+
+using namespace nas3d;
+
+extern "C" {
+
+int nas3d_version(void) { return 100; }
+const char* nas3d_last_error(void) { return g_err; }
+unsigned long long nas3d_launch_count(void) { return g_launches.load(); }
+
+int nas3d_moments_nc(const float* x, int N, long long V, int C, int ld, double* S, void* stream) {
+  int U, P, logP;
+  int rc = check_channels(C, ld, &U, &P, &logP);
+  if (rc) return rc;
+  NAS3D_REQUIRE(aligned16(x), "moments_nc: x not 16B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  NAS3D_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  long long total = V * P;
+  dim3 grid((unsigned)((total + RB * RITER - 1) / (RB * RITER)), N);
+  if (U == 1) moments_nc_kernel<1><<<grid, RB, 0, st>>>(x, V, C, ld, P, logP, S);
+  else moments_nc_kernel<3><<<grid, RB, 0, st>>>(x, V, C, ld, P, logP, S);
+  return launched("moments_nc");
+}
+
+int nas3d_gn_coef(const double* S, const float* gamma, const float* beta, int N, int C, int G,
+                  long long V, float eps, float* a, float* b, float* mean_rstd, void* stream) {
+  NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "gn_coef: bad groups %d for C=%d", G, C);
+  double inv_m = 1.0 / ((double)(C / G) * (double)V);
+  gn_coef_kernel<<<N, TB, 0, (cudaStream_t)stream>>>(S, gamma, beta, C, G, inv_m, eps, a, b,
+                                                     mean_rstd);
+  return launched("gn_coef");
+}
+
+int nas3d_se_excite(const double* S, const float* W1, const float* b1, const float* W2,
+                    const float* b2, int N, int C, long long V, float* s, float* hz, void* stream) {
+  se_excite_kernel<<<N, TB, 0, (cudaStream_t)stream>>>(S, W1, b1, W2, b2, C, 1.0 / (double)V, s,
+                                                       hz);
+  return launched("se_excite");
+}
+
+int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld_x,
+                                const float* const* a, const float* const* b, const int* relu,
+                                const float* dout, int ld_dout, double* const* R, int N,
+                                long long V, int C, void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "bwd_reduce: nterms=%d", nterms);
+  int U, P, logP;
+  int rc = check_channels(C, ld_dout, &U, &P, &logP);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  ReduceTerms T;
+  T.nterms = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    NAS3D_REQUIRE(ld_x[k] % 4 == 0 && aligned16(x[k]), "bwd_reduce: term %d misaligned", k);
+    T.x[k] = x[k]; T.a[k] = a ? a[k] : nullptr; T.b[k] = b ? b[k] : nullptr;
+    T.R[k] = R[k]; T.ld[k] = ld_x[k]; T.relu[k] = relu ? relu[k] : 0;
+    NAS3D_CUDA(cudaMemsetAsync(R[k], 0, sizeof(double) * 2 * (size_t)N * C, st));
+  }
+  long long total = V * P;
+  unsigned gx = (unsigned)((total + RB * RITER - 1) / (RB * RITER));
+  // TG=2 keeps the fp64 staging array (TG*C*2 doubles) inside 48 KB static smem for C<=768/..;
+  // wide tensors are tiny in this network so TG=1 there.
+  if (U == 1 && C <= 256) {
+    dim3 grid(gx, N, (nterms + 1) / 2);
+    bwd_reduce_kernel<1, 2><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP);
+  } else if (U == 1) {
+    dim3 grid(gx, N, nterms);
+    bwd_reduce_kernel<1, 1><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP);
+  } else {
+    dim3 grid(gx, N, nterms);
+    bwd_reduce_kernel<3, 1><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP);
+  }
+  return launched("affine_sum_bwd_reduce");
+}
+
+int nas3d_gn_bwd_coef(const double* R, const float* mean_rstd, const float* gamma,
+                      const float* a, const float* b, const float* w, int N, int C, int G,
+                      long long V, float* p, float* q, float* r, float* dgamma, float* dbeta,
+                      float* dw, void* stream) {
+  NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "gn_bwd_coef: bad groups %d for C=%d", G, C);
+  double inv_m = 1.0 / ((double)(C / G) * (double)V);
+  gn_bwd_coef_kernel<<<N, TB, 0, (cudaStream_t)stream>>>(R, mean_rstd, gamma, a, b, w, C, G,
+                                                         inv_m, p, q, r, dgamma, dbeta, dw);
+  return launched("gn_bwd_coef");
+}
+
+int nas3d_se_bwd_coef(const double* R, const double* S, const float* s, const float* hz,
+                      const float* W1, const float* W2, const float* w, int N, int C, long long V,
+                      float* p, float* r, float* dW1, float* db1, float* dW2, float* db2,
+                      float* dw, void* stream) {
+  se_bwd_coef_kernel<<<N, TB, 0, (cudaStream_t)stream>>>(R, S, s, hz, W1, W2, w, C,
+                                                         1.0 / (double)V, p, r, dW1, db1, dW2,
+                                                         db2, dw);
+  return launched("se_bwd_coef");
+}
+
+int nas3d_plain_bwd_coef(const double* R, const float* w, int N, int C, float* dw, void* stream) {
+  (void)w;
+  NAS3D_REQUIRE(dw != nullptr, "plain_bwd_coef: dw is NULL");
+  plain_bwd_coef_kernel<<<1, TB, 0, (cudaStream_t)stream>>>(R, N * C, dw);
+  return launched("plain_bwd_coef");
+}
+
+}  // extern "C"

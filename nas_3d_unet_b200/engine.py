@@ -1,0 +1,616 @@
+"""Host-side executor of the B200 compute path.
+
+The reference builds its graph out of torch.nn leaf modules and lets torch autograd replay
+it (prim_ops.py:68-83, cell.py:24-33,66-82).  Here the module tree (same classes, same
+state_dict) *records a tape of C-ABI kernel launches* instead: one torch.autograd.Function
+wraps the outermost module call, its forward walks the tree launching the sm_100a kernels of
+libnas3d_b200.so on torch's current stream, its backward replays the tape in reverse.  Torch
+only supplies device memory, streams and the autograd edge to the caller.
+
+Vocabulary
+  Act   an activation: logical (N,C,D,H,W) torch tensor, physically NDHWC with voxel pitch ld
+        (possibly a channel slice of a wider buffer = zero-copy concat).
+  Term  a lazily evaluated per-(n,c) affine view  act(a[n,c]*x + b[n,c])  of an Act: GroupNorm
+        apply, ReLU, SE channel scale and the softmax(alpha) weight all fold into a Term, and
+        affine_sum() evaluates a whole list of Terms in one pass over memory.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, int_array, ptr_array
+
+
+class Nas3dDeviceError(RuntimeError):
+    pass
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise Nas3dDeviceError(
+            "%s is on %s: the nas3d_b200 path runs on CUDA (sm_100a) only, there is no CPU fallback"
+            % (what, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (what, t.dtype))
+
+
+# ----------------------------------------------------------------------------------------
+# activations
+# ----------------------------------------------------------------------------------------
+class Act:
+    __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad")
+
+    def __init__(self, t, ld, requires_grad=True):
+        self.t = t
+        self.g = None
+        self.N, self.C, self.D, self.H, self.W = t.shape
+        self.ld = ld
+        self.requires_grad = requires_grad
+
+    @property
+    def V(self):
+        return self.D * self.H * self.W
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def grad_slot(self):
+        """(grad Act-like tensor, accumulate flag) for a producer of d(this)."""
+        if self.g is None:
+            self.g = alloc(self.N, self.C, self.D, self.H, self.W, self.t.device)
+            return self.g, 0
+        return self.g, 1
+
+    def slice(self, c0, c1):
+        a = Act(self.t[:, c0:c1], self.ld, self.requires_grad)
+        return a
+
+
+def alloc(N, Cc, D, H, W, device):
+    """logical (N,C,D,H,W) tensor, physical NDHWC dense"""
+    return torch.empty((N, D, H, W, Cc), device=device, dtype=torch.float32).permute(0, 4, 1, 2, 3)
+
+
+def new_act(N, Cc, D, H, W, device):
+    return Act(alloc(N, Cc, D, H, W, device), Cc)
+
+
+def _ndhwc_pitch(t):
+    """voxel pitch if t is laid out NDHWC (possibly channel-sliced), else None"""
+    N, Cc, D, H, W = t.shape
+    sn, sc, sd, sh, sw = t.stride()
+    ld = sw
+    if ld < Cc:
+        return None
+    ok = (sc == 1 or Cc == 1) and (sh == W * ld or H == 1) and (sd == H * W * ld or D == 1) and (
+        sn == D * H * W * ld or N == 1)
+    return ld if ok else None
+
+
+def as_act(t, requires_grad):
+    """wrap a caller tensor; NCDHW input is re-laid out by our own kernel"""
+    _require_cuda(t, "input tensor")
+    if t.dim() != 5:
+        raise ValueError("expected a 5-D (N,C,D,H,W) tensor, got shape %s" % (tuple(t.shape),))
+    ld = _ndhwc_pitch(t)
+    if ld is not None and ld % 4 == 0 and t.data_ptr() % 16 == 0:
+        return Act(t, ld, requires_grad)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    N, Cc, D, H, W = t.shape
+    ldd = (Cc + 3) // 4 * 4
+    buf = torch.empty((N, D, H, W, ldd), device=t.device, dtype=torch.float32)
+    if ldd != Cc:
+        buf.zero_()
+    check(_lib.load().nas3d_ncdhw_to_ndhwc(t.data_ptr(), buf.data_ptr(), N, Cc, D * H * W, ldd,
+                                           _stream()), "ncdhw_to_ndhwc")
+    return Act(buf.permute(0, 4, 1, 2, 3)[:, :Cc], ldd, requires_grad)
+
+
+def owned_grad(g, like, force_copy=False):
+    """normalise an incoming gradient tensor to like's NDHWC layout"""
+    ld = _ndhwc_pitch(g)
+    if ld is not None and not force_copy and g.data_ptr() % 16 == 0 and (ld % 4 == 0 or like.C % 4):
+        return g, ld
+    out = alloc(like.N, like.C, like.D, like.H, like.W, g.device)
+    out.copy_(g)
+    return out, like.C
+
+
+# ----------------------------------------------------------------------------------------
+# execution context (one per outermost module call)
+# ----------------------------------------------------------------------------------------
+class Alpha:
+    """softmax(alpha) matrix or row handed in by the caller (cell.py:24-33)"""
+    __slots__ = ("t", "g", "ncol")
+
+    def __init__(self, t):
+        _require_cuda(t, "alpha")
+        self.t = t.contiguous()
+        self.g = None
+        self.ncol = t.shape[-1]
+
+    def ptr(self, row, k):
+        off = (row * self.ncol + k) if self.t.dim() == 2 else k
+        return self.t.data_ptr() + 4 * off
+
+    def gptr(self, row, k):
+        if self.g is None:
+            self.g = torch.zeros_like(self.t)
+        off = (row * self.ncol + k) if self.t.dim() == 2 else k
+        return self.g.data_ptr() + 4 * off
+
+
+class ExecCtx:
+    def __init__(self, record, training, device):
+        self.record = record
+        self.training = training
+        self.device = device
+        self.tape = []
+        self.params = {}        # id(param) -> param (those touched in forward)
+        self.bucket = None
+        self.views = {}
+        self.lib = _lib.load()
+        self.stream = _stream()
+
+    def use(self, *params):
+        for p in params:
+            if p is not None:
+                self.params[id(p)] = p
+
+    def push(self, fn):
+        if self.record:
+            self.tape.append(fn)
+
+    # ---- backward side -------------------------------------------------------------
+    def begin_backward(self):
+        self.stream = _stream()
+        plist = list(self.params.values())
+        total = sum((p.numel() + 3) // 4 * 4 for p in plist)
+        self.bucket = torch.zeros(max(total, 4), device=self.device, dtype=torch.float32)
+        off = 0
+        for p in plist:
+            n = p.numel()
+            self.views[id(p)] = self.bucket[off:off + n].view(p.shape)
+            off += (n + 3) // 4 * 4
+
+    def gptr(self, p):
+        return self.views[id(p)].data_ptr() if p is not None else None
+
+
+# ----------------------------------------------------------------------------------------
+# Terms and the fused affine-sum
+# ----------------------------------------------------------------------------------------
+class Term:
+    __slots__ = ("x", "a", "b", "relu", "kind", "alpha", "aux")
+
+    def __init__(self, x, a=None, b=None, relu=False, kind="plain", aux=None):
+        self.x = x
+        self.a = a
+        self.b = b
+        self.relu = relu
+        self.kind = kind      # 'plain' | 'gn' | 'se' | 'coef' (fixed per-(n,c) scale, no grad to it)
+        self.alpha = None     # (Alpha, row, k)
+        self.aux = aux
+
+    @property
+    def is_identity(self):
+        return self.a is None and self.b is None and not self.relu and self.alpha is None
+
+
+def _tp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def affine_sum(ctx, terms, out):
+    """out = sum_k w_k act_k(a_k x_k + b_k)   (cell.py:30,32,81 / prim_ops.py:75-80,152)"""
+    n = len(terms)
+    lib = ctx.lib
+    rc = lib.nas3d_affine_sum_fwd(
+        n, ptr_array([t.x.ptr for t in terms]), int_array([t.x.ld for t in terms]),
+        ptr_array([_tp(t.a) for t in terms]), ptr_array([_tp(t.b) for t in terms]),
+        ptr_array([t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None for t in terms]),
+        int_array([1 if t.relu else 0 for t in terms]),
+        out.ptr, out.ld, out.N, out.V, out.C, ctx.stream)
+    check(rc, "affine_sum_fwd")
+    ctx.push(lambda: _affine_sum_bwd(ctx, terms, out))
+    return out
+
+
+def _affine_sum_bwd(ctx, terms, out):
+    if out.g is None:
+        return
+    lib = ctx.lib
+    dout = out.g
+    ld_dout = _ndhwc_pitch(dout)
+    N, Cc, V = out.N, out.C, out.V
+    dev = dout.device
+    st = ctx.stream
+    # pass 1: reductions for the terms that need them
+    need = [t for t in terms if t.kind in ("gn", "se") or (t.alpha is not None)]
+    R = {}
+    if need:
+        Rbuf = torch.empty((len(need), N, Cc, 2), device=dev, dtype=torch.float64)
+        for i, t in enumerate(need):
+            R[id(t)] = Rbuf[i]
+        rc = lib.nas3d_affine_sum_bwd_reduce(
+            len(need), ptr_array([t.x.ptr for t in need]), int_array([t.x.ld for t in need]),
+            ptr_array([_tp(t.a) for t in need]), ptr_array([_tp(t.b) for t in need]),
+            int_array([1 if t.relu else 0 for t in need]),
+            dout.data_ptr(), ld_dout, ptr_array([R[id(t)].data_ptr() for t in need]),
+            N, V, Cc, st)
+        check(rc, "affine_sum_bwd_reduce")
+    # per-term coefficient kernels
+    P, Q, Rr = {}, {}, {}
+    for t in terms:
+        wptr = t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None
+        dwptr = t.alpha[0].gptr(t.alpha[1], t.alpha[2]) if t.alpha else None
+        if t.kind == "gn":
+            aux = t.aux
+            pq = torch.empty((3, N, Cc), device=dev, dtype=torch.float32)
+            P[id(t)], Q[id(t)], Rr[id(t)] = pq[0], pq[1], pq[2]
+            rc = lib.nas3d_gn_bwd_coef(
+                R[id(t)].data_ptr(), aux["mean_rstd"].data_ptr(), aux["gamma"].data_ptr(),
+                t.a.data_ptr(), t.b.data_ptr(), wptr, N, Cc, aux["G"], V,
+                pq[0].data_ptr(), pq[1].data_ptr(), pq[2].data_ptr(),
+                ctx.gptr(aux["gamma"]), ctx.gptr(aux["beta"]), dwptr, st)
+            check(rc, "gn_bwd_coef")
+        elif t.kind == "se":
+            aux = t.aux
+            pq = torch.empty((2, N, Cc), device=dev, dtype=torch.float32)
+            P[id(t)], Rr[id(t)] = pq[0], pq[1]
+            fc0, fc2 = aux["fc0"], aux["fc2"]
+            rc = lib.nas3d_se_bwd_coef(
+                R[id(t)].data_ptr(), aux["S"].data_ptr(), t.a.data_ptr(), aux["hz"].data_ptr(),
+                fc0.weight.data_ptr(), fc2.weight.data_ptr(), wptr, N, Cc, V,
+                pq[0].data_ptr(), pq[1].data_ptr(),
+                ctx.gptr(fc0.weight), ctx.gptr(fc0.bias), ctx.gptr(fc2.weight), ctx.gptr(fc2.bias),
+                dwptr, st)
+            check(rc, "se_bwd_coef")
+        elif t.alpha is not None:
+            # plain / fixed-coefficient term under a softmax weight: d alpha = <dout, y>
+            if t.a is None and t.b is None and not t.relu:
+                check(lib.nas3d_plain_bwd_coef(R[id(t)].data_ptr(), wptr, N, Cc, dwptr, st),
+                      "plain_bwd_coef")
+            else:
+                raise NotImplementedError("alpha-weighted term of kind %r with coefficients" % t.kind)
+    # pass 2: dx_k
+    live = [t for t in terms if t.x.requires_grad]
+    if not live:
+        return
+    seen = set()
+    dxs, accs = [], []
+    for t in live:
+        g, acc = t.x.grad_slot()
+        key = id(t.x)
+        if key in seen:
+            acc = 1
+        seen.add(key)
+        dxs.append(g)
+        accs.append(acc)
+
+    def pcoef(t):
+        if id(t) in P:
+            return P[id(t)].data_ptr()
+        if t.kind == "coef" and t.a is not None:
+            return t.a.data_ptr()     # y = a*x with constant a:  dx = a*dout
+        return None
+
+    rc = lib.nas3d_affine_sum_bwd_apply(
+        len(live), ptr_array([t.x.ptr for t in live]), int_array([t.x.ld for t in live]),
+        ptr_array([_tp(t.a) for t in live]), ptr_array([_tp(t.b) for t in live]),
+        int_array([1 if t.relu else 0 for t in live]),
+        ptr_array([pcoef(t) for t in live]),
+        ptr_array([Q[id(t)].data_ptr() if id(t) in Q else None for t in live]),
+        ptr_array([Rr[id(t)].data_ptr() if id(t) in Rr else None for t in live]),
+        ptr_array([t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None for t in live]),
+        ptr_array([g.data_ptr() for g in dxs]), int_array([_ndhwc_pitch(g) for g in dxs]),
+        int_array(accs), dout.data_ptr(), ld_dout, N, V, Cc, st)
+    check(rc, "affine_sum_bwd_apply")
+
+
+def materialize(ctx, term):
+    """evaluate a Term into an Act (no-op for identity terms)"""
+    if term.is_identity:
+        return term.x
+    x = term.x
+    out = new_act(x.N, x.C, x.D, x.H, x.W, ctx.device)
+    return affine_sum(ctx, [term], out)
+
+
+def bind_concat(ctx, out, nodes, c_node):
+    """zero-copy concat (cell.py:82): nodes were written into channel slices of `out`; in the
+    backward the node gradients alias the matching slices of d(out)."""
+    def bwd():
+        if out.g is None:
+            return
+        for j, node in enumerate(nodes):
+            node.g = out.g[:, j * c_node:(j + 1) * c_node]
+    ctx.push(bwd)
+
+
+# ----------------------------------------------------------------------------------------
+# GroupNorm / SE coefficient producers
+# ----------------------------------------------------------------------------------------
+def moments(ctx, x):
+    S = torch.empty((x.N, x.C, 2), device=ctx.device, dtype=torch.float64)
+    check(ctx.lib.nas3d_moments_nc(x.ptr, x.N, x.V, x.C, x.ld, S.data_ptr(), ctx.stream),
+          "moments_nc")
+    return S
+
+
+def gn_term(ctx, x, norm, relu):
+    """GroupNorm (+ReLU) of x as a lazy Term (prim_ops.py:56-58,75-80)"""
+    if norm.num_channels != x.C:
+        raise ValueError("GroupNorm expects %d channels, got %d" % (norm.num_channels, x.C))
+    ctx.use(norm.weight, norm.bias)
+    S = moments(ctx, x)
+    G = norm.num_groups
+    ab = torch.empty((2, x.N, x.C), device=ctx.device, dtype=torch.float32)
+    mr = torch.empty((x.N, G, 2), device=ctx.device, dtype=torch.float32)
+    check(ctx.lib.nas3d_gn_coef(S.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), x.N,
+                                x.C, G, x.V, float(norm.eps), ab[0].data_ptr(), ab[1].data_ptr(),
+                                mr.data_ptr(), ctx.stream), "gn_coef")
+    aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G}
+    return Term(x, ab[0], ab[1], relu, "gn", aux)
+
+
+def se_term(ctx, x, fc):
+    """x * sigmoid(fc(mean(x))) as a lazy Term (prim_ops.py:133-139,149-152)"""
+    fc0, fc2 = fc[0], fc[2]
+    ctx.use(fc0.weight, fc0.bias, fc2.weight, fc2.bias)
+    S = moments(ctx, x)
+    s = torch.empty((x.N, x.C), device=ctx.device, dtype=torch.float32)
+    hz = torch.empty((x.N, 2), device=ctx.device, dtype=torch.float32)
+    check(ctx.lib.nas3d_se_excite(S.data_ptr(), fc0.weight.data_ptr(), fc0.bias.data_ptr(),
+                                  fc2.weight.data_ptr(), fc2.bias.data_ptr(), x.N, x.C, x.V,
+                                  s.data_ptr(), hz.data_ptr(), ctx.stream), "se_excite")
+    return Term(x, s, None, False, "se", {"S": S, "hz": hz, "fc0": fc0, "fc2": fc2})
+
+
+# ----------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------
+class ConvSpec:
+    """static description of an nn.Conv3d / nn.ConvTranspose3d (prim_ops.py:93-110)"""
+    __slots__ = ("k", "stride", "dil", "pad", "out_pad", "transposed", "depthwise", "cin", "cout")
+
+    def __init__(self, m):
+        self.transposed = isinstance(m, torch.nn.ConvTranspose3d)
+        ks, st, dl, pd = m.kernel_size, m.stride, m.dilation, m.padding
+        if len(set(ks)) != 1 or len(set(st)) != 1 or len(set(dl)) != 1 or len(set(pd)) != 1:
+            raise NotImplementedError("anisotropic convolution parameters are not used by this network")
+        self.k, self.stride, self.dil, self.pad = ks[0], st[0], dl[0], pd[0]
+        self.out_pad = m.output_padding[0] if self.transposed else 0
+        self.cin, self.cout = m.in_channels, m.out_channels
+        if m.groups == 1:
+            self.depthwise = False
+        elif m.groups == m.in_channels == m.out_channels:
+            self.depthwise = True
+        else:
+            raise NotImplementedError("groups must be 1 or C")
+        if self.k not in (1, 3):
+            raise NotImplementedError("kernel size %d (1 or 3 supported)" % self.k)
+
+    def out_extent(self, n):
+        if self.transposed:
+            return (n - 1) * self.stride - 2 * self.pad + self.dil * (self.k - 1) + self.out_pad + 1
+        return (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
+
+
+def _desc(spec, big, small):
+    d = ConvDesc()
+    d.N = big.N
+    d.Db, d.Hb, d.Wb, d.Cb, d.ld_big = big.D, big.H, big.W, big.C, big.ld
+    d.Ds, d.Hs, d.Ws, d.Cs, d.ld_small = small.D, small.H, small.W, small.C, small.ld
+    d.k, d.stride, d.dil, d.pad = spec.k, spec.stride, spec.dil, spec.pad
+    d.depthwise = 1 if spec.depthwise else 0
+    return d
+
+
+class _GradView:
+    """lets the conv backward address a gradient tensor like an Act"""
+    __slots__ = ("t", "N", "C", "D", "H", "W", "ld")
+
+    def __init__(self, t, like):
+        self.t = t
+        self.N, self.C, self.D, self.H, self.W = like.N, like.C, like.D, like.H, like.W
+        self.ld = _ndhwc_pitch(t)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False):
+    """y = conv(f(x)) with f = optional relu / per-(n,c) scale prologue; returns the raw Act.
+
+    Conv3d forward is the small-from-big gather, ConvTranspose3d forward the big-from-small
+    gather of the same conv view (include/nas3d_b200.h)."""
+    if x.C != spec.cin:
+        raise ValueError("conv expects %d input channels, got %d" % (spec.cin, x.C))
+    lib = ctx.lib
+    ctx.use(m.weight, m.bias)
+    y = new_act(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
+                ctx.device)
+    bias = m.bias.data_ptr() if m.bias is not None else None
+    if not spec.transposed:
+        d = _desc(spec, x, y)
+        check(lib.nas3d_conv_small_from_big(C.byref(d), x.ptr, m.weight.data_ptr(), bias,
+                                            _tp(in_scale), 1 if in_relu else 0,
+                                            1 if sigmoid else 0, y.ptr, 0, ctx.stream),
+              "conv_small_from_big")
+    else:
+        if in_relu or in_scale is not None or sigmoid:
+            raise NotImplementedError("prologue/epilogue on a transposed convolution")
+        d = _desc(spec, y, x)
+        check(lib.nas3d_conv_big_from_small(C.byref(d), x.ptr, m.weight.data_ptr(), bias, None, 0,
+                                            None, y.ptr, 0, ctx.stream), "conv_big_from_small")
+    ctx.push(lambda: _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid))
+    return y
+
+
+def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
+    if y.g is None:
+        return
+    lib = ctx.lib
+    st = ctx.stream
+    dy_t = y.g
+    if sigmoid:
+        # y holds probabilities; dlogit = dprob * p * (1-p)   (nn.Sigmoid, nas.py:52)
+        dl = torch.empty_like(dy_t)
+        assert _ndhwc_pitch(dy_t) == y.ld == y.C
+        check(lib.nas3d_sigmoid_bwd(y.ptr, dy_t.data_ptr(), dl.data_ptr(), y.N * y.V * y.C, st),
+              "sigmoid_bwd")
+        dy_t = dl
+    dy = _GradView(dy_t, y)
+    dW = ctx.gptr(m.weight)
+    db = ctx.gptr(m.bias) if m.bias is not None else None
+    if not spec.transposed:
+        d = _desc(spec, x, dy)
+        check(lib.nas3d_conv_wgrad(C.byref(d), dy.ptr, x.ptr, _tp(in_scale), 1 if in_relu else 0,
+                                   dW, db, None, st), "conv_wgrad")
+        if x.requires_grad:
+            g, acc = x.grad_slot()
+            gv = _GradView(g, x)
+            d2 = _desc(spec, gv, dy)
+            check(lib.nas3d_conv_big_from_small(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
+                                                x.ptr if in_relu else None, x.ld, _tp(in_scale),
+                                                gv.ptr, acc, st), "conv dgrad")
+    else:
+        d = _desc(spec, dy, x)
+        check(lib.nas3d_conv_wgrad(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, st),
+              "convT wgrad")
+        if x.requires_grad:
+            g, acc = x.grad_slot()
+            gv = _GradView(g, x)
+            d2 = _desc(spec, dy, gv)
+            check(lib.nas3d_conv_small_from_big(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
+                                                None, 0, 0, gv.ptr, acc, st), "convT dgrad")
+
+
+# ----------------------------------------------------------------------------------------
+# pooling
+# ----------------------------------------------------------------------------------------
+def pool2(ctx, x, kind):
+    if x.D % 2 or x.H % 2 or x.W % 2:
+        raise ValueError("2x2x2 pooling needs even extents, got %s" % ((x.D, x.H, x.W),))
+    y = new_act(x.N, x.C, x.D // 2, x.H // 2, x.W // 2, ctx.device)
+    check(ctx.lib.nas3d_pool2_fwd(kind, x.ptr, x.ld, y.ptr, y.ld, x.N, y.D, y.H, y.W, x.C,
+                                  ctx.stream), "pool2_fwd")
+
+    def bwd():
+        if y.g is None or not x.requires_grad:
+            return
+        g, acc = x.grad_slot()
+        check(ctx.lib.nas3d_pool2_bwd(kind, x.ptr, x.ld, y.g.data_ptr(), _ndhwc_pitch(y.g),
+                                      g.data_ptr(), _ndhwc_pitch(g), acc, x.N, y.D, y.H, y.W, x.C,
+                                      ctx.stream), "pool2_bwd")
+    ctx.push(bwd)
+    return y
+
+
+# ----------------------------------------------------------------------------------------
+# the autograd bridge
+# ----------------------------------------------------------------------------------------
+_dp_state = {"enabled": False, "group": None}
+
+
+class _ModuleFn(torch.autograd.Function):
+    """One autograd node for a whole module call (prim op, MixedOp, Cell or a full net)."""
+
+    @staticmethod
+    def forward(fctx, module, n_acts, n_extras, record, *tensors):
+        acts_t = tensors[:n_acts]
+        extras_t = tensors[n_acts:n_acts + n_extras]
+        dev = acts_t[0].device
+        ctx = ExecCtx(record, module.training, dev)
+        with torch.cuda.device(dev):
+            acts = [as_act(t, bool(record and t.requires_grad)) for t in acts_t]
+            extras = [Alpha(t) for t in extras_t]
+            out = module._run(ctx, *acts, *extras)
+            if isinstance(out, Term):
+                out = materialize(ctx, out)
+        fctx.ectx = ctx
+        fctx.acts = acts
+        fctx.extras = extras
+        fctx.out = out
+        fctx.module = module
+        fctx.n_acts, fctx.n_extras = n_acts, n_extras
+        fctx.param_ids = [id(p) for p in tensors[n_acts + n_extras:]]
+        res = out.t
+        if any(res.data_ptr() == a.t.data_ptr() for a in acts):
+            res = res.clone()   # never hand an input back as the output
+            fctx.out = Act(res, _ndhwc_pitch(res))
+            out_src = out
+
+            def bwd_alias():
+                if fctx.out.g is not None and out_src.requires_grad:
+                    g, acc = out_src.grad_slot()
+                    if acc:
+                        g.add_(fctx.out.g)
+                    else:
+                        g.copy_(fctx.out.g)
+            ctx.push(bwd_alias)
+        return res
+
+    @staticmethod
+    def backward(fctx, gout):
+        ctx = fctx.ectx
+        if ctx is None or not ctx.record:
+            raise RuntimeError("backward through a nas3d module call that was not recorded")
+        out = fctx.out
+        with torch.cuda.device(ctx.device):
+            ctx.begin_backward()
+            g, _ = owned_grad(gout, out, force_copy=getattr(fctx.module, "_mutates_out_grad", False))
+            out.g = g
+            for fn in reversed(ctx.tape):
+                fn()
+            ctx.tape = []
+            if _dp_state["enabled"]:
+                _dp_allreduce(ctx, fctx.extras)
+        grads = [None, None, None, None]
+        for a in fctx.acts:
+            grads.append(a.g if a.requires_grad else None)
+        for e in fctx.extras:
+            grads.append(e.g if e.g is not None else (torch.zeros_like(e.t)))
+        for pid in fctx.param_ids:
+            grads.append(ctx.views.get(pid))
+        fctx.ectx = None
+        fctx.acts = fctx.extras = fctx.out = None
+        return tuple(grads)
+
+
+def _dp_allreduce(ctx, extras):
+    """patch-batch data parallelism: average the flat gradient bucket over ranks (NCCL)"""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return
+    world = dist.get_world_size(_dp_state["group"])
+    if world == 1:
+        return
+    dist.all_reduce(ctx.bucket, group=_dp_state["group"])
+    ctx.bucket.mul_(1.0 / world)
+    for e in extras:
+        if e.g is not None:
+            dist.all_reduce(e.g, group=_dp_state["group"])
+            e.g.mul_(1.0 / world)
+
+
+def run_module(module, acts, extras=()):
+    """entry used by every nn.Module.forward of this package"""
+    acts = tuple(acts)
+    extras = tuple(extras)
+    for t in acts:
+        _require_cuda(t, "%s input" % type(module).__name__)
+    params = [p for p in module.parameters()]
+    record = torch.is_grad_enabled() and (
+        any(t.requires_grad for t in acts) or any(t.requires_grad for t in extras)
+        or any(p.requires_grad for p in params))
+    return _ModuleFn.apply(module, len(acts), len(extras), record, *acts, *extras, *params)

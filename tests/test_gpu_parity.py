@@ -1,0 +1,204 @@
+"""GPU: the CUDA path (through the C-ABI) against the reference's golden outputs and the
+oracle.  Tolerances are SURVEY.md §8c's: logits max_rel <= 1e-3, Dice |d| <= 1e-4, flat
+gradient vector max_rel <= 1e-3 (the fp32 kernels land ~1e-5)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nas3d_oracle as O
+from helpers import make_prim, make_searched, make_supernet, prim_inputs, rel_err, tstats
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3
+GRAD_TOL = 1e-3
+DICE_TOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib_loaded(lib):
+    from nas_3d_unet_b200 import _lib
+    before = _lib.launch_count()
+    yield
+    assert _lib.launch_count() > before, "no nas3d kernel was launched: CUDA path not exercised"
+
+
+def _load_params(mod, G, key):
+    with torch.no_grad():
+        for k, p in mod.named_parameters():
+            p.copy_(torch.from_numpy(G[key + '/param/' + k]))
+
+
+def test_prims_match_reference(golden_prims):
+    meta, G = golden_prims
+    worst = {}
+    for e in meta:
+        key = '%s_c%d' % (e['name'], e['c'])
+        op = make_prim(e)
+        _load_params(op, G, key)
+        op = op.cuda()
+        y_ref = G[key + '/y']
+        x, r, _ = prim_inputs(e, y_ref.shape)
+        xg = x.cuda().requires_grad_(True)
+        y = op(xg)
+        assert tuple(y.shape) == y_ref.shape, key
+        (y * r.cuda()).sum().backward()
+        ey = rel_err(y.detach().cpu().numpy(), y_ref)
+        ex = rel_err(xg.grad.cpu().numpy(), G[key + '/dx'])
+        assert ey <= 1e-4, (key, 'y', ey)
+        assert ex <= 1e-4, (key, 'dx', ex)
+        for k, p in op.named_parameters():
+            ref = G[key + '/grad/' + k]
+            assert p.grad is not None, (key, k)
+            eg = rel_err(p.grad.cpu().numpy(), ref)
+            # tiny-magnitude gradients (SE fc.0) are compared absolutely against the scale of y
+            assert eg <= 2e-3 or np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-5, (key, k, eg)
+        worst[key] = (ey, ex)
+    print(json.dumps({k: [float('%.2e' % v) for v in w] for k, w in worst.items()}))
+
+
+def test_prim_accepts_channels_last_and_no_grad(golden_prims):
+    meta, G = golden_prims
+    e = next(m for m in meta if m['name'] == 'conv' and m['c'] == 8)
+    key = 'conv_c8'
+    op = make_prim(e)
+    _load_params(op, G, key)
+    op = op.cuda()
+    x, _, _ = prim_inputs(e)
+    xcl = x.cuda().contiguous(memory_format=torch.channels_last_3d)
+    with torch.no_grad():
+        y = op(xcl)
+    assert rel_err(y.cpu().numpy(), G[key + '/y']) <= 1e-4
+    assert not y.requires_grad
+
+
+@pytest.mark.parametrize("tag,downward", [("down", True), ("up", False)])
+def test_cells_match_reference(golden_cells, tag, downward):
+    from nas_3d_unet_b200.cell import Cell
+    G = golden_cells
+    torch.manual_seed(11)
+    c = Cell(3, 12, 24, 8, downward=downward).cuda()
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.randn(1, 12, 8, 8, 8, generator=g).cuda().requires_grad_(True)
+    x1 = torch.randn(1, 24, 4, 4, 4, generator=g).cuda().requires_grad_(True)
+    a2 = torch.softmax(torch.randn(9, 6 if downward else 4, generator=g), -1).cuda().requires_grad_(True)
+    a1 = torch.softmax(torch.randn(9, 5, generator=g), -1).cuda().requires_grad_(True)
+    y = c(x0, x1, a1, a2)
+    r = torch.randn(y.shape, generator=g).cuda()
+    (y * r).sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), G[tag + '/y']) <= 1e-4
+    assert rel_err(x0.grad.cpu().numpy(), G[tag + '/dx0']) <= GRAD_TOL
+    assert rel_err(x1.grad.cpu().numpy(), G[tag + '/dx1']) <= GRAD_TOL
+    assert rel_err(a1.grad.cpu().numpy(), G[tag + '/da1']) <= GRAD_TOL
+    assert rel_err(a2.grad.cpu().numpy(), G[tag + '/da2']) <= GRAD_TOL
+    gs = np.stack([tstats(p.grad if p.grad is not None else torch.zeros_like(p)) for p in c.parameters()])
+    ref = G[tag + '/grad_stats']
+    # per-tensor L2 norms of the parameter gradients
+    np.testing.assert_allclose(gs[:, 1], ref[:, 1], rtol=5e-3, atol=1e-6)
+
+
+def _run_net(model, x, y):
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    model.zero_grad()
+    pred = model(x.cuda())
+    loss = WeightedDiceLoss()(pred, y.cuda())
+    loss.backward()
+    return pred, loss
+
+
+def _check_net(G, prefix, model, pred, loss):
+    flat = pred.detach().permute(0, 1, 2, 3, 4).reshape(-1).cpu()
+    e_logit = rel_err(flat[torch.from_numpy(G[prefix + '/pred_idx'])].numpy(), G[prefix + '/pred'])
+    e_loss = abs(loss.item() - G[prefix + '/loss'][0])
+    flatg = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                       for _, p in model.named_parameters()]).cpu()
+    e_grad = rel_err(flatg[torch.from_numpy(G[prefix + '/grad_idx'])].numpy(), G[prefix + '/grad_sample'])
+    print(prefix, 'logits %.2e dice %.2e flat-grad %.2e' % (e_logit, e_loss, e_grad))
+    assert e_logit <= LOGIT_TOL and e_loss <= DICE_TOL and e_grad <= GRAD_TOL
+    # whole-vector statistics: L2 norm of the full gradient
+    np.testing.assert_allclose(tstats(flatg)[1], G[prefix + '/grad_flat_stats'][1], rtol=1e-3)
+
+
+def test_searched_net_matches_reference(golden_nets):
+    m = make_searched().cuda()
+    for prefix, (n, seed, brain) in (('searched32', (2, 1, False)), ('searched32_brain', (1, 2, True))):
+        x, y = O.synthetic_batch(n, 32, seed=seed, brain_like=brain)
+        pred, loss = _run_net(m, x, y)
+        assert tuple(pred.shape) == (n, 3, 32, 32, 32)
+        _check_net(golden_nets, prefix, m, pred, loss)
+
+
+def test_supernet_matches_reference(golden_nets):
+    G = golden_nets
+    s = make_supernet().cuda()
+    x, y = O.synthetic_batch(1, 32, seed=3)
+    pred, loss = _run_net(s, x, y)
+    _check_net(G, 'supernet32', s, pred, loss)
+    for k in ('alpha1_down', 'alpha1_up', 'alpha2_down', 'alpha2_up'):
+        e = rel_err(getattr(s, k).grad.cpu().numpy(), G['supernet32/dalpha/' + k])
+        assert e <= GRAD_TOL, (k, e)
+
+
+def test_search_steps_match_reference(golden_nets):
+    """search.py:222-238 verbatim against our modules: alpha step on a val batch, w step on a
+    train batch, torch Adam for both."""
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    G = golden_nets
+    s = make_supernet(random_alphas=False, dropout0=True, train=True).cuda()
+    lossf = WeightedDiceLoss().cuda()
+    optim_shell = torch.optim.Adam(s.alphas())
+    optim_kernel = torch.optim.Adam(s.kernel.parameters())
+    g = torch.Generator().manual_seed(1)
+    losses = []
+    for _ in range(2):
+        x = torch.randn(1, 4, 32, 32, 32, generator=g).cuda()
+        y = (torch.rand(1, 3, 32, 32, 32, generator=g) > 0.7).float().cuda()
+        vx = torch.randn(1, 4, 32, 32, 32, generator=g).cuda()
+        vy = (torch.rand(1, 3, 32, 32, 32, generator=g) > 0.7).float().cuda()
+        optim_shell.zero_grad()
+        vl = lossf(s(vx), vy)
+        vl.backward()
+        optim_shell.step()
+        optim_kernel.zero_grad()
+        l = lossf(s(x), y)
+        l.backward()
+        optim_kernel.step()
+        losses.append([vl.item(), l.item()])
+    np.testing.assert_allclose(np.array(losses), G['search2/losses'], rtol=0, atol=DICE_TOL)
+    assert rel_err(s.alpha2_down.detach().cpu().numpy(), G['search2/alpha2_down']) <= 2e-2
+
+
+@pytest.mark.parametrize("layout", ["ncdhw", "ndhwc"])
+def test_dice_matches_oracle(layout):
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(2, 3, 12, 10, 14, generator=g)
+    t = (torch.rand(2, 3, 12, 10, 14, generator=g) > 0.6).float()
+    pr = p.clone().requires_grad_(True)
+    ref = O.dice_loss(pr, t)
+    ref.backward()
+    pg = p.cuda()
+    if layout == "ndhwc":
+        pg = pg.contiguous(memory_format=torch.channels_last_3d)
+    pg.requires_grad_(True)
+    out = WeightedDiceLoss()(pg, t.cuda())
+    out.backward()
+    assert abs(out.item() - ref.item()) <= 1e-6
+    assert rel_err(pg.grad.cpu().numpy(), pr.grad.numpy()) <= 1e-5
+
+
+def test_searched_net_training_mode_dropout_is_torch_rng_compatible():
+    """Dropout3d(p=0.5) on the head input draws its (N,C) mask from torch's CUDA generator the
+    way feature_dropout does, so the oracle fed with that mask reproduces the output."""
+    m = make_searched().cuda()
+    m.train()
+    x, y = O.synthetic_batch(1, 32, seed=9)
+    torch.manual_seed(1234)
+    pred = m(x.cuda())
+    torch.manual_seed(1234)
+    mask = torch.empty((1, 12, 1, 1, 1), device='cuda').bernoulli_(0.5).div_(0.5).cpu()
+    sd = O.leaf_state(m.state_dict())
+    ref = O.searched_net(sd, x, 4, 3, O.G0, drop_mask=mask)
+    assert O.max_rel(pred, ref) <= LOGIT_TOL
