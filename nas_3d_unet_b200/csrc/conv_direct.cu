@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(CT) conv_gather_kernel(const ConvArgs A) {
   const int Cprod = BFS ? A.Cb : A.Cs, Cred = BFS ? A.Cs : A.Cb;
   const int ldd = BFS ? A.ldb : A.lds, ldr = BFS ? A.lds : A.ldb;
   const int chunk = (A.k == 1) ? RED_CHUNK1 : RED_CHUNK3;
+  const bool vec = (Cred % 4 == 0) && (ldr % 4 == 0);
 
   const long long nvox = (long long)A.N * Dd * Hd * Wd;
   const long long o = (long long)blockIdx.x * CT + threadIdx.x;
@@ -113,20 +114,33 @@ __global__ void __launch_bounds__(CT) conv_gather_kernel(const ConvArgs A) {
           const float* px = A.src + ((((long long)n * Dr + id) * Hr + ih) * Wr + iw) * ldr + c0;
           const float* pw = Wsm + (long long)tap * cn * PT;
           for (int c4 = 0; c4 < cn; c4 += 4) {
-            float4 x4 = ldg4(px + c4);
+            const int nv = min(4, cn - c4);
+            float4 x4;
+            if (vec) {
+              x4 = ldg4(px + c4);
+            } else {
+              x4.x = __ldg(px + c4);
+              x4.y = nv > 1 ? __ldg(px + c4 + 1) : 0.f;
+              x4.z = nv > 2 ? __ldg(px + c4 + 2) : 0.f;
+              x4.w = nv > 3 ? __ldg(px + c4 + 3) : 0.f;
+            }
             if (!BFS) {
               if (A.relu) {
                 x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f);
                 x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f);
               }
               if (A.scale) {
-                const float4 s4 = ldg4(A.scale + (long long)n * A.Cb + c0 + c4);
-                x4.x *= s4.x; x4.y *= s4.y; x4.z *= s4.z; x4.w *= s4.w;
+                const float* ps = A.scale + (long long)n * A.Cb + c0 + c4;
+                x4.x *= __ldg(ps);
+                if (nv > 1) x4.y *= __ldg(ps + 1);
+                if (nv > 2) x4.z *= __ldg(ps + 2);
+                if (nv > 3) x4.w *= __ldg(ps + 3);
               }
             }
             const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              if (e >= nv) break;
               const float4* wr = reinterpret_cast<const float4*>(pw + (c4 + e) * PT);
 #pragma unroll
               for (int j4 = 0; j4 < PT / 4; ++j4) {
@@ -432,9 +446,9 @@ static int launch_gather(const ConvArgs& A, bool depthwise, cudaStream_t st) {
   const int ldr = BFS ? A.lds : A.ldb;
   const long long nvox = BFS ? (long long)A.N * A.Db * A.Hb * A.Wb
                              : (long long)A.N * A.Ds * A.Hs * A.Ws;
-  NAS3D_REQUIRE(Cred % 4 == 0 && ldr % 4 == 0 && aligned16(A.src),
-                "conv: reduced channels %d / pitch %d must be multiples of 4", Cred, ldr);
+  NAS3D_REQUIRE((Cred % 4 != 0 || ldr % 4 != 0) || aligned16(A.src), "conv: src not 16B aligned");
   if (depthwise) {
+    NAS3D_REQUIRE(Cred % 4 == 0 && ldr % 4 == 0, "depthwise conv: C=%d pitch %d", Cred, ldr);
     const int ldd = BFS ? A.ldb : A.lds;
     NAS3D_REQUIRE(ldd % 4 == 0 && aligned16(A.dst), "depthwise conv: dst misaligned");
     NAS3D_REQUIRE(!A.relu && !A.scale && !A.mask && !A.sigmoid, "depthwise conv: no prologue/epilogue");

@@ -30,6 +30,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def get_lib():
+    """the C-ABI library (or bench.py's event-timing proxy around it)"""
+    from . import profiling
+    return profiling.active() or _lib.load()
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise Nas3dDeviceError(
@@ -108,7 +114,7 @@ def as_act(t, requires_grad):
     buf = torch.empty((N, D, H, W, ldd), device=t.device, dtype=torch.float32)
     if ldd != Cc:
         buf.zero_()
-    check(_lib.load().nas3d_ncdhw_to_ndhwc(t.data_ptr(), buf.data_ptr(), N, Cc, D * H * W, ldd,
+    check(get_lib().nas3d_ncdhw_to_ndhwc(t.data_ptr(), buf.data_ptr(), N, Cc, D * H * W, ldd,
                                            _stream()), "ncdhw_to_ndhwc")
     return Act(buf.permute(0, 4, 1, 2, 3)[:, :Cc], ldd, requires_grad)
 
@@ -156,7 +162,7 @@ class ExecCtx:
         self.params = {}        # id(param) -> param (those touched in forward)
         self.bucket = None
         self.views = {}
-        self.lib = _lib.load()
+        self.lib = get_lib()
         self.stream = _stream()
 
     def use(self, *params):
@@ -601,6 +607,14 @@ def _dp_allreduce(ctx, extras):
         if e.g is not None:
             dist.all_reduce(e.g, group=_dp_state["group"])
             e.g.mul_(1.0 / world)
+
+
+def enable_data_parallel(group=None, enabled=True):
+    """patch-batch data parallelism (one process per GPU): every module backward ends with an
+    NCCL all-reduce (mean) of its flat gradient bucket, so the unchanged reference drivers
+    (search.py / train.py step loops) train replicas in lock-step."""
+    _dp_state["enabled"] = bool(enabled)
+    _dp_state["group"] = group
 
 
 def run_module(module, acts, extras=()):

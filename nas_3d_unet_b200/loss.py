@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import _require_cuda, _stream
+from .engine import _require_cuda, _stream, get_lib
 
 
 def _voxel_strides(t):
@@ -22,7 +22,7 @@ def _voxel_strides(t):
 class _DiceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y_pred, y_truth, smooth):
-        lib = _lib.load()
+        lib = get_lib()
         if _voxel_strides(y_pred) is None:
             y_pred = y_pred.contiguous()
         if _voxel_strides(y_truth) is None:
@@ -45,7 +45,7 @@ class _DiceFn(torch.autograd.Function):
     def backward(ctx, gout):
         y_truth, sums = ctx.saved_tensors
         N, C, V, ps, ts, smooth, shape, stride = ctx.geom
-        lib = _lib.load()
+        lib = get_lib()
         gout = gout.contiguous()
         dpred = torch.empty_strided(shape, stride, device=y_truth.device, dtype=torch.float32)
         with torch.cuda.device(y_truth.device):
