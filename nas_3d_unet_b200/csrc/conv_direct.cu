@@ -10,8 +10,55 @@
 // The hot dense 3x3x3 shapes are taken over by specialised kernels (conv_tiled.cu /
 // conv_umma.cu); this file is the always-correct fallback and the odd-shape path.
 #include "common.cuh"
+#include "conv_tiled.h"
+
+#include <stdlib.h>
 
 namespace nas3d {
+
+// conv_pointwise.cu
+int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
+                  const float* scale, int relu, int sigmoid, float* small, int accumulate,
+                  cudaStream_t st);
+int pointwise_bfs(const nas3d_conv_desc* d, const float* small, const float* w, const float* bias,
+                  const float* mask_big, int ld_mask, const float* scale, float* big,
+                  int accumulate, cudaStream_t st);
+int pointwise_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,
+                    const float* scale, int relu, float* dW, float* dbias_small, cudaStream_t st);
+
+static bool tiled_enabled() {
+  const char* e = getenv("NAS3D_DISABLE_TILED");   // read per call so tests can A/B the paths
+  return !(e && e[0] == '1');
+}
+static bool pointwise_shape(const nas3d_conv_desc* d) {
+  return tiled_enabled() && d->k == 1 && !d->depthwise && d->pad == 0;
+}
+// 1: stride-1 (dil 1|2) ; 2: stride-2 dilation-2 (= stride-1 dil-1 on the even sub-lattice of big)
+static int tiled_kind(const nas3d_conv_desc* d, bool wgrad = false) {
+  if (!tiled_enabled() || d->k != 3 || d->depthwise || d->Cb != d->Cs) return 0;
+  if (wgrad) {
+    if (d->Cb % 4 || d->Cb > 64) return 0;
+  } else if (!(d->Cb == 4 || d->Cb == 8 || d->Cb == 16)) {
+    return 0;
+  }
+  if (d->stride == 1 && d->pad == d->dil && (d->dil == 1 || d->dil == 2)) return 1;
+  if (d->stride == 2 && d->dil == 2 && d->pad == 2 && d->Db == 2 * d->Ds && d->Hb == 2 * d->Hs &&
+      d->Wb == 2 * d->Ws)
+    return 2;
+  return 0;
+}
+static void tiled_fill(const nas3d_conv_desc* d, int kind, bool x_is_big, TiledArgs* T) {
+  T->N = d->N; T->D = d->Ds; T->H = d->Hs; T->W = d->Ws;
+  const int bs = kind == 2 ? 2 : 1;
+  if (x_is_big) {
+    T->xs = bs; T->Dx = d->Db; T->Hx = d->Hb; T->Wx = d->Wb; T->ldx = d->ld_big;
+    T->ys = 1;  T->Dy = d->Ds; T->Hy = d->Hs; T->Wy = d->Ws; T->ldy = d->ld_small;
+  } else {
+    T->xs = 1;  T->Dx = d->Ds; T->Hx = d->Hs; T->Wx = d->Ws; T->ldx = d->ld_small;
+    T->ys = bs; T->Dy = d->Db; T->Hy = d->Hb; T->Wy = d->Wb; T->ldy = d->ld_big;
+  }
+  T->tiles_w = T->tiles_h = T->tiles_d = 0;
+}
 
 struct ConvArgs {
   const float* src;
@@ -484,6 +531,18 @@ int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const 
   if (rc) return rc;
   A.src = big; A.w = w; A.bias = bias; A.scale = big_scale; A.relu = big_relu;
   A.sigmoid = out_sigmoid; A.dst = small; A.accumulate = accumulate;
+  if (pointwise_shape(d)) {
+    rc = pointwise_sfb(d, big, w, bias, big_scale, big_relu, out_sigmoid, small, accumulate,
+                       (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
+  if (const int kind = tiled_kind(d); kind && !big_scale && !big_relu && !out_sigmoid) {
+    TiledArgs T{};
+    tiled_fill(d, kind, true, &T);
+    T.x = big; T.w = w; T.bias = bias; T.y = small; T.accumulate = accumulate;
+    rc = tiled_conv3_s1(d->Cb, kind == 2 ? 1 : d->dil, false, T, (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   return launch_gather<false>(A, d->depthwise != 0, (cudaStream_t)stream);
 }
 
@@ -495,6 +554,31 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
   if (rc) return rc;
   A.src = small; A.w = w; A.bias = bias; A.mask = mask_big; A.ld_mask = ld_mask;
   A.scale = big_scale; A.dst = big; A.accumulate = accumulate;
+  if (pointwise_shape(d)) {
+    rc = pointwise_bfs(d, small, w, bias, mask_big, ld_mask, big_scale, big, accumulate,
+                       (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
+  if (const int kind = tiled_kind(d);
+      kind && !big_scale && !mask_big && (kind == 1 || accumulate || d->ld_big == d->Cb) &&
+      d->Ws >= 8 && d->ld_small % 4 == 0 && d->ld_big % 4 == 0 && aligned16(small) && aligned16(big)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == 2 && !accumulate) {
+      // voxels off the even lattice receive no tap: they are bias (transposed fwd) or 0 (dgrad)
+      const long long nvb = (long long)d->N * d->Db * d->Hb * d->Wb;
+      if (bias) {
+        rc = fill_channels(big, bias, nvb, d->Cb, d->ld_big, st);
+        if (rc) return rc;
+      } else {
+        NAS3D_CUDA(cudaMemsetAsync(big, 0, sizeof(float) * (size_t)nvb * d->Cb, st));
+      }
+    }
+    TiledArgs T{};
+    tiled_fill(d, kind, false, &T);
+    T.x = small; T.w = w; T.bias = bias; T.y = big; T.accumulate = accumulate;
+    rc = tiled_conv3_s1(d->Cb, kind == 2 ? 1 : d->dil, true, T, st);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   return launch_gather<true>(A, d->depthwise != 0, (cudaStream_t)stream);
 }
 
@@ -508,7 +592,26 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   const int T = A.k * A.k * A.k;
   const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
-  if (d->depthwise) {
+  bool done = false;
+  if (pointwise_shape(d)) {
+    rc = pointwise_wgrad(d, small, big, big_scale, big_relu, dW, d_bias_small, st);
+    if (rc == NAS3D_OK) done = true;
+    else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    rc = NAS3D_OK;
+  }
+  if (const int kind = tiled_kind(d, true); !done && kind && !big_scale && !big_relu) {
+    WgradArgs T{};
+    T.x = big; T.dy = small; T.dW = dW; T.dbias = d_bias_small;
+    T.N = d->N; T.D = d->Ds; T.H = d->Hs; T.W = d->Ws; T.ldx = d->ld_big; T.ldy = d->ld_small;
+    T.xs = kind == 2 ? 2 : 1; T.Dx = d->Db; T.Hx = d->Hb; T.Wx = d->Wb;
+    T.ys = 1; T.Dy = d->Ds; T.Hy = d->Hs; T.Wy = d->Ws;
+    rc = tiled_wgrad3_s1(d->Cb, kind == 2 ? 1 : d->dil, T, st);
+    if (rc == NAS3D_OK) done = true;
+    else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    rc = NAS3D_OK;
+  }
+  if (done) {
+  } else if (d->depthwise) {
     const int C4 = A.Cb / 4;
     NAS3D_REQUIRE(A.Cb % 4 == 0 && WG_T % C4 == 0 && A.lds % 4 == 0 && A.ldb % 4 == 0,
                   "depthwise wgrad: C=%d unsupported", A.Cb);

@@ -1,0 +1,418 @@
+// Tiled direct 3x3x3 stride-1 convolution (dilation 1 or 2, Cin == Cout == C in {4,8,16}) on
+// NDHWC fp32: the shapes that carry ~70 % of the network's FLOPs and bytes (C=4 @128^3,
+// C=8 @64^3).
+//
+// Why CUDA-core FFMA and not tcgen05 here: with N = Cout = 4..8 a UMMA tile re-reads its A
+// operand (128 voxels x K) from shared memory for 4..8 output columns only, so the tensor pipe
+// is bounded by the smem operand bandwidth at ~1/8 of its peak, and 3xTF32 (needed for the
+// 1e-3 gradient tolerance) divides that by 3 again - below what exact-fp32 FFMA delivers.
+// (conv_umma.cu holds the tcgen05 path for the wide layers.)  See DESIGN.md "Kernels".
+//
+// One CTA = one output tile TD x TH x 32 voxels.  The input tile + halo is staged ONCE in
+// shared memory (cp.async, zero-filled outside the volume = the conv's zero padding) in
+// channel-chunk planes [C/4][PD][PH][PW] of float4 so that a warp's 32 lanes (consecutive w)
+// read 512 contiguous bytes.  A thread owns MD x 4 (d x h) output voxels x 4 output channels:
+// for every (kd,kw,cin-chunk) it loads the 3x4x4 weights once (broadcast LDS) and a column of
+// 4+2*DIL input float4 per d, and issues 48 FFMA per loaded float4.
+//
+//   forward : out[o,co]  = bias[co] + sum_{tap,ci} x[o - pad + tap*dil, ci] * W[co][ci][tap]
+//   dgrad   : dx[i,ci]   =           sum_{tap,co} dy[i - pad + (2-tap)*dil, co] * W[co][ci][tap]
+// (same kernel: FLIP re-indexes the weights while they are staged).
+//
+//   wgrad   : dW[co][ci][tap] += sum_o dy[o,co] * x[o - pad + tap*dil, ci]
+// lanes <-> taps: lane t < 27 owns the 4x4 (ci,co) block of tap t for the warp's voxels, so no
+// cross-lane reduction is needed until the end; lane 27 accumulates the bias gradient.
+#include "common.cuh"
+#include "conv_tiled.h"
+
+namespace nas3d {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int C, int DIL, int HG, int DG, int MD>
+struct TileShape {
+  static constexpr int C4 = C / 4;
+  static constexpr int TW = 32, TH = 4 * HG, TD = MD * DG;
+  static constexpr int PW = TW + 2 * DIL, PH = TH + 2 * DIL, PD = TD + 2 * DIL;
+  static constexpr int NR = 4 + 2 * DIL;
+  static constexpr int THREADS = 32 * HG * DG * C4;
+  static constexpr int PLANE = PD * PH * PW;                   // float4 per channel chunk
+  static constexpr size_t SMEM = sizeof(float4) * PLANE * C4 + sizeof(float) * 27 * C * C;
+};
+
+template <int C, int DIL, int HG, int DG, int MD, bool FLIP>
+__global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
+    conv3_s1_kernel(const TiledArgs A) {
+  using TS = TileShape<C, DIL, HG, DG, MD>;
+  constexpr int C4 = TS::C4, PW = TS::PW, PH = TS::PH, PD = TS::PD, NR = TS::NR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tile = reinterpret_cast<float4*>(smem_raw);
+  float* wsm = reinterpret_cast<float*>(smem_raw + sizeof(float4) * TS::PLANE * C4);
+
+  int b = blockIdx.x;
+  const int tw = b % A.tiles_w; b /= A.tiles_w;
+  const int th = b % A.tiles_h; b /= A.tiles_h;
+  const int td = b % A.tiles_d;
+  const int n = b / A.tiles_d;
+  const int w0 = tw * TS::TW, h0 = th * TS::TH, d0 = td * TS::TD;
+
+  // ---- stage weights: wsm[tap][ci][co] ------------------------------------------------
+  for (int i = threadIdx.x; i < 27 * C * C; i += TS::THREADS) {
+    const int co = i % C, ci = (i / C) % C, tap = i / (C * C);
+    // fwd : reduce over ci, produce co, tap as is
+    // flip: reduce over (W's dim0), produce (W's dim1), tap mirrored
+    const int gi = FLIP ? (ci * C + co) * 27 + (26 - tap) : (co * C + ci) * 27 + tap;
+    wsm[i] = __ldg(A.w + gi);
+  }
+  // ---- stage the input tile + halo ------------------------------------------------------
+  const float* xb = A.x + (long long)n * A.Dx * A.Hx * A.Wx * A.ldx;
+  for (int i = threadIdx.x; i < TS::PLANE * C4; i += TS::THREADS) {
+    const int cc = i % C4;
+    int r = i / C4;
+    const int pw = r % PW; r /= PW;
+    const int ph = r % PH;
+    const int pd = r / PH;
+    const int gd = d0 - DIL + pd, gh = h0 - DIL + ph, gw = w0 - DIL + pw;
+    const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
+    const float* src =
+        ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx + cc * 4 : A.x;
+    cp_async16(&tile[cc * TS::PLANE + (pd * PH + ph) * PW + pw], src, ok);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- compute ----------------------------------------------------------------------------
+  const int tx = threadIdx.x & 31;
+  int ty = threadIdx.x >> 5;
+  const int cg = ty % C4; ty /= C4;       // output-channel group (4 channels)
+  const int hg = ty % HG;
+  const int dg = ty / HG;
+
+  float acc[MD][4][4];
+#pragma unroll
+  for (int a = 0; a < MD; ++a)
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][h][c] = 0.f;
+
+#pragma unroll 1
+  for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll 1
+    for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll 1
+      for (int cc = 0; cc < C4; ++cc) {
+        // weights of taps (kd, 0..2, kw), input channels cc*4..+3, my 4 output channels
+        float4 wr[3][4];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci)
+            wr[kh][ci] = *reinterpret_cast<const float4*>(
+                wsm + (((kd * 3 + kh) * 3 + kw) * C + cc * 4 + ci) * C + cg * 4);
+#pragma unroll
+        for (int od = 0; od < MD; ++od) {
+          const float4* col = tile + cc * TS::PLANE +
+                              ((dg * MD + od + kd * DIL) * PH + hg * 4) * PW + tx + kw * DIL;
+          float4 xin[NR];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) xin[r] = col[r * PW];
+#pragma unroll
+          for (int oh = 0; oh < 4; ++oh)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const float4 xv = xin[oh + kh * DIL];
+              acc[od][oh][0] += xv.x * wr[kh][0].x; acc[od][oh][1] += xv.x * wr[kh][0].y;
+              acc[od][oh][2] += xv.x * wr[kh][0].z; acc[od][oh][3] += xv.x * wr[kh][0].w;
+              acc[od][oh][0] += xv.y * wr[kh][1].x; acc[od][oh][1] += xv.y * wr[kh][1].y;
+              acc[od][oh][2] += xv.y * wr[kh][1].z; acc[od][oh][3] += xv.y * wr[kh][1].w;
+              acc[od][oh][0] += xv.z * wr[kh][2].x; acc[od][oh][1] += xv.z * wr[kh][2].y;
+              acc[od][oh][2] += xv.z * wr[kh][2].z; acc[od][oh][3] += xv.z * wr[kh][2].w;
+              acc[od][oh][0] += xv.w * wr[kh][3].x; acc[od][oh][1] += xv.w * wr[kh][3].y;
+              acc[od][oh][2] += xv.w * wr[kh][3].z; acc[od][oh][3] += xv.w * wr[kh][3].w;
+            }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (A.bias) bias4 = ldg4(A.bias + cg * 4);
+  const int gw = w0 + tx;
+  if (gw >= A.W) return;
+  float* yb = A.y + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + cg * 4;
+#pragma unroll
+  for (int od = 0; od < MD; ++od) {
+    const int gd = d0 + dg * MD + od;
+    if (gd >= A.D) break;
+#pragma unroll
+    for (int oh = 0; oh < 4; ++oh) {
+      const int gh = h0 + hg * 4 + oh;
+      if (gh >= A.H) break;
+      float* p = yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy;
+      float4 v = make_float4(acc[od][oh][0] + bias4.x, acc[od][oh][1] + bias4.y,
+                             acc[od][oh][2] + bias4.z, acc[od][oh][3] + bias4.w);
+      if (A.accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(p);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      st4(p, v);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// wgrad:  dW[co][ci][tap] += sum_o dy[o,co] * x[o - DIL + tap*DIL, ci]   (lattice coordinates)
+//
+// The CTA stages the x tile (+halo) and the dy tile in shared memory.  Inside a warp, lane
+// l < 27 is (kdkh = l / 3, j = l % 3): it owns the three taps (kd, kh, kw = 0..2) for tile row
+// (3*i + j) and WALKS ALONG W with a sliding window of 2*DIL+1 x-values, so each step costs one
+// new 128-bit x load + one dy load for 3 taps x 16 = 48 FFMA.  All partial sums stay in the
+// lane's registers until the end of the tile (no cross-lane reduction in the hot loop).
+// Lanes 27..29 ride along and accumulate the bias gradient (sum of dy) of rows j = 0..2.
+// For C > 4 the (ci-chunk, co-chunk) pairs are looped over the same staged tile.
+// -----------------------------------------------------------------------------------------
+template <int DIL, int TH, int TD, int NWARP>
+struct WgShape {
+  static constexpr int TW = 32;
+  static constexpr int PW = TW + 2 * DIL, PH = TH + 2 * DIL, PD = TD + 2 * DIL;
+  static constexpr int PWP = PW | 1;                  // odd row pitch: spreads the 27 lanes' rows over banks
+  static constexpr int XPLANE = PD * PH * PWP;
+  static constexpr int YPLANE = TD * TH * TW;
+  static constexpr int THREADS = 32 * NWARP;
+  static constexpr int WN = 2 * DIL + 1;              // sliding window length
+  static constexpr int ROWS = TD * TH;
+  static constexpr int NIT = (ROWS + 3 * NWARP - 1) / (3 * NWARP);
+  static constexpr size_t SMEM = sizeof(float4) * (XPLANE + YPLANE) + sizeof(float) * (27 * 16 + 4);
+};
+
+// PERSISTENT: blockIdx.x strides over the tiles, blockIdx.y = (ci-chunk, co-chunk) pair; the
+// 48 partial sums of a lane live in registers across all tiles of the CTA and are flushed once.
+template <int DIL, int TH, int TD, int NWARP>
+__global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP>::THREADS)
+    wgrad3_s1_kernel(const WgradArgs A, int C, int ntiles) {
+  using WS = WgShape<DIL, TH, TD, NWARP>;
+  constexpr int PW = WS::PW, PWP = WS::PWP, PH = WS::PH, TW = WS::TW, WN = WS::WN;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* xt = reinterpret_cast<float4*>(smem_raw);
+  float4* yt = xt + WS::XPLANE;
+  float* red = reinterpret_cast<float*>(yt + WS::YPLANE);   // [27][4][4] + [4]
+
+  const int C4 = C / 4;
+  const int cic = blockIdx.y / C4, coc = blockIdx.y % C4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tap_lane = lane < 27;
+  const int kdkh = tap_lane ? lane / 3 : 0;
+  const int j = lane < 30 ? lane % 3 : 0;
+  const bool active = lane < 30;
+  const int kd = kdkh / 3, kh = kdkh % 3;
+
+  float acc[3][4][4];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[t][a][c] = 0.f;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int i = threadIdx.x; i < 27 * 16 + 4; i += WS::THREADS) red[i] = 0.f;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int b = tile;
+    const int tw = b % A.tiles_w; b /= A.tiles_w;
+    const int th = b % A.tiles_h; b /= A.tiles_h;
+    const int td = b % A.tiles_d;
+    const int n = b / A.tiles_d;
+    const int w0 = tw * TW, h0 = th * TH, d0 = td * TD;
+    __syncthreads();     // previous tile fully consumed
+    const float* xb = A.x + (long long)n * A.Dx * A.Hx * A.Wx * A.ldx + cic * 4;
+    for (int i = threadIdx.x; i < WS::PD * PH * PW; i += WS::THREADS) {
+      int r = i;
+      const int pw = r % PW; r /= PW;
+      const int ph = r % PH;
+      const int pd = r / PH;
+      const int gd = d0 - DIL + pd, gh = h0 - DIL + ph, gw = w0 - DIL + pw;
+      const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
+      const float* src =
+          ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx : A.x;
+      cp_async16(&xt[(pd * PH + ph) * PWP + pw], src, ok);
+    }
+    const float* yb = A.dy + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + coc * 4;
+    for (int i = threadIdx.x; i < WS::YPLANE; i += WS::THREADS) {
+      int r = i;
+      const int pw = r % TW; r /= TW;
+      const int ph = r % TH;
+      const int pd = r / TH;
+      const int gd = d0 + pd, gh = h0 + ph, gw = w0 + pw;
+      const bool ok = gd < A.D && gh < A.H && gw < A.W;   // outside: dy = 0 contributes nothing
+      const float* src =
+          ok ? yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy : A.dy;
+      cp_async16(&yt[(pd * TH + ph) * TW + pw], src, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+#pragma unroll 1
+    for (int it = 0; it < WS::NIT; ++it) {
+      const int row = (it * 3 + j) * NWARP + warp;
+      if (row >= WS::ROWS || !active) continue;   // lane-group granular; rows are independent
+      const int pd = row / TH, ph = row % TH;
+      const float4* xr = xt + ((pd + kd * DIL) * PH + ph + kh * DIL) * PWP;
+      const float4* yr = yt + (pd * TH + ph) * TW;
+      float4 win[WN];
+#pragma unroll
+      for (int q = 0; q < WN - 1; ++q) win[q + 1] = xr[q];
+      float4 xn = xr[WN - 1];
+      float4 gn = yr[0];
+#pragma unroll 2
+      for (int wb = 0; wb < TW; wb += WN) {
+#pragma unroll
+        for (int u = 0; u < WN; ++u) {
+          const int w = wb + u;
+          if (w < TW) {
+#pragma unroll
+            for (int q = 0; q < WN - 1; ++q) win[q] = win[q + 1];
+            win[WN - 1] = xn;
+            const float4 g = gn;
+            if (w + 1 < TW) {          // prefetch the next step's operands
+              xn = xr[w + WN];
+              gn = yr[w + 1];
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float4 xv = win[kw * DIL];
+              acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
+              acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
+              acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
+              acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
+            }
+            bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+          }
+        }
+      }
+    }
+  }
+
+  // flush once per CTA
+  if (tap_lane) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], acc[kw][a][c]);
+  } else if (active) {
+    atomicAdd(&red[27 * 16 + 0], bsum.x); atomicAdd(&red[27 * 16 + 1], bsum.y);
+    atomicAdd(&red[27 * 16 + 2], bsum.z); atomicAdd(&red[27 * 16 + 3], bsum.w);
+  }
+  __syncthreads();
+  // red[tap][ci][co] -> dW[co][ci][tap]
+  for (int i = threadIdx.x; i < 27 * 16; i += WS::THREADS) {
+    const int co = coc * 4 + i % 4, ci = cic * 4 + (i / 4) % 4, t = i / 16;
+    atomicAdd(A.dW + (co * C + ci) * 27 + t, red[i]);
+  }
+  if (A.dbias && cic == 0 && threadIdx.x < 4) atomicAdd(A.dbias + coc * 4 + threadIdx.x, red[27 * 16 + threadIdx.x]);
+}
+
+template <int C, int DIL, int HG, int DG, int MD, bool FLIP>
+static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
+  using TS = TileShape<C, DIL, HG, DG, MD>;
+  TiledArgs A = A0;
+  A.tiles_w = (A.W + TS::TW - 1) / TS::TW;
+  A.tiles_h = (A.H + TS::TH - 1) / TS::TH;
+  A.tiles_d = (A.D + TS::TD - 1) / TS::TD;
+  auto kern = conv3_s1_kernel<C, DIL, HG, DG, MD, FLIP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM));
+    attr_done = true;
+  }
+  const long long blocks = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
+  kern<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A);
+  return launched("conv3_s1");
+}
+
+template <int DIL, int TH, int TD, int NWARP>
+static int launch_wgrad3(const WgradArgs& A0, int C, cudaStream_t st) {
+  using WS = WgShape<DIL, TH, TD, NWARP>;
+  WgradArgs A = A0;
+  A.tiles_w = (A.W + WS::TW - 1) / WS::TW;
+  A.tiles_h = (A.H + TH - 1) / TH;
+  A.tiles_d = (A.D + TD - 1) / TD;
+  auto kern = wgrad3_s1_kernel<DIL, TH, TD, NWARP>;
+  static int occ = 0;
+  if (!occ) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
+    NAS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WS::THREADS, WS::SMEM));
+    if (occ < 1) occ = 1;
+  }
+  const long long ntiles = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
+  const int pairs = (C / 4) * (C / 4);
+  long long gx = (long long)kNumSMs * occ / pairs;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  kern<<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, C, (int)ntiles);
+  return launched("wgrad3_s1");
+}
+
+__global__ void __launch_bounds__(256)
+    fill_channels_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total,
+                         int C4, int ld) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / C4;
+    const int c = (int)(i - v * C4) * 4;
+    st4(y + v * ld + c, ldg4(bias + c));
+  }
+}
+
+int fill_channels(float* y, const float* bias, long long nvox, int C, int ld, cudaStream_t st) {
+  NAS3D_REQUIRE(C % 4 == 0 && ld % 4 == 0 && aligned16(y) && aligned16(bias), "fill_channels: alignment");
+  const long long total = nvox * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  fill_channels_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, bias, total, C / 4, ld);
+  return launched("fill_channels");
+}
+
+// returns NAS3D_ERR_UNSUPPORTED (without setting an error) when the shape is not covered
+int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st) {
+  if (A.W < 8 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.y)) return NAS3D_ERR_UNSUPPORTED;
+#define NAS3D_CASE(CC, DD, HG, DG, MD)                                          \
+  if (C == CC && dil == DD)                                                      \
+    return flip ? launch_conv3<CC, DD, HG, DG, MD, true>(A, st)                  \
+                : launch_conv3<CC, DD, HG, DG, MD, false>(A, st);
+  NAS3D_CASE(4, 1, 4, 2, 2)
+  NAS3D_CASE(4, 2, 4, 2, 2)
+  NAS3D_CASE(8, 1, 2, 2, 2)
+  NAS3D_CASE(8, 2, 2, 2, 2)
+  NAS3D_CASE(16, 1, 2, 1, 2)
+  NAS3D_CASE(16, 2, 2, 1, 2)
+#undef NAS3D_CASE
+  return NAS3D_ERR_UNSUPPORTED;
+}
+
+int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st) {
+  if (A.W < 8 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.dy)) return NAS3D_ERR_UNSUPPORTED;
+  if (C % 4 || C > 64) return NAS3D_ERR_UNSUPPORTED;
+  if (A.H >= 12) {
+    if (dil == 1) return launch_wgrad3<1, 12, 4, 8>(A, C, st);
+    if (dil == 2) return launch_wgrad3<2, 12, 4, 8>(A, C, st);
+  } else {
+    if (dil == 1) return launch_wgrad3<1, 6, 4, 8>(A, C, st);
+    if (dil == 2) return launch_wgrad3<2, 6, 4, 8>(A, C, st);
+  }
+  return NAS3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace nas3d

@@ -1,0 +1,43 @@
+// argument blocks of the tiled 3x3x3 kernels (conv_tiled.cu), shared with conv_direct.cu
+#pragma once
+#include <cuda_runtime.h>
+
+namespace nas3d {
+
+// The kernels work on a LATTICE of D x H x W points.  Tensor x holds lattice point (d,h,w) at
+// voxel (d*xs, h*xs, w*xs) of a (Dx,Hx,Wx) volume, tensor y at (d*ys,...) of (Dy,Hy,Wy):
+// xs = ys = 1 is the plain stride-1 conv; a stride-2 dilation-2 conv touches only the even
+// voxels of its big tensor, i.e. it IS a stride-1 dilation-1 conv between the
+// small tensor and the even sub-lattice of the big one (xs or ys = 2).
+struct TiledArgs {
+  const float* x;      // input (fwd: x, dgrad: dy)
+  const float* w;      // W[C][C][27]
+  const float* bias;   // fwd only
+  float* y;            // output (fwd: y, dgrad: dx)
+  int N, D, H, W;      // lattice extents
+  int ldx, ldy;
+  int accumulate;
+  int xs, Dx, Hx, Wx;
+  int ys, Dy, Hy, Wy;
+  int tiles_w, tiles_h, tiles_d;
+};
+
+struct WgradArgs {
+  const float* x;
+  const float* dy;
+  float* dW;
+  float* dbias;
+  int N, D, H, W;      // lattice extents (= extents of the dy side)
+  int ldx, ldy;
+  int xs, Dx, Hx, Wx;  // x lives on a lattice of stride xs inside a (Dx,Hx,Wx) volume
+  int ys, Dy, Hy, Wy;
+  int tiles_w, tiles_h, tiles_d;
+};
+
+
+// return NAS3D_ERR_UNSUPPORTED (without error text) when the shape is not covered
+int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st);
+int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st);
+int fill_channels(float* y, const float* bias, long long nvox, int C, int ld, cudaStream_t st);
+
+}  // namespace nas3d
