@@ -184,14 +184,22 @@ template <int DIL, int TH, int TD, int NWARP>
 struct WgShape {
   static constexpr int TW = 32;
   static constexpr int PW = TW + 2 * DIL, PH = TH + 2 * DIL, PD = TD + 2 * DIL;
-  static constexpr int PWP = PW | 1;                  // odd row pitch: spreads the 27 lanes' rows over banks
-  static constexpr int XPLANE = PD * PH * PWP;
-  static constexpr int YPLANE = TD * TH * TW;
+  // Row / plane / dy-row pitches (in float4) found by exhaustive search so that every 8-lane
+  // phase of the two LDS.128 per step hits 8 distinct 16-byte bank groups (8 wavefronts per
+  // step = the minimum; the naive layout needs 26).
+  static constexpr int PWP = PW | 1;
+  static constexpr int PLANE_PAD = DIL == 1 ? (TH == 12 ? 5 : 7) : (TH == 12 ? 0 : 2);
+  static constexpr int XPLANE = PH * PWP + PLANE_PAD;       // pitch of one d-plane
+  static constexpr int XTILE = PD * XPLANE + 8;
+  static constexpr int YP = TW + 1;                          // dy row pitch
+  static constexpr int YTILE = TD * TH * YP + 8;
   static constexpr int THREADS = 32 * NWARP;
   static constexpr int WN = 2 * DIL + 1;              // sliding window length
   static constexpr int ROWS = TD * TH;
-  static constexpr int NIT = (ROWS + 3 * NWARP - 1) / (3 * NWARP);
-  static constexpr size_t SMEM = sizeof(float4) * (XPLANE + YPLANE) + sizeof(float) * (27 * 16 + 4);
+  static constexpr int NGROUPS = ROWS / 3;            // 3 adjacent rows per warp step
+  static_assert(ROWS % 3 == 0 && NGROUPS % NWARP == 0, "tile rows must split into 3-row groups per warp");
+  static_assert(TH == 12 || TH == 6, "bank-conflict-free pitches are tabulated for TH = 12 / 6");
+  static constexpr size_t SMEM = sizeof(float4) * (XTILE + YTILE) + sizeof(float) * (27 * 16 + 4);
 };
 
 // PERSISTENT: blockIdx.x strides over the tiles, blockIdx.y = (ci-chunk, co-chunk) pair; the
@@ -203,8 +211,8 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP>::THREADS)
   constexpr int PW = WS::PW, PWP = WS::PWP, PH = WS::PH, TW = WS::TW, WN = WS::WN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* xt = reinterpret_cast<float4*>(smem_raw);
-  float4* yt = xt + WS::XPLANE;
-  float* red = reinterpret_cast<float*>(yt + WS::YPLANE);   // [27][4][4] + [4]
+  float4* yt = xt + WS::XTILE;
+  float* red = reinterpret_cast<float*>(yt + WS::YTILE);   // [27][4][4] + [4]
 
   const int C4 = C / 4;
   const int cic = blockIdx.y / C4, coc = blockIdx.y % C4;
@@ -245,10 +253,10 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP>::THREADS)
       const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
       const float* src =
           ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx : A.x;
-      cp_async16(&xt[(pd * PH + ph) * PWP + pw], src, ok);
+      cp_async16(&xt[pd * WS::XPLANE + ph * PWP + pw], src, ok);
     }
     const float* yb = A.dy + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + coc * 4;
-    for (int i = threadIdx.x; i < WS::YPLANE; i += WS::THREADS) {
+    for (int i = threadIdx.x; i < TD * TH * TW; i += WS::THREADS) {
       int r = i;
       const int pw = r % TW; r /= TW;
       const int ph = r % TH;
@@ -257,47 +265,59 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP>::THREADS)
       const bool ok = gd < A.D && gh < A.H && gw < A.W;   // outside: dy = 0 contributes nothing
       const float* src =
           ok ? yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy : A.dy;
-      cp_async16(&yt[(pd * TH + ph) * TW + pw], src, ok);
+      cp_async16(&yt[(pd * TH + ph) * WS::YP + pw], src, ok);
     }
     cp_async_wait_all();
     __syncthreads();
 
 #pragma unroll 1
-    for (int it = 0; it < WS::NIT; ++it) {
-      const int row = (it * 3 + j) * NWARP + warp;
-      if (row >= WS::ROWS || !active) continue;   // lane-group granular; rows are independent
+    for (int grp = warp; grp < WS::NGROUPS; grp += NWARP) {
+      if (!active) continue;
+      const int row = grp * 3 + j;
       const int pd = row / TH, ph = row % TH;
-      const float4* xr = xt + ((pd + kd * DIL) * PH + ph + kh * DIL) * PWP;
-      const float4* yr = yt + (pd * TH + ph) * TW;
+      const float4* xr = xt + (pd + kd * DIL) * WS::XPLANE + (ph + kh * DIL) * PWP;
+      const float4* yr = yt + (pd * TH + ph) * WS::YP;
+      // circular window: slot q holds xr[wb + q] at the top of every WN-step block
       float4 win[WN];
 #pragma unroll
-      for (int q = 0; q < WN - 1; ++q) win[q + 1] = xr[q];
-      float4 xn = xr[WN - 1];
-      float4 gn = yr[0];
+      for (int q = 0; q < WN - 1; ++q) win[q] = xr[q];
+      constexpr int NFULL = TW / WN;
 #pragma unroll 2
-      for (int wb = 0; wb < TW; wb += WN) {
+      for (int blk = 0; blk < NFULL; ++blk) {
+        const float4* xq = xr + blk * WN;
+        const float4* yq = yr + blk * WN;
 #pragma unroll
         for (int u = 0; u < WN; ++u) {
-          const int w = wb + u;
-          if (w < TW) {
+          win[(u + WN - 1) % WN] = xq[u + WN - 1];
+          const float4 g = yq[u];
 #pragma unroll
-            for (int q = 0; q < WN - 1; ++q) win[q] = win[q + 1];
-            win[WN - 1] = xn;
-            const float4 g = gn;
-            if (w + 1 < TW) {          // prefetch the next step's operands
-              xn = xr[w + WN];
-              gn = yr[w + 1];
-            }
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const float4 xv = win[kw * DIL];
-              acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
-              acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
-              acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
-              acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
-            }
-            bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 xv = win[(u + kw * DIL) % WN];
+            acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
+            acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
+            acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
+            acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
           }
+          bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+        }
+      }
+      // tail: TW % WN steps
+      {
+        const float4* xq = xr + NFULL * WN;
+        const float4* yq = yr + NFULL * WN;
+#pragma unroll
+        for (int u = 0; u < TW % WN; ++u) {
+          win[(u + WN - 1) % WN] = xq[u + WN - 1];
+          const float4 g = yq[u];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 xv = win[(u + kw * DIL) % WN];
+            acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
+            acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
+            acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
+            acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
+          }
+          bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
         }
       }
     }
