@@ -94,6 +94,24 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
                      float* d_bias_big, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05.mma kind::tf32, fp32 accumulators in TMEM, 3xTF32 error
+ * compensation => fp32-grade results) for dense 3x3x3 convolutions with Cb == Cs in {16,32,64},
+ * any stride / dilation, both gather directions (same conv view as above).
+ *   nas3d_umma_packed_floats : size (floats) of the packed [W_hi | W_lo] operand, 0 = shape not
+ *                              covered (the caller then uses the entry points above)
+ *   nas3d_umma_pack_weights  : W[Cs][Cb][27] -> packed K-major core-matrix layout; produce_big
+ *                              selects which channel dim is reduced (0: Cb, 1: Cs)
+ *   nas3d_umma_conv          : produce_big = 0: small = bias + conv(big)   (Conv3d fwd, ConvT dgrad)
+ *                              produce_big = 1: big (+)= bias + convT(small) (ConvT fwd, Conv3d dgrad)
+ * ------------------------------------------------------------------------------------- */
+long long nas3d_umma_packed_floats(const nas3d_conv_desc* d, int produce_big);
+int nas3d_umma_pack_weights(const nas3d_conv_desc* d, const float* w, int produce_big,
+                            float* packed, void* stream);
+int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
+                    const float* packed_w, const float* bias, float* dst, int accumulate,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-(n,c) moments: S[n][c] = {sum x, sum x^2} in fp64 (zeroed inside the call).
  * Serves GroupNorm statistics (prim_ops.py:56-58,77) and the SE squeeze
  * (AdaptiveAvgPool3d, prim_ops.py:133,150).

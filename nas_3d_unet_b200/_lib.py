@@ -38,6 +38,9 @@ _SIGNATURES = {
     "nas3d_conv_big_from_small": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
                                   c_int, c_vp],
     "nas3d_conv_wgrad": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_umma_packed_floats": [C.POINTER(ConvDesc), c_int],
+    "nas3d_umma_pack_weights": [C.POINTER(ConvDesc), c_vp, c_int, c_vp, c_vp],
+    "nas3d_umma_conv": [C.POINTER(ConvDesc), c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
     "nas3d_moments_nc": [c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp],
     "nas3d_gn_coef": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, C.c_float, c_vp, c_vp, c_vp, c_vp],
     "nas3d_se_excite": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp],
@@ -65,6 +68,7 @@ _SIGNATURES = {
 _RESTYPES = {
     "nas3d_last_error": C.c_char_p,
     "nas3d_launch_count": C.c_ulonglong,
+    "nas3d_umma_packed_floats": C.c_longlong,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,377 @@
+// tcgen05 / TMEM implicit-GEMM 3x3x3 convolution for the WIDE layers (C = 16, 32, 64), any
+// stride / dilation, plain and transposed, forward and dgrad:
+//
+//     D[128 voxels][N = Cprod]  =  sum over k = (tap, cred)   A[voxel][k] * W[k][n]
+//
+// * A is never materialised in HBM: the CTA's 128 threads gather their voxel's row for the
+//   taps of one K-stage straight from the NDHWC activation (zero rows where the tap falls into
+//   the padding or, for transposed convs, off the stride lattice) and write it to shared memory
+//   in the canonical K-major SWIZZLE_NONE core-matrix layout ([m/8][k/4][m%8][16 B]).
+// * fp32-grade accuracy on the TF32 pipe (1xTF32 misses the 1e-3 gradient
+//   tolerance): 3xTF32 error compensation.  x = hi + lo with hi = top 19 bits; the weights are
+//   pre-split and packed as B' = [W_hi | W_lo] along N, so per 8-wide K step the issuing thread
+//   launches   D[:, 0:2N] += A_hi * B'      (one read of A_hi feeds hi*hi and hi*lo)
+//              D[:, 0:N ] += A_lo * W_hi
+//   and the epilogue adds the two N-column halves.  fp32 accumulation in TMEM.
+// * one elected thread issues tcgen05.mma (cta_group::1, kind::tf32, M=128), completion is
+//   tracked with tcgen05.commit -> mbarrier, two smem stages so the gather of stage i+1 overlaps
+//   the MMAs of stage i; the epilogue reads TMEM with tcgen05.ld (32 lanes x 8 columns).
+#include "common.cuh"
+
+namespace nas3d {
+
+struct UmmaArgs {
+  const float* src;
+  const float* wp;     // packed weights (umma_pack_kernel)
+  const float* bias;
+  float* dst;
+  int N;
+  int Dd, Hd, Wd, ldd;     // produced tensor
+  int Dr, Hr, Wr, ldr;     // reduced (gathered) tensor
+  int k, stride, dil, pad;
+  int bfs;                 // 0: src = big (pos = o*s - p + t*d) ; 1: src = small (pos = (o + p - t*d)/s)
+  int accumulate;
+  long long nvox;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  // SmemDescriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+  // | layout_type = SWIZZLE_NONE (0) [61,64)
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
+  // InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2) [10,13)
+  // | a,b K-major (0) | n>>3 [17,23) | m>>4 [24,29)  with M = 128
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int CRED, int NPROD>
+struct UmmaShape {
+  static constexpr int KS = CRED == 16 ? 32 : CRED;      // K floats per smem stage
+  static constexpr int TPS = KS / CRED;                  // taps per stage
+  static constexpr int NIT = (27 + TPS - 1) / TPS;       // stages per tile
+  static constexpr int KCH = KS / 4;                     // 16-byte chunks per row per stage
+  static constexpr int A_BYTES = 128 * KS * 4;
+  static constexpr int B_BYTES = 2 * NPROD * KS * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * NPROD < 32 ? 32 : 2 * NPROD;   // 32 / 64 / 128
+  static constexpr size_t SMEM = 2 * STAGE_BYTES + 64;
+  static constexpr int PACKED_FLOATS = NIT * 2 * NPROD * KS;
+};
+
+// Wp[it][n/8][c][n%8][e] ; k = it*KS + c*4 + e -> (tap = k / CRED, cr = k % CRED)
+// rows n < NPROD: hi(W[prod = n][cr][tap]) ; rows n >= NPROD: lo(...)
+template <int CRED, int NPROD>
+__global__ void umma_pack_kernel(const float* __restrict__ w, int Cb, int bfs,
+                                 float* __restrict__ wp) {
+  using US = UmmaShape<CRED, NPROD>;
+  const int total = US::PACKED_FLOATS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int r = i;
+    const int e = r % 4; r /= 4;
+    const int n8 = r % 8; r /= 8;
+    const int c = r % US::KCH; r /= US::KCH;
+    const int nb = r % (2 * NPROD / 8);
+    const int it = r / (2 * NPROD / 8);
+    const int n = nb * 8 + n8;
+    const int kk = it * US::KS + c * 4 + e;
+    const int tap = kk / CRED, cr = kk % CRED;
+    float v = 0.f;
+    if (tap < 27) {
+      const int prod = n % NPROD;
+      // W[cs][cb][tap]; SFB: prod = cs, red = cb ; BFS: red = cs, prod = cb
+      const long long gi = bfs ? ((long long)cr * Cb + prod) * 27 + tap
+                               : ((long long)prod * Cb + cr) * 27 + tap;
+      const float x = __ldg(w + gi);
+      const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      v = (n < NPROD) ? hi : (x - hi);
+    }
+    wp[i] = v;
+  }
+}
+
+template <int CRED, int NPROD>
+__global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
+  using US = UmmaShape<CRED, NPROD>;
+  constexpr int KS = US::KS, KCH = US::KCH, NIT = US::NIT;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * US::STAGE_BYTES);   // empty[0], empty[1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * US::STAGE_BYTES + 32);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)US::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // my output voxel (row m = tid of the 128-row tile)
+  const long long o = (long long)blockIdx.x * 128 + tid;
+  const bool row_valid = o < A.nvox;
+  int n = 0, od = 0, oh = 0, ow = 0;
+  if (row_valid) {
+    long long t = o;
+    ow = (int)(t % A.Wd); t /= A.Wd;
+    oh = (int)(t % A.Hd); t /= A.Hd;
+    od = (int)(t % A.Dd);
+    n = (int)(t / A.Dd);
+  }
+  const float* src_n = A.src + (long long)n * A.Dr * A.Hr * A.Wr * A.ldr;
+  const uint32_t row_off = (uint32_t)((tid >> 3) * (KCH * 128) + (tid & 7) * 16);   // bytes
+
+  constexpr uint32_t IDESC1 = make_idesc_tf32(2 * NPROD);
+  constexpr uint32_t IDESC2 = make_idesc_tf32(NPROD);
+
+#pragma unroll 1
+  for (int it = 0; it < NIT; ++it) {
+    const int s = it & 1;
+    unsigned char* stage = smem + s * US::STAGE_BYTES;
+    unsigned char* a_hi = stage;
+    unsigned char* a_lo = stage + US::A_BYTES;
+    unsigned char* b_sm = stage + 2 * US::A_BYTES;
+    if (it >= 2) mbar_wait(&bars[s], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of it-2 drained
+
+    // ---- B: packed weights of this stage (contiguous) ----
+    {
+      const float4* g = reinterpret_cast<const float4*>(A.wp + (long long)it * (US::B_BYTES / 4));
+      float4* d = reinterpret_cast<float4*>(b_sm);
+#pragma unroll
+      for (int i = tid; i < US::B_BYTES / 16; i += 128) d[i] = __ldg(g + i);
+    }
+    // ---- A: gather my row for the taps of this stage, split hi / lo ----
+#pragma unroll
+    for (int tp = 0; tp < US::TPS; ++tp) {
+      const int tap = it * US::TPS + tp;
+      const float* px = nullptr;
+      if (row_valid && tap < 27) {
+        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        int id, ih, iw;
+        bool ok = true;
+        if (A.bfs) {
+          const int nd = od + A.pad - kd * A.dil, nh = oh + A.pad - kh * A.dil,
+                    nw = ow + A.pad - kw * A.dil;
+          ok = nd >= 0 && nh >= 0 && nw >= 0 && (nd % A.stride) == 0 && (nh % A.stride) == 0 &&
+               (nw % A.stride) == 0;
+          id = nd / A.stride; ih = nh / A.stride; iw = nw / A.stride;
+        } else {
+          id = od * A.stride - A.pad + kd * A.dil;
+          ih = oh * A.stride - A.pad + kh * A.dil;
+          iw = ow * A.stride - A.pad + kw * A.dil;
+        }
+        ok = ok && id >= 0 && id < A.Dr && ih >= 0 && ih < A.Hr && iw >= 0 && iw < A.Wr;
+        if (ok) px = src_n + (((long long)id * A.Hr + ih) * A.Wr + iw) * A.ldr;
+      }
+      float4 xv[CRED / 4];
+#pragma unroll
+      for (int c = 0; c < CRED / 4; ++c)
+        xv[c] = px ? ldg4(px + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < CRED / 4; ++c) {
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(xv[c].x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(xv[c].y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(xv[c].z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(xv[c].w) & 0xFFFFE000u);
+        lo.x = xv[c].x - hi.x; lo.y = xv[c].y - hi.y; lo.z = xv[c].z - hi.z; lo.w = xv[c].w - hi.w;
+        const uint32_t off = row_off + (uint32_t)(tp * (CRED / 4) + c) * 128u;
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      }
+    }
+    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_s = smem_u32(b_sm);
+#pragma unroll
+      for (int kk = 0; kk < KS / 8; ++kk) {
+        const uint64_t da_hi = make_smem_desc(a_hi_s + kk * 256, 128, KCH * 128);
+        const uint64_t da_lo = make_smem_desc(a_lo_s + kk * 256, 128, KCH * 128);
+        const uint64_t db = make_smem_desc(b_s + kk * 256, 128, KCH * 128);
+        umma_tf32(tmem_base, da_hi, db, IDESC1, (it | kk) ? 1u : 0u);   // hi*[hi|lo] -> cols [0,2N)
+        umma_tf32(tmem_base, da_lo, db, IDESC2, 1u);                    // lo*hi      -> cols [0,N)
+      }
+      umma_commit(&bars[s]);
+    }
+  }
+
+  // ---- epilogue: all MMAs done when the last stage's commit lands ----
+  mbar_wait(&bars[(NIT - 1) & 1], (uint32_t)(((NIT - 1) >> 1) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  float* pd = A.dst + o * A.ldd;
+#pragma unroll 1
+  for (int c8 = 0; c8 < NPROD / 8; ++c8) {
+    float hi[8], lo[8];
+    tmem_ld8(trow + c8 * 8, hi);
+    tmem_ld8(trow + NPROD + c8 * 8, lo);
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    if (row_valid) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = hi[i] + lo[i];
+        if (A.bias) v[i] += __ldg(A.bias + c8 * 8 + i);
+      }
+      float4 v0 = make_float4(v[0], v[1], v[2], v[3]), v1 = make_float4(v[4], v[5], v[6], v[7]);
+      if (A.accumulate) {
+        const float4 o0 = *reinterpret_cast<const float4*>(pd + c8 * 8);
+        const float4 o1 = *reinterpret_cast<const float4*>(pd + c8 * 8 + 4);
+        v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+        v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
+      }
+      st4(pd + c8 * 8, v0);
+      st4(pd + c8 * 8 + 4, v1);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
+                 "r"((uint32_t)US::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int CRED, int NPROD>
+static int launch_umma(const UmmaArgs& A, cudaStream_t st) {
+  using US = UmmaShape<CRED, NPROD>;
+  auto kern = umma_conv_kernel<CRED, NPROD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US::SMEM));
+    attr_done = true;
+  }
+  const unsigned blocks = (unsigned)((A.nvox + 127) / 128);
+  kern<<<blocks, 128, US::SMEM, st>>>(A);
+  return launched("umma_conv");
+}
+
+template <int CRED, int NPROD>
+static int launch_pack(const float* w, int Cb, int bfs, float* wp, cudaStream_t st) {
+  using US = UmmaShape<CRED, NPROD>;
+  umma_pack_kernel<CRED, NPROD><<<(US::PACKED_FLOATS + 255) / 256, 256, 0, st>>>(w, Cb, bfs, wp);
+  return launched("umma_pack");
+}
+
+static bool umma_channels_ok(int c) { return c == 16 || c == 32 || c == 64; }
+
+}  // namespace nas3d
+
+using namespace nas3d;
+
+extern "C" {
+
+long long nas3d_umma_packed_floats(const nas3d_conv_desc* d, int produce_big) {
+  if (!d || d->k != 3 || d->depthwise || d->Cb != d->Cs || !umma_channels_ok(d->Cb)) return 0;
+  (void)produce_big;
+  switch (d->Cb) {
+    case 16: return UmmaShape<16, 16>::PACKED_FLOATS;
+    case 32: return UmmaShape<32, 32>::PACKED_FLOATS;
+    default: return UmmaShape<64, 64>::PACKED_FLOATS;
+  }
+}
+
+int nas3d_umma_pack_weights(const nas3d_conv_desc* d, const float* w, int produce_big, float* packed,
+                            void* stream) {
+  NAS3D_REQUIRE(nas3d_umma_packed_floats(d, produce_big) > 0, "umma_pack: unsupported conv shape");
+  NAS3D_REQUIRE(aligned16(packed), "umma_pack: packed buffer must be 16B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->Cb) {
+    case 16: return launch_pack<16, 16>(w, d->Cb, produce_big, packed, st);
+    case 32: return launch_pack<32, 32>(w, d->Cb, produce_big, packed, st);
+    default: return launch_pack<64, 64>(w, d->Cb, produce_big, packed, st);
+  }
+}
+
+int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
+                    const float* packed_w, const float* bias, float* dst, int accumulate,
+                    void* stream) {
+  NAS3D_REQUIRE(nas3d_umma_packed_floats(d, produce_big) > 0, "umma_conv: unsupported conv shape");
+  NAS3D_REQUIRE(d->ld_big % 4 == 0 && d->ld_small % 4 == 0 && aligned16(src) && aligned16(dst) &&
+                    aligned16(packed_w),
+                "umma_conv: pitches must be multiples of 4 and pointers 16B aligned");
+  for (int ax = 0; ax < 3; ++ax) {
+    const int b = ax == 0 ? d->Db : ax == 1 ? d->Hb : d->Wb;
+    const int s = ax == 0 ? d->Ds : ax == 1 ? d->Hs : d->Ws;
+    const int expect = (b + 2 * d->pad - d->dil * (d->k - 1) - 1) / d->stride + 1;
+    NAS3D_REQUIRE(s == expect, "umma_conv: small extent %d != %d implied by big extent %d", s, expect, b);
+  }
+  UmmaArgs A;
+  A.src = src; A.wp = packed_w; A.bias = bias; A.dst = dst; A.N = d->N;
+  if (produce_big) {
+    A.Dd = d->Db; A.Hd = d->Hb; A.Wd = d->Wb; A.ldd = d->ld_big;
+    A.Dr = d->Ds; A.Hr = d->Hs; A.Wr = d->Ws; A.ldr = d->ld_small;
+  } else {
+    A.Dd = d->Ds; A.Hd = d->Hs; A.Wd = d->Ws; A.ldd = d->ld_small;
+    A.Dr = d->Db; A.Hr = d->Hb; A.Wr = d->Wb; A.ldr = d->ld_big;
+  }
+  A.k = d->k; A.stride = d->stride; A.dil = d->dil; A.pad = d->pad;
+  A.bfs = produce_big ? 1 : 0;
+  A.accumulate = accumulate;
+  A.nvox = (long long)d->N * A.Dd * A.Hd * A.Wd;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->Cb) {
+    case 16: return launch_umma<16, 16>(A, st);
+    case 32: return launch_umma<32, 32>(A, st);
+    default: return launch_umma<64, 64>(A, st);
+  }
+}
+
+}  // extern "C"

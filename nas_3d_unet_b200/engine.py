@@ -164,6 +164,7 @@ class ExecCtx:
         self.views = {}
         self.lib = get_lib()
         self.stream = _stream()
+        self.packed = {}
 
     def use(self, *params):
         for p in params:
@@ -434,6 +435,27 @@ class _GradView:
         return self.t.data_ptr()
 
 
+def _umma_enabled():
+    import os
+    return os.environ.get("NAS3D_DISABLE_UMMA", "0") != "1"
+
+
+def _umma_packed(ctx, d, m, produce_big):
+    """packed [W_hi|W_lo] operand of the tcgen05 path, cached per (weight, direction) for the
+    lifetime of one forward/backward (weights only change in optimizer.step)"""
+    n = ctx.lib.nas3d_umma_packed_floats(C.byref(d), produce_big)
+    if n <= 0 or not _umma_enabled():
+        return None
+    key = (id(m.weight), produce_big)
+    wp = ctx.packed.get(key)
+    if wp is None:
+        wp = torch.empty(int(n), device=ctx.device, dtype=torch.float32)
+        check(ctx.lib.nas3d_umma_pack_weights(C.byref(d), m.weight.data_ptr(), produce_big,
+                                              wp.data_ptr(), ctx.stream), "umma_pack_weights")
+        ctx.packed[key] = wp
+    return wp
+
+
 def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False):
     """y = conv(f(x)) with f = optional relu / per-(n,c) scale prologue; returns the raw Act.
 
@@ -446,18 +468,30 @@ def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False):
     y = new_act(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
                 ctx.device)
     bias = m.bias.data_ptr() if m.bias is not None else None
+    plain = not (in_relu or in_scale is not None or sigmoid)
     if not spec.transposed:
         d = _desc(spec, x, y)
-        check(lib.nas3d_conv_small_from_big(C.byref(d), x.ptr, m.weight.data_ptr(), bias,
-                                            _tp(in_scale), 1 if in_relu else 0,
-                                            1 if sigmoid else 0, y.ptr, 0, ctx.stream),
-              "conv_small_from_big")
+        wp = _umma_packed(ctx, d, m, 0) if plain else None
+        if wp is not None:
+            check(lib.nas3d_umma_conv(C.byref(d), 0, x.ptr, wp.data_ptr(), bias, y.ptr, 0,
+                                      ctx.stream), "umma_conv fwd")
+        else:
+            check(lib.nas3d_conv_small_from_big(C.byref(d), x.ptr, m.weight.data_ptr(), bias,
+                                                _tp(in_scale), 1 if in_relu else 0,
+                                                1 if sigmoid else 0, y.ptr, 0, ctx.stream),
+                  "conv_small_from_big")
     else:
-        if in_relu or in_scale is not None or sigmoid:
+        if not plain:
             raise NotImplementedError("prologue/epilogue on a transposed convolution")
         d = _desc(spec, y, x)
-        check(lib.nas3d_conv_big_from_small(C.byref(d), x.ptr, m.weight.data_ptr(), bias, None, 0,
-                                            None, y.ptr, 0, ctx.stream), "conv_big_from_small")
+        wp = _umma_packed(ctx, d, m, 1)
+        if wp is not None:
+            check(lib.nas3d_umma_conv(C.byref(d), 1, x.ptr, wp.data_ptr(), bias, y.ptr, 0,
+                                      ctx.stream), "umma_conv convT fwd")
+        else:
+            check(lib.nas3d_conv_big_from_small(C.byref(d), x.ptr, m.weight.data_ptr(), bias, None,
+                                                0, None, y.ptr, 0, ctx.stream),
+                  "conv_big_from_small")
     ctx.push(lambda: _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid))
     return y
 
@@ -486,9 +520,14 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
             g, acc = x.grad_slot()
             gv = _GradView(g, x)
             d2 = _desc(spec, gv, dy)
-            check(lib.nas3d_conv_big_from_small(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
-                                                x.ptr if in_relu else None, x.ld, _tp(in_scale),
-                                                gv.ptr, acc, st), "conv dgrad")
+            wp = _umma_packed(ctx, d2, m, 1) if not (in_relu or in_scale is not None) else None
+            if wp is not None:
+                check(lib.nas3d_umma_conv(C.byref(d2), 1, dy.ptr, wp.data_ptr(), None, gv.ptr, acc,
+                                          st), "umma_conv dgrad")
+            else:
+                check(lib.nas3d_conv_big_from_small(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
+                                                    x.ptr if in_relu else None, x.ld,
+                                                    _tp(in_scale), gv.ptr, acc, st), "conv dgrad")
     else:
         d = _desc(spec, dy, x)
         check(lib.nas3d_conv_wgrad(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, st),
@@ -497,8 +536,13 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
             g, acc = x.grad_slot()
             gv = _GradView(g, x)
             d2 = _desc(spec, dy, gv)
-            check(lib.nas3d_conv_small_from_big(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
-                                                None, 0, 0, gv.ptr, acc, st), "convT dgrad")
+            wp = _umma_packed(ctx, d2, m, 0)
+            if wp is not None:
+                check(lib.nas3d_umma_conv(C.byref(d2), 0, dy.ptr, wp.data_ptr(), None, gv.ptr, acc,
+                                          st), "umma_conv convT dgrad")
+            else:
+                check(lib.nas3d_conv_small_from_big(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
+                                                    None, 0, 0, gv.ptr, acc, st), "convT dgrad")
 
 
 # ----------------------------------------------------------------------------------------

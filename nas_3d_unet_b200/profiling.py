@@ -36,6 +36,11 @@ def _work(name, args):
     """(algorithmic bytes, flops, tag) of one call"""
     if name in ("nas3d_conv_small_from_big", "nas3d_conv_big_from_small", "nas3d_conv_wgrad"):
         return _conv_work(args[0])
+    if name == "nas3d_umma_conv":
+        b, f, tag = _conv_work(args[0])
+        return b, f, tag + (" umma-T" if args[1] else " umma")
+    if name == "nas3d_umma_pack_weights":
+        return 0.0, 0.0, "pack"
     if name == "nas3d_affine_sum_fwd":
         n, N, V, Cc = args[0], args[9], args[10], args[11]
         return 4.0 * (n + 1) * N * V * Cc, 0.0, "K=%d C=%d V=%d" % (n, Cc, V)
@@ -82,7 +87,8 @@ class ProfiledLib:
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
         if not name.startswith("nas3d_") or name in ("nas3d_last_error", "nas3d_version",
-                                                       "nas3d_launch_count"):
+                                                       "nas3d_launch_count",
+                                                       "nas3d_umma_packed_floats"):
             return fn
 
         def wrapped(*args):

@@ -238,3 +238,43 @@ def test_tiled_conv_kernels_match_oracle_on_ragged_volume(c, dil):
         assert O.max_rel(dx, xr.grad) <= 1e-5, mode
         assert O.max_rel(dw, sd['conv.weight'].grad) <= 1e-4, mode
         assert O.max_rel(db, sd['conv.bias'].grad) <= 1e-4, mode
+
+
+@pytest.mark.parametrize("c", [16, 32, 64])
+@pytest.mark.parametrize("stride,dil,transposed", [(1, 1, False), (1, 2, False), (2, 1, False),
+                                                   (2, 1, True), (2, 2, False), (2, 2, True)])
+def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
+    """tensor-core path (tcgen05 kind::tf32 + 3xTF32 compensation, TMEM accumulators) for the
+    wide layers: forward and dgrad of every conv flavour against the fp32 oracle at fp32-grade
+    tolerance, and against the CUDA-core path"""
+    import os
+    from nas_3d_unet_b200.prim_ops import ConvOps
+    torch.manual_seed(c + 7 * stride + dil)
+    op = ConvOps(c, c, stride=stride, dilation=dil, transposed=transposed, ops_order='weight')
+    g = torch.Generator().manual_seed(3 * c + stride)
+    s_in = (6, 10, 12) if not transposed else (3, 5, 6)
+    x = torch.randn(2, c, *s_in, generator=g) * 3.0
+    sd = O.leaf_state(op.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = O.conv_ops(sd, '', xr, 3, stride, dil, transposed, order='weight')
+    r = torch.randn(yr.shape, generator=g)
+    (yr * r).sum().backward()
+    op = op.cuda()
+    from nas_3d_unet_b200 import profiling
+    for mode in ("umma", "ffma"):
+        os.environ["NAS3D_DISABLE_UMMA"] = "1" if mode == "ffma" else "0"
+        prof = profiling.enable()
+        try:
+            op.zero_grad()
+            xg = x.cuda().requires_grad_(True)
+            y = op(xg)
+            (y * r.cuda()).sum().backward()
+            names = [rec[0] for rec in prof.records]
+        finally:
+            profiling.disable()
+            os.environ["NAS3D_DISABLE_UMMA"] = "0"
+        assert ("nas3d_umma_conv" in names) == (mode == "umma"), names
+        assert tuple(y.shape) == tuple(yr.shape)
+        assert O.max_rel(y, yr) <= 2e-5, (mode, O.max_rel(y, yr))
+        assert O.max_rel(xg.grad, xr.grad) <= 2e-5, (mode, O.max_rel(xg.grad, xr.grad))
+        assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
