@@ -88,6 +88,28 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// branch-free predicated 128-bit load (zeros when !ok) so that all gathers of a stage are in
+// flight together instead of being serialised behind per-load branches
+__device__ __forceinline__ float4 ldg4_pred(const float* p, bool ok) {
+  float4 v;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\t"
+      "mov.f32 %1, 0f00000000;\n\t"
+      "mov.f32 %2, 0f00000000;\n\t"
+      "mov.f32 %3, 0f00000000;\n\t"
+      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}\n"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "r"((int)ok));
+  return v;
+}
+__device__ __forceinline__ void cp_async16_u(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+
 template <int CRED, int NPROD>
 struct UmmaShape {
   static constexpr int KS = CRED == 16 ? 32 : CRED;      // K floats per smem stage
@@ -176,6 +198,34 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   constexpr uint32_t IDESC1 = make_idesc_tf32(2 * NPROD);
   constexpr uint32_t IDESC2 = make_idesc_tf32(NPROD);
 
+  // gather of one stage into registers: my row, TPS taps x CRED channels
+  float4 xv[US::TPS][CRED / 4];
+  auto gather = [&](int it) {
+#pragma unroll
+    for (int tp = 0; tp < US::TPS; ++tp) {
+      const int tap = it * US::TPS + tp;
+      const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+      int id, ih, iw;
+      bool ok = row_valid && tap < 27;
+      if (A.bfs) {
+        const int nd = od + A.pad - kd * A.dil, nh = oh + A.pad - kh * A.dil,
+                  nw = ow + A.pad - kw * A.dil;
+        ok = ok && nd >= 0 && nh >= 0 && nw >= 0 && (nd % A.stride) == 0 &&
+             (nh % A.stride) == 0 && (nw % A.stride) == 0;
+        id = nd / A.stride; ih = nh / A.stride; iw = nw / A.stride;
+      } else {
+        id = od * A.stride - A.pad + kd * A.dil;
+        ih = oh * A.stride - A.pad + kh * A.dil;
+        iw = ow * A.stride - A.pad + kw * A.dil;
+      }
+      ok = ok && id >= 0 && id < A.Dr && ih >= 0 && ih < A.Hr && iw >= 0 && iw < A.Wr;
+      const float* px = ok ? src_n + (((long long)id * A.Hr + ih) * A.Wr + iw) * A.ldr : A.src;
+#pragma unroll
+      for (int c = 0; c < CRED / 4; ++c) xv[tp][c] = ldg4_pred(px + c * 4, ok);
+    }
+  };
+  gather(0);
+
 #pragma unroll 1
   for (int it = 0; it < NIT; ++it) {
     const int s = it & 1;
@@ -185,53 +235,33 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
     unsigned char* b_sm = stage + 2 * US::A_BYTES;
     if (it >= 2) mbar_wait(&bars[s], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of it-2 drained
 
-    // ---- B: packed weights of this stage (contiguous) ----
+    // ---- B: packed weights of this stage (contiguous), asynchronous copy ----
     {
-      const float4* g = reinterpret_cast<const float4*>(A.wp + (long long)it * (US::B_BYTES / 4));
-      float4* d = reinterpret_cast<float4*>(b_sm);
+      const float* g = A.wp + (long long)it * (US::B_BYTES / 4);
 #pragma unroll
-      for (int i = tid; i < US::B_BYTES / 16; i += 128) d[i] = __ldg(g + i);
+      for (int i = tid; i < US::B_BYTES / 16; i += 128) cp_async16_u(b_sm + i * 16, g + i * 4);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    // ---- A: gather my row for the taps of this stage, split hi / lo ----
+    // ---- A: split the gathered row into hi / lo and store in core-matrix layout ----
 #pragma unroll
     for (int tp = 0; tp < US::TPS; ++tp) {
-      const int tap = it * US::TPS + tp;
-      const float* px = nullptr;
-      if (row_valid && tap < 27) {
-        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        int id, ih, iw;
-        bool ok = true;
-        if (A.bfs) {
-          const int nd = od + A.pad - kd * A.dil, nh = oh + A.pad - kh * A.dil,
-                    nw = ow + A.pad - kw * A.dil;
-          ok = nd >= 0 && nh >= 0 && nw >= 0 && (nd % A.stride) == 0 && (nh % A.stride) == 0 &&
-               (nw % A.stride) == 0;
-          id = nd / A.stride; ih = nh / A.stride; iw = nw / A.stride;
-        } else {
-          id = od * A.stride - A.pad + kd * A.dil;
-          ih = oh * A.stride - A.pad + kh * A.dil;
-          iw = ow * A.stride - A.pad + kw * A.dil;
-        }
-        ok = ok && id >= 0 && id < A.Dr && ih >= 0 && ih < A.Hr && iw >= 0 && iw < A.Wr;
-        if (ok) px = src_n + (((long long)id * A.Hr + ih) * A.Wr + iw) * A.ldr;
-      }
-      float4 xv[CRED / 4];
-#pragma unroll
-      for (int c = 0; c < CRED / 4; ++c)
-        xv[c] = px ? ldg4(px + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < CRED / 4; ++c) {
+        const float4 x = xv[tp][c];
         float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(xv[c].x) & 0xFFFFE000u);
-        hi.y = __uint_as_float(__float_as_uint(xv[c].y) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(xv[c].z) & 0xFFFFE000u);
-        hi.w = __uint_as_float(__float_as_uint(xv[c].w) & 0xFFFFE000u);
-        lo.x = xv[c].x - hi.x; lo.y = xv[c].y - hi.y; lo.z = xv[c].z - hi.z; lo.w = xv[c].w - hi.w;
+        hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
         const uint32_t off = row_off + (uint32_t)(tp * (CRED / 4) + c) * 128u;
         *reinterpret_cast<float4*>(a_hi + off) = hi;
         *reinterpret_cast<float4*>(a_lo + off) = lo;
       }
     }
+    // next stage's gather goes in flight now; it lands while this stage's MMAs are issued
+    if (it + 1 < NIT) gather(it + 1);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

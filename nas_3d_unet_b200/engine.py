@@ -435,16 +435,20 @@ class _GradView:
         return self.t.data_ptr()
 
 
-def _umma_enabled():
+def _umma_enabled(channels):
+    """tcgen05 path policy (measured, tools/umma_micro.py): it wins 2.5-5x over the CUDA-core
+    kernels from 32 channels up; at 16 channels the tiled FFMA kernel is still ahead."""
     import os
-    return os.environ.get("NAS3D_DISABLE_UMMA", "0") != "1"
+    if os.environ.get("NAS3D_DISABLE_UMMA", "0") == "1":
+        return False
+    return channels >= int(os.environ.get("NAS3D_UMMA_MIN_C", "32"))
 
 
 def _umma_packed(ctx, d, m, produce_big):
     """packed [W_hi|W_lo] operand of the tcgen05 path, cached per (weight, direction) for the
     lifetime of one forward/backward (weights only change in optimizer.step)"""
     n = ctx.lib.nas3d_umma_packed_floats(C.byref(d), produce_big)
-    if n <= 0 or not _umma_enabled():
+    if n <= 0 or not _umma_enabled(d.Cb):
         return None
     key = (id(m.weight), produce_big)
     wp = ctx.packed.get(key)

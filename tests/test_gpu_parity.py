@@ -261,6 +261,7 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
     (yr * r).sum().backward()
     op = op.cuda()
     from nas_3d_unet_b200 import profiling
+    os.environ["NAS3D_UMMA_MIN_C"] = "16"
     for mode in ("umma", "ffma"):
         os.environ["NAS3D_DISABLE_UMMA"] = "1" if mode == "ffma" else "0"
         prof = profiling.enable()
@@ -273,6 +274,8 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
         finally:
             profiling.disable()
             os.environ["NAS3D_DISABLE_UMMA"] = "0"
+            if mode == "ffma":
+                os.environ.pop("NAS3D_UMMA_MIN_C", None)
         assert ("nas3d_umma_conv" in names) == (mode == "umma"), names
         assert tuple(y.shape) == tuple(yr.shape)
         assert O.max_rel(y, yr) <= 2e-5, (mode, O.max_rel(y, yr))
