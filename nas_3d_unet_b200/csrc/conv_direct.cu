@@ -47,6 +47,17 @@ static int tiled_kind(const nas3d_conv_desc* d, bool wgrad = false) {
     return 2;
   return 0;
 }
+static bool s2d1_shape(const nas3d_conv_desc* d) {
+  return tiled_enabled() && d->k == 3 && d->stride == 2 && d->dil == 1 && d->pad == 1 && !d->depthwise;
+}
+static S2Args s2_args(const nas3d_conv_desc* d, const float* big, const float* small, const float* w) {
+  S2Args A{};
+  A.big = const_cast<float*>(big); A.small = const_cast<float*>(small); A.w = w;
+  A.N = d->N;
+  A.Db = d->Db; A.Hb = d->Hb; A.Wb = d->Wb; A.Cb = d->Cb; A.ld_big = d->ld_big;
+  A.Ds = d->Ds; A.Hs = d->Hs; A.Ws = d->Ws; A.Cs = d->Cs; A.ld_small = d->ld_small;
+  return A;
+}
 static void tiled_fill(const nas3d_conv_desc* d, int kind, bool x_is_big, TiledArgs* T) {
   T->N = d->N; T->D = d->Ds; T->H = d->Hs; T->W = d->Ws;
   const int bs = kind == 2 ? 2 : 1;
@@ -536,6 +547,12 @@ int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const 
                        (cudaStream_t)stream);
     if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
   }
+  if (s2d1_shape(d) && !big_scale && !big_relu && !out_sigmoid) {
+    S2Args S = s2_args(d, big, small, w);
+    S.bias = bias; S.accumulate = accumulate;
+    rc = tiled_s2_sfb(S, (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   if (const int kind = tiled_kind(d); kind && !big_scale && !big_relu && !out_sigmoid) {
     TiledArgs T{};
     tiled_fill(d, kind, true, &T);
@@ -557,6 +574,12 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
   if (pointwise_shape(d)) {
     rc = pointwise_bfs(d, small, w, bias, mask_big, ld_mask, big_scale, big, accumulate,
                        (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
+  if (s2d1_shape(d) && !big_scale && !mask_big) {
+    S2Args S = s2_args(d, big, small, w);
+    S.bias = bias; S.accumulate = accumulate;
+    rc = tiled_s2_bfs(S, (cudaStream_t)stream);
     if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
   }
   if (const int kind = tiled_kind(d);
@@ -595,6 +618,14 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
   bool done = false;
   if (pointwise_shape(d)) {
     rc = pointwise_wgrad(d, small, big, big_scale, big_relu, dW, d_bias_small, st);
+    if (rc == NAS3D_OK) done = true;
+    else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    rc = NAS3D_OK;
+  }
+  if (!done && s2d1_shape(d) && !big_scale && !big_relu) {
+    S2Args S = s2_args(d, big, small, nullptr);
+    S.dW = dW; S.dbias_small = d_bias_small;
+    rc = tiled_s2_wgrad(S, st);
     if (rc == NAS3D_OK) done = true;
     else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
     rc = NAS3D_OK;

@@ -35,6 +35,24 @@ struct WgradArgs {
 };
 
 
+// stride-2 dilation-1 family (conv_tiled_s2.cu): conv view big_pos = 2*small_pos - 1 + tap
+struct S2Args {
+  float* big;
+  float* small;
+  const float* w;
+  const float* bias;
+  float* dW;
+  float* dbias_small;
+  int N;
+  int Db, Hb, Wb, Cb, ld_big;
+  int Ds, Hs, Ws, Cs, ld_small;
+  int accumulate;
+  int tiles_w, tiles_h, tiles_d;
+};
+int tiled_s2_sfb(const S2Args& A, cudaStream_t st);
+int tiled_s2_bfs(const S2Args& A, cudaStream_t st);
+int tiled_s2_wgrad(const S2Args& A, cudaStream_t st);
+
 // return NAS3D_ERR_UNSUPPORTED (without error text) when the shape is not covered
 int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st);
 int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st);

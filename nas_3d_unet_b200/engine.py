@@ -435,20 +435,24 @@ class _GradView:
         return self.t.data_ptr()
 
 
-def _umma_enabled(channels):
+def _umma_enabled(d):
     """tcgen05 path policy (measured, tools/umma_micro.py): it wins 2.5-5x over the CUDA-core
-    kernels from 32 channels up; at 16 channels the tiled FFMA kernel is still ahead."""
+    kernels from 32 channels up; at 16 channels the tiled FFMA kernel is still ahead for
+    stride 1, while the stride-2 dilation-1 tiled kernels stop at 8 channels."""
     import os
     if os.environ.get("NAS3D_DISABLE_UMMA", "0") == "1":
         return False
-    return channels >= int(os.environ.get("NAS3D_UMMA_MIN_C", "32"))
+    floor = os.environ.get("NAS3D_UMMA_MIN_C")
+    if floor is not None:
+        return d.Cb >= int(floor)
+    return d.Cb >= (16 if (d.stride == 2 and d.dil == 1) else 32)
 
 
 def _umma_packed(ctx, d, m, produce_big):
     """packed [W_hi|W_lo] operand of the tcgen05 path, cached per (weight, direction) for the
     lifetime of one forward/backward (weights only change in optimizer.step)"""
     n = ctx.lib.nas3d_umma_packed_floats(C.byref(d), produce_big)
-    if n <= 0 or not _umma_enabled(d.Cb):
+    if n <= 0 or not _umma_enabled(d):
         return None
     key = (id(m.weight), produce_big)
     wp = ctx.packed.get(key)

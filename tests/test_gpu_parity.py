@@ -281,3 +281,36 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
         assert O.max_rel(y, yr) <= 2e-5, (mode, O.max_rel(y, yr))
         assert O.max_rel(xg.grad, xr.grad) <= 2e-5, (mode, O.max_rel(xg.grad, xr.grad))
         assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
+
+
+@pytest.mark.parametrize("cin,cout,transposed", [(4, 4, False), (8, 8, False), (4, 12, False),
+                                                 (4, 4, True), (8, 8, True)])
+def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
+    """stride-2 dilation-1 tiled kernels (down_conv / up_conv / stem1 family): fwd, dgrad, wgrad
+    on tile-ragged extents against the oracle and the generic gather kernels"""
+    import os
+    from nas_3d_unet_b200.prim_ops import ConvOps
+    torch.manual_seed(cin * 3 + cout + transposed)
+    op = ConvOps(cin, cout, stride=2, transposed=transposed, ops_order='weight')
+    g = torch.Generator().manual_seed(cin + cout)
+    shape = (5, 6, 18) if transposed else (10, 12, 36)
+    x = torch.randn(2, cin, *shape, generator=g)
+    sd = O.leaf_state(op.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = O.conv_ops(sd, '', xr, 3, 2, 1, transposed, order='weight')
+    r = torch.randn(yr.shape, generator=g)
+    (yr * r).sum().backward()
+    op = op.cuda()
+    for mode in ("tiled", "generic"):
+        os.environ["NAS3D_DISABLE_TILED"] = "1" if mode == "generic" else "0"
+        try:
+            op.zero_grad()
+            xg = x.cuda().requires_grad_(True)
+            y = op(xg)
+            (y * r.cuda()).sum().backward()
+        finally:
+            os.environ["NAS3D_DISABLE_TILED"] = "0"
+        assert O.max_rel(y, yr) <= 1e-5, mode
+        assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
+        assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
+        assert O.max_rel(op.conv.bias.grad, sd['conv.bias'].grad) <= 1e-4, mode
