@@ -73,17 +73,22 @@ typedef struct {
  * f = optional prologue on the big tensor: relu (preprocess 'act_weight_norm', cell.py:47-50)
  * and/or per-(n,cb) scale `big_scale` [N,Cb] (Dropout3d mask, nas.py:50; may be NULL).
  * out_sigmoid: apply 1/(1+exp(-v)) in the epilogue (nn.Sigmoid of last_conv, nas.py:52).
- * Used for: Conv3d forward, ConvTranspose3d dgrad. */
+ * Used for: Conv3d forward, ConvTranspose3d dgrad.
+ * moments (optional, [N][Cs][2] fp64): receives {sum, sum of squares} per (n,c) of the tensor
+ * just written (= nas3d_moments_nc of it; GroupNorm statistics fused into the conv epilogue
+ * where the kernel supports it, a separate pass otherwise).  Zeroed inside the call. */
 int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const float* w,
                               const float* bias, const float* big_scale, int big_relu,
-                              int out_sigmoid, float* small, int accumulate, void* stream);
+                              int out_sigmoid, float* small, int accumulate, double* moments,
+                              void* stream);
 
 /* big[i,cb] (+)= bias[cb] + sum over (o,tap) with o*s-p+t*d == i of small[o,cs]*W[cs][cb][tap]
  * Optional epilogue for the dgrad of a prologue'd Conv3d: result *= (mask_big>0) and
  * *= big_scale[n,cb].  Used for: ConvTranspose3d forward, Conv3d dgrad. */
 int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, const float* w,
                               const float* bias, const float* mask_big, int ld_mask,
-                              const float* big_scale, float* big, int accumulate, void* stream);
+                              const float* big_scale, float* big, int accumulate, double* moments,
+                              void* stream);
 
 /* dW[cs][cb][tap] += sum_{n,o} small[o,cs] * f(big[o*s-p+t*d, cb]);
  * d_bias_small[cs] += sum small (if non-NULL);  d_bias_big[cb] += sum big (if non-NULL).
@@ -109,7 +114,7 @@ int nas3d_umma_pack_weights(const nas3d_conv_desc* d, const float* w, int produc
                             float* packed, void* stream);
 int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
                     const float* packed_w, const float* bias, float* dst, int accumulate,
-                    void* stream);
+                    double* moments, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Per-(n,c) moments: S[n][c] = {sum x, sum x^2} in fp64 (zeroed inside the call).

@@ -34,13 +34,13 @@ _SIGNATURES = {
     "nas3d_launch_count": [],
     "nas3d_ncdhw_to_ndhwc": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp],
     "nas3d_conv_small_from_big": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp,
-                                  c_int, c_vp],
+                                  c_int, c_vp, c_vp],
     "nas3d_conv_big_from_small": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
-                                  c_int, c_vp],
+                                  c_int, c_vp, c_vp],
     "nas3d_conv_wgrad": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     "nas3d_umma_packed_floats": [C.POINTER(ConvDesc), c_int],
     "nas3d_umma_pack_weights": [C.POINTER(ConvDesc), c_vp, c_int, c_vp, c_vp],
-    "nas3d_umma_conv": [C.POINTER(ConvDesc), c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "nas3d_umma_conv": [C.POINTER(ConvDesc), c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "nas3d_moments_nc": [c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp],
     "nas3d_gn_coef": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, C.c_float, c_vp, c_vp, c_vp, c_vp],
     "nas3d_se_excite": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp],

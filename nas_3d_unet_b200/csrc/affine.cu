@@ -20,33 +20,50 @@ struct FwdTerms {
   int nterms;
 };
 
+// grid = (chunks, N): blockIdx.y is the sample, so no 64-bit division in the hot loop; every
+// thread keeps two independent float4 elements (x K terms) in flight.
+__device__ __forceinline__ float4 affine_term(const FwdTerms& T, int k, const float* base_k,
+                                              unsigned vox, int c, long long nc) {
+  float4 v = ldg4(base_k + (long long)vox * T.ld[k] + c);
+  if (T.a[k]) {
+    const float4 a = ldg4(T.a[k] + nc);
+    v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w;
+  }
+  if (T.b[k]) {
+    const float4 b = ldg4(T.b[k] + nc);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if (T.relu[k]) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(256)
     affine_sum_fwd_kernel(const __grid_constant__ FwdTerms T, float* __restrict__ out, int ld_out,
-                          long long V, int C, int C4, long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long gv = i / C4;
-    const int c = (int)(i - gv * C4) * 4;
-    const long long nc = (gv / V) * C + c;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                          long long V, int C, int C4, unsigned per_sample) {
+  const int n = blockIdx.y;
+  const long long vbase = (long long)n * V;
+  float* outn = out + vbase * ld_out;
+  const unsigned stride = gridDim.x * 256u;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < per_sample; i += 2 * stride) {
+    const unsigned i2 = i + stride;
+    const bool has2 = i2 < per_sample;
+    const unsigned vox0 = i / (unsigned)C4, vox1 = has2 ? i2 / (unsigned)C4 : vox0;
+    const int c0 = (int)(i - vox0 * C4) * 4, c1 = has2 ? (int)(i2 - vox1 * C4) * 4 : c0;
+    const long long nc0 = (long long)n * C + c0, nc1 = (long long)n * C + c1;
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
 #pragma unroll 2
     for (int k = 0; k < T.nterms; ++k) {
-      float4 v = ldg4(T.x[k] + gv * T.ld[k] + c);
-      if (T.a[k]) {
-        const float4 a = ldg4(T.a[k] + nc);
-        v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w;
-      }
-      if (T.b[k]) {
-        const float4 b = ldg4(T.b[k] + nc);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      }
-      if (T.relu[k]) {
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      }
+      const float* bk = T.x[k] + vbase * T.ld[k];
+      const float4 v0 = affine_term(T, k, bk, vox0, c0, nc0);
+      const float4 v1 = affine_term(T, k, bk, vox1, c1, nc1);
       const float w = T.w[k] ? __ldg(T.w[k]) : 1.f;
-      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+      acc0.x += w * v0.x; acc0.y += w * v0.y; acc0.z += w * v0.z; acc0.w += w * v0.w;
+      acc1.x += w * v1.x; acc1.y += w * v1.y; acc1.z += w * v1.z; acc1.w += w * v1.w;
     }
-    st4(out + gv * ld_out + c, acc);
+    st4(outn + (long long)vox0 * ld_out + c0, acc0);
+    if (has2) st4(outn + (long long)vox1 * ld_out + c1, acc1);
   }
 }
 
@@ -68,18 +85,20 @@ struct BwdTerms {
 
 __global__ void __launch_bounds__(256)
     affine_sum_bwd_apply_kernel(const __grid_constant__ BwdTerms T, const float* __restrict__ dout,
-                                int ld_dout, long long V, int C, int C4, long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long gv = i / C4;
-    const int c = (int)(i - gv * C4) * 4;
-    const long long nc = (gv / V) * C + c;
-    const float4 d = ldg4(dout + gv * ld_dout + c);
+                                int ld_dout, long long V, int C, int C4, unsigned per_sample) {
+  const int n = blockIdx.y;
+  const long long vbase = (long long)n * V;
+  const float* dn = dout + vbase * ld_dout;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < per_sample; i += gridDim.x * 256u) {
+    const unsigned vox = i / (unsigned)C4;
+    const int c = (int)(i - vox * C4) * 4;
+    const long long nc = (long long)n * C + c;
+    const float4 d = ldg4(dn + (long long)vox * ld_dout + c);
     for (int k = 0; k < T.nterms; ++k) {
       float4 g = d;
       const bool need_x = T.relu[k] || T.q[k];
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (need_x) x = ldg4(T.x[k] + gv * T.ld[k] + c);
+      if (need_x) x = ldg4(T.x[k] + (vbase + vox) * T.ld[k] + c);
       if (T.relu[k]) {
         float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (T.a[k]) a = ldg4(T.a[k] + nc);
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(256)
         const float4 r = ldg4(T.r[k] + nc);
         g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
       }
-      float* dst = T.dx[k] + gv * T.ld_dx[k] + c;
+      float* dst = T.dx[k] + (vbase + vox) * T.ld_dx[k] + c;
       if (T.acc[k]) {
         // plain load (not the read-only path): an earlier term of this very launch may have
         // written this location from this same thread
@@ -171,6 +190,16 @@ static inline unsigned grid_for(long long total, int block) {
   return (unsigned)b;
 }
 
+// 2-D grid: x covers one sample (elems_per_block elements per CTA pass), y = sample; the x extent
+// is capped so that the whole grid is ~8 CTAs per SM
+static inline dim3 grid2d(long long per_sample, int N, int elems_per_block) {
+  long long bx = (per_sample + elems_per_block - 1) / elems_per_block;
+  long long cap = ((long long)kNumSMs * 8 + N - 1) / N;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, (unsigned)N);
+}
+
 }  // namespace nas3d
 
 using namespace nas3d;
@@ -193,9 +222,10 @@ int nas3d_affine_sum_fwd(int nterms, const float* const* x, const int* ld_x,
     T.relu[k] = relu ? relu[k] : 0;
   }
   const int C4 = C / 4;
-  const long long total = (long long)N * V * C4;
-  affine_sum_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(T, out, ld_out, V,
-                                                                                C, C4, total);
+  const long long per_sample = V * C4;
+  NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_fwd: sample too large for 32-bit indexing");
+  affine_sum_fwd_kernel<<<grid2d(per_sample, N, 512), 256, 0, (cudaStream_t)stream>>>(
+      T, out, ld_out, V, C, C4, (unsigned)per_sample);
   return launched("affine_sum_fwd");
 }
 
@@ -222,9 +252,10 @@ int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_
     NAS3D_REQUIRE(!(T.relu[k] || T.q[k]) || T.x[k], "affine_sum_bwd_apply: term %d needs x", k);
   }
   const int C4 = C / 4;
-  const long long total = (long long)N * V * C4;
-  affine_sum_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      T, dout, ld_dout, V, C, C4, total);
+  const long long per_sample = V * C4;
+  NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_bwd_apply: sample too large");
+  affine_sum_bwd_apply_kernel<<<grid2d(per_sample, N, 256), 256, 0, (cudaStream_t)stream>>>(
+      T, dout, ld_dout, V, C, C4, (unsigned)per_sample);
   return launched("affine_sum_bwd_apply");
 }
 

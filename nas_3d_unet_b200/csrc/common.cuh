@@ -60,6 +60,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Fused GroupNorm statistics for conv epilogues: a warp whose 32 lanes hold values of the SAME 4
+// channels (c0..c0+3) of one sample reduces its per-lane partial {sum, sum of squares} and adds
+// them to a per-CTA shared array sm[2*C] (doubles); cta_moments_flush() then does one fp64
+// atomicAdd per (channel, moment) per CTA into moments[n][C][2].
+__device__ __forceinline__ void warp_moments_add(double* sm, int c0, const float s[4],
+                                                 const float q[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const double a = warp_sum((double)s[e]);
+    const double b = warp_sum((double)q[e]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sm[(c0 + e) * 2 + 0], a);
+      atomicAdd(&sm[(c0 + e) * 2 + 1], b);
+    }
+  }
+}
+__device__ __forceinline__ void cta_moments_flush(const double* sm, double* moments, int n, int C,
+                                                  int nthreads) {
+  for (int i = threadIdx.x; i < 2 * C; i += nthreads)
+    atomicAdd(&moments[(long long)n * C * 2 + i], sm[i]);
+}
+
 // odd part / power-of-two part of the float4-group count of a channel dimension
 static inline void split_c4(int C4, int* U, int* P) {
   int u = C4, p = 1;

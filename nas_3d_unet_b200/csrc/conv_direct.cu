@@ -19,7 +19,7 @@ namespace nas3d {
 // conv_pointwise.cu
 int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
                   const float* scale, int relu, int sigmoid, float* small, int accumulate,
-                  cudaStream_t st);
+                  double* moments, cudaStream_t st);
 int pointwise_bfs(const nas3d_conv_desc* d, const float* small, const float* w, const float* bias,
                   const float* mask_big, int ld_mask, const float* scale, float* big,
                   int accumulate, cudaStream_t st);
@@ -534,38 +534,55 @@ using namespace nas3d;
 
 extern "C" {
 
+// moments of a freshly written produced tensor for the paths that cannot fuse them
+static int moments_fallback(double* moments, const float* y, int N, long long V, int C, int ld,
+                            void* stream) {
+  if (!moments) return NAS3D_OK;
+  return nas3d_moments_nc(y, N, V, C, ld, moments, stream);
+}
+
 int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const float* w,
                               const float* bias, const float* big_scale, int big_relu,
-                              int out_sigmoid, float* small, int accumulate, void* stream) {
+                              int out_sigmoid, float* small, int accumulate, double* moments,
+                              void* stream) {
+  const long long Vs = d ? (long long)d->Ds * d->Hs * d->Ws : 0;
+  if (moments && d) NAS3D_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)d->N * d->Cs, (cudaStream_t)stream));
   ConvArgs A;
   int rc = fill_args(d, &A);
   if (rc) return rc;
   A.src = big; A.w = w; A.bias = bias; A.scale = big_scale; A.relu = big_relu;
   A.sigmoid = out_sigmoid; A.dst = small; A.accumulate = accumulate;
   if (pointwise_shape(d)) {
+    // measured: per-voxel warp reductions cost more than a separate streaming statistics pass for
+    // these 1-voxel-per-thread kernels, so the 1x1 path does not fuse the moments
     rc = pointwise_sfb(d, big, w, bias, big_scale, big_relu, out_sigmoid, small, accumulate,
-                       (cudaStream_t)stream);
-    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+                       nullptr, (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED)
+      return rc ? rc : moments_fallback(moments, small, d->N, Vs, d->Cs, d->ld_small, stream);
   }
   if (s2d1_shape(d) && !big_scale && !big_relu && !out_sigmoid) {
     S2Args S = s2_args(d, big, small, w);
-    S.bias = bias; S.accumulate = accumulate;
+    S.bias = bias; S.accumulate = accumulate; S.moments = moments;
     rc = tiled_s2_sfb(S, (cudaStream_t)stream);
     if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
   }
   if (const int kind = tiled_kind(d); kind && !big_scale && !big_relu && !out_sigmoid) {
     TiledArgs T{};
     tiled_fill(d, kind, true, &T);
-    T.x = big; T.w = w; T.bias = bias; T.y = small; T.accumulate = accumulate;
+    T.x = big; T.w = w; T.bias = bias; T.y = small; T.accumulate = accumulate; T.moments = moments;
     rc = tiled_conv3_s1(d->Cb, kind == 2 ? 1 : d->dil, false, T, (cudaStream_t)stream);
     if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
   }
-  return launch_gather<false>(A, d->depthwise != 0, (cudaStream_t)stream);
+  rc = launch_gather<false>(A, d->depthwise != 0, (cudaStream_t)stream);
+  return rc ? rc : moments_fallback(moments, small, d->N, Vs, d->Cs, d->ld_small, stream);
 }
 
 int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, const float* w,
                               const float* bias, const float* mask_big, int ld_mask,
-                              const float* big_scale, float* big, int accumulate, void* stream) {
+                              const float* big_scale, float* big, int accumulate, double* moments,
+                              void* stream) {
+  const long long Vb = d ? (long long)d->Db * d->Hb * d->Wb : 0;
+  if (moments && d) NAS3D_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)d->N * d->Cb, (cudaStream_t)stream));
   ConvArgs A;
   int rc = fill_args(d, &A);
   if (rc) return rc;
@@ -574,11 +591,12 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
   if (pointwise_shape(d)) {
     rc = pointwise_bfs(d, small, w, bias, mask_big, ld_mask, big_scale, big, accumulate,
                        (cudaStream_t)stream);
-    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    if (rc != NAS3D_ERR_UNSUPPORTED)
+      return rc ? rc : moments_fallback(moments, big, d->N, Vb, d->Cb, d->ld_big, stream);
   }
   if (s2d1_shape(d) && !big_scale && !mask_big) {
     S2Args S = s2_args(d, big, small, w);
-    S.bias = bias; S.accumulate = accumulate;
+    S.bias = bias; S.accumulate = accumulate; S.moments = moments;
     rc = tiled_s2_bfs(S, (cudaStream_t)stream);
     if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
   }
@@ -599,10 +617,13 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
     TiledArgs T{};
     tiled_fill(d, kind, false, &T);
     T.x = small; T.w = w; T.bias = bias; T.y = big; T.accumulate = accumulate;
+    T.moments = kind == 1 ? moments : nullptr;    // lattice writes skip the bias-only voxels
     rc = tiled_conv3_s1(d->Cb, kind == 2 ? 1 : d->dil, true, T, st);
-    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    if (rc != NAS3D_ERR_UNSUPPORTED)
+      return (rc || kind == 1) ? rc : moments_fallback(moments, big, d->N, Vb, d->Cb, d->ld_big, stream);
   }
-  return launch_gather<true>(A, d->depthwise != 0, (cudaStream_t)stream);
+  rc = launch_gather<true>(A, d->depthwise != 0, (cudaStream_t)stream);
+  return rc ? rc : moments_fallback(moments, big, d->N, Vb, d->Cb, d->ld_big, stream);
 }
 
 int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,

@@ -27,6 +27,7 @@ struct PwArgs {
   int stride;
   int relu, sigmoid, accumulate;
   int w_stride_in, w_stride_out;   // W element (in,out) at w[in*w_stride_in + out*w_stride_out]
+  double* moments;                 // optional fused GN statistics of dst (SFB, V % 128 == 0)
 };
 
 constexpr int PW_T = 128;
@@ -36,6 +37,8 @@ constexpr int PW_MAX_W = 4096;   // floats of weights per (Cin x CO tile) in sme
 template <int CO, bool SRC_IS_BIG>
 __global__ void __launch_bounds__(PW_T) pointwise_kernel(const PwArgs A) {
   __shared__ __align__(16) float Wsm[PW_MAX_W];
+  __shared__ double sm_mom[2 * CO];
+  if (threadIdx.x < 2 * CO) sm_mom[threadIdx.x] = 0.0;
   const int co0 = blockIdx.y * CO;
   // Wsm[ci][CO]
   for (int i = threadIdx.x; i < A.Cin * CO; i += PW_T) {
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const PwArgs A) {
   __syncthreads();
   const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
   const long long o = (long long)blockIdx.x * PW_T + threadIdx.x;
-  if (o >= nvox) return;
+  if (o >= nvox) return;     // never taken when moments are fused (host guarantees V % PW_T == 0)
   long long big_idx = o;
   int n;
   {
@@ -120,6 +123,12 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const PwArgs A) {
       }
       v[e] = t;
     }
+    if (A.moments) {
+      float ms[4], mq[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ms[e] = v[e]; mq[e] = v[e] * v[e]; }
+      warp_moments_add(sm_mom, j4 * 4, ms, mq);
+    }
     if (vec_out) {
       float4 r = make_float4(v[0], v[1], v[2], v[3]);
       if (A.accumulate) {
@@ -134,6 +143,12 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const PwArgs A) {
         if (c < A.Cout) pd[j4 * 4 + e] = A.accumulate ? pd[j4 * 4 + e] + v[e] : v[e];
       }
     }
+  }
+  if (A.moments) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CO; i += PW_T)
+      if (co0 + i / 2 < A.Cout)
+        atomicAdd(&A.moments[((long long)n * A.Cout + co0) * 2 + i], sm_mom[i]);
   }
 }
 
@@ -259,7 +274,9 @@ static int launch_pointwise(const PwArgs& A, cudaStream_t st) {
 // entry points used by conv_direct.cu; NAS3D_ERR_UNSUPPORTED = "not my shape" (no error text)
 int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
                   const float* scale, int relu, int sigmoid, float* small, int accumulate,
-                  cudaStream_t st) {
+                  double* moments, cudaStream_t st) {
+  if (moments && (((long long)d->Ds * d->Hs * d->Ws) % PW_T != 0 || accumulate || sigmoid))
+    return NAS3D_ERR_UNSUPPORTED;
   if (d->Cb % 4 == 0 && d->ld_big % 4 == 0 && !aligned16(big)) return NAS3D_ERR_UNSUPPORTED;
   PwArgs A{};
   A.src = big; A.w = w; A.bias = bias; A.scale = scale; A.mask = nullptr; A.dst = small;
@@ -267,6 +284,7 @@ int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, co
   A.Cin = d->Cb; A.Cout = d->Cs; A.ld_src = d->ld_big; A.ld_dst = d->ld_small; A.ld_mask = 0;
   A.stride = d->stride; A.relu = relu; A.sigmoid = sigmoid; A.accumulate = accumulate;
   A.w_stride_in = 1; A.w_stride_out = d->Cb;      // W[cs][cb]: in = cb, out = cs
+  A.moments = moments;
   if (d->ld_small % 4 == 0 && !aligned16(small)) return NAS3D_ERR_UNSUPPORTED;
   return launch_pointwise<true>(A, st);
 }

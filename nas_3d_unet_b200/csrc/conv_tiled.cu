@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);
   float* wsm = reinterpret_cast<float*>(smem_raw + sizeof(float4) * TS::PLANE * C4);
+  __shared__ double sm_mom[2 * C];
+  if (threadIdx.x < 2 * C) sm_mom[threadIdx.x] = 0.0;
 
   int b = blockIdx.x;
   const int tw = b % A.tiles_w; b /= A.tiles_w;
@@ -147,25 +149,34 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (A.bias) bias4 = ldg4(A.bias + cg * 4);
   const int gw = w0 + tx;
-  if (gw >= A.W) return;
-  float* yb = A.y + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + cg * 4;
+  float ms[4] = {0.f, 0.f, 0.f, 0.f}, mq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (gw < A.W) {
+    float* yb = A.y + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + cg * 4;
 #pragma unroll
-  for (int od = 0; od < MD; ++od) {
-    const int gd = d0 + dg * MD + od;
-    if (gd >= A.D) break;
+    for (int od = 0; od < MD; ++od) {
+      const int gd = d0 + dg * MD + od;
+      if (gd >= A.D) break;
 #pragma unroll
-    for (int oh = 0; oh < 4; ++oh) {
-      const int gh = h0 + hg * 4 + oh;
-      if (gh >= A.H) break;
-      float* p = yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy;
-      float4 v = make_float4(acc[od][oh][0] + bias4.x, acc[od][oh][1] + bias4.y,
-                             acc[od][oh][2] + bias4.z, acc[od][oh][3] + bias4.w);
-      if (A.accumulate) {
-        const float4 o = *reinterpret_cast<const float4*>(p);
-        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      for (int oh = 0; oh < 4; ++oh) {
+        const int gh = h0 + hg * 4 + oh;
+        if (gh >= A.H) break;
+        float* p = yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy;
+        float4 v = make_float4(acc[od][oh][0] + bias4.x, acc[od][oh][1] + bias4.y,
+                               acc[od][oh][2] + bias4.z, acc[od][oh][3] + bias4.w);
+        if (A.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(p);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        st4(p, v);
+        ms[0] += v.x; ms[1] += v.y; ms[2] += v.z; ms[3] += v.w;
+        mq[0] += v.x * v.x; mq[1] += v.y * v.y; mq[2] += v.z * v.z; mq[3] += v.w * v.w;
       }
-      st4(p, v);
     }
+  }
+  if (A.moments) {      // uniform per launch
+    warp_moments_add(sm_mom, cg * 4, ms, mq);
+    __syncthreads();
+    cta_moments_flush(sm_mom, A.moments, n, C, TS::THREADS);
   }
 }
 

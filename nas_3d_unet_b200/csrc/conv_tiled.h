@@ -20,6 +20,7 @@ struct TiledArgs {
   int xs, Dx, Hx, Wx;
   int ys, Dy, Hy, Wy;
   int tiles_w, tiles_h, tiles_d;
+  double* moments;     // optional [N][C][2] {sum, sum^2} of the written output (fused GN stats)
 };
 
 struct WgradArgs {
@@ -48,6 +49,7 @@ struct S2Args {
   int Ds, Hs, Ws, Cs, ld_small;
   int accumulate;
   int tiles_w, tiles_h, tiles_d;
+  double* moments;     // optional fused GN statistics of the produced tensor
 };
 int tiled_s2_sfb(const S2Args& A, cudaStream_t st);
 int tiled_s2_bfs(const S2Args& A, cudaStream_t st);

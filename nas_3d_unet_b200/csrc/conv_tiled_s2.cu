@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);
   float* wsm = reinterpret_cast<float*>(smem_raw + sizeof(float4) * TS::PLANE * C4I);
+  __shared__ double sm_mom[2 * COUT];
+  if (threadIdx.x < 2 * COUT) sm_mom[threadIdx.x] = 0.0;
 
   int b = blockIdx.x;
   const int tw = b % A.tiles_w; b /= A.tiles_w;
@@ -131,20 +133,29 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (A.bias) bias4 = ldg4(A.bias + cg * 4);
   const int gw = w0 + tx, gd = d0 + dg;
-  if (gw >= A.Ws || gd >= A.Ds) return;
-  float* yb = A.small + (long long)n * A.Ds * A.Hs * A.Ws * A.ld_small + cg * 4;
+  float ms[4] = {0.f, 0.f, 0.f, 0.f}, mq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (gw < A.Ws && gd < A.Ds) {
+    float* yb = A.small + (long long)n * A.Ds * A.Hs * A.Ws * A.ld_small + cg * 4;
 #pragma unroll
-  for (int oh = 0; oh < 4; ++oh) {
-    const int gh = h0 + hg * 4 + oh;
-    if (gh >= A.Hs) break;
-    float* p = yb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small;
-    float4 v = make_float4(acc[oh][0] + bias4.x, acc[oh][1] + bias4.y, acc[oh][2] + bias4.z,
-                           acc[oh][3] + bias4.w);
-    if (A.accumulate) {
-      const float4 o = *reinterpret_cast<const float4*>(p);
-      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    for (int oh = 0; oh < 4; ++oh) {
+      const int gh = h0 + hg * 4 + oh;
+      if (gh >= A.Hs) break;
+      float* p = yb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small;
+      float4 v = make_float4(acc[oh][0] + bias4.x, acc[oh][1] + bias4.y, acc[oh][2] + bias4.z,
+                             acc[oh][3] + bias4.w);
+      if (A.accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(p);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      st4(p, v);
+      ms[0] += v.x; ms[1] += v.y; ms[2] += v.z; ms[3] += v.w;
+      mq[0] += v.x * v.x; mq[1] += v.y * v.y; mq[2] += v.z * v.z; mq[3] += v.w * v.w;
     }
-    st4(p, v);
+  }
+  if (A.moments) {
+    warp_moments_add(sm_mom, cg * 4, ms, mq);
+    __syncthreads();
+    cta_moments_flush(sm_mom, A.moments, n, COUT, TS::THREADS);
   }
 }
 
@@ -168,6 +179,8 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);
   float* wsm = reinterpret_cast<float*>(smem_raw + sizeof(float4) * TS::PLANE * C4);
+  __shared__ double sm_mom[2 * C];
+  if (threadIdx.x < 2 * C) sm_mom[threadIdx.x] = 0.0;
 
   int b = blockIdx.x;
   const int tw = b % A.tiles_w; b /= A.tiles_w;
@@ -263,25 +276,34 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (A.bias) bias4 = ldg4(A.bias + cg * 4);
   const int gd = d0 + dp;
-  if (gd >= A.Db) return;
-  float* yb = A.big + (long long)n * A.Db * A.Hb * A.Wb * A.ld_big + cg * 4;
+  float ms[4] = {0.f, 0.f, 0.f, 0.f}, mq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (gd < A.Db) {
+    float* yb = A.big + (long long)n * A.Db * A.Hb * A.Wb * A.ld_big + cg * 4;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int gh = h0 + hg * 4 + r;
-    if (gh >= A.Hb) break;
+    for (int r = 0; r < 4; ++r) {
+      const int gh = h0 + hg * 4 + r;
+      if (gh >= A.Hb) break;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int gw = w0 + 2 * tx + e;
-      if (gw >= A.Wb) continue;
-      float* p = yb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big;
-      float4 v = make_float4(acc[r][e][0] + bias4.x, acc[r][e][1] + bias4.y, acc[r][e][2] + bias4.z,
-                             acc[r][e][3] + bias4.w);
-      if (A.accumulate) {
-        const float4 o = *reinterpret_cast<const float4*>(p);
-        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      for (int e = 0; e < 2; ++e) {
+        const int gw = w0 + 2 * tx + e;
+        if (gw >= A.Wb) continue;
+        float* p = yb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big;
+        float4 v = make_float4(acc[r][e][0] + bias4.x, acc[r][e][1] + bias4.y,
+                               acc[r][e][2] + bias4.z, acc[r][e][3] + bias4.w);
+        if (A.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(p);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        st4(p, v);
+        ms[0] += v.x; ms[1] += v.y; ms[2] += v.z; ms[3] += v.w;
+        mq[0] += v.x * v.x; mq[1] += v.y * v.y; mq[2] += v.z * v.z; mq[3] += v.w * v.w;
       }
-      st4(p, v);
     }
+  }
+  if (A.moments) {
+    warp_moments_add(sm_mom, cg * 4, ms, mq);
+    __syncthreads();
+    cta_moments_flush(sm_mom, A.moments, n, C, TS::THREADS);
   }
 }
 

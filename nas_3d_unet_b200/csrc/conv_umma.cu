@@ -32,6 +32,7 @@ struct UmmaArgs {
   int bfs;                 // 0: src = big (pos = o*s - p + t*d) ; 1: src = small (pos = (o + p - t*d)/s)
   int accumulate;
   long long nvox;
+  double* moments;         // optional fused GN statistics (host guarantees V % 128 == 0)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -162,6 +163,8 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * US::STAGE_BYTES);   // empty[0], empty[1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * US::STAGE_BYTES + 32);
+  __shared__ double sm_mom[2 * NPROD];
+  if (threadIdx.x < 2 * NPROD) sm_mom[threadIdx.x] = 0.0;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
@@ -308,7 +311,18 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
       }
       st4(pd + c8 * 8, v0);
       st4(pd + c8 * 8 + 4, v1);
+      if (A.moments) {
+        const float s0[4] = {v0.x, v0.y, v0.z, v0.w}, s1[4] = {v1.x, v1.y, v1.z, v1.w};
+        const float q0[4] = {v0.x * v0.x, v0.y * v0.y, v0.z * v0.z, v0.w * v0.w};
+        const float q1[4] = {v1.x * v1.x, v1.y * v1.y, v1.z * v1.z, v1.w * v1.w};
+        warp_moments_add(sm_mom, c8 * 8, s0, q0);
+        warp_moments_add(sm_mom, c8 * 8 + 4, s1, q1);
+      }
     }
+  }
+  if (A.moments) {
+    __syncthreads();
+    cta_moments_flush(sm_mom, A.moments, n, NPROD, 128);
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -372,7 +386,7 @@ int nas3d_umma_pack_weights(const nas3d_conv_desc* d, const float* w, int produc
 
 int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
                     const float* packed_w, const float* bias, float* dst, int accumulate,
-                    void* stream) {
+                    double* moments, void* stream) {
   NAS3D_REQUIRE(nas3d_umma_packed_floats(d, produce_big) > 0, "umma_conv: unsupported conv shape");
   NAS3D_REQUIRE(d->ld_big % 4 == 0 && d->ld_small % 4 == 0 && aligned16(src) && aligned16(dst) &&
                     aligned16(packed_w),
@@ -396,12 +410,21 @@ int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
   A.bfs = produce_big ? 1 : 0;
   A.accumulate = accumulate;
   A.nvox = (long long)d->N * A.Dd * A.Hd * A.Wd;
+  const long long V = (long long)A.Dd * A.Hd * A.Wd;
+  const bool fuse = moments != nullptr && V % 128 == 0;
+  A.moments = fuse ? moments : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  if (fuse)
+    NAS3D_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)d->N * (produce_big ? d->Cb : d->Cs), st));
+  int rc;
   switch (d->Cb) {
-    case 16: return launch_umma<16, 16>(A, st);
-    case 32: return launch_umma<32, 32>(A, st);
-    default: return launch_umma<64, 64>(A, st);
+    case 16: rc = launch_umma<16, 16>(A, st); break;
+    case 32: rc = launch_umma<32, 32>(A, st); break;
+    default: rc = launch_umma<64, 64>(A, st); break;
   }
+  if (rc == NAS3D_OK && moments && !fuse)     // tile straddles samples: separate statistics pass
+    rc = nas3d_moments_nc(dst, d->N, V, produce_big ? d->Cb : d->Cs, A.ldd, moments, stream);
+  return rc;
 }
 
 }  // extern "C"

@@ -49,11 +49,12 @@ def _require_cuda(t, what):
 # activations
 # ----------------------------------------------------------------------------------------
 class Act:
-    __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad")
+    __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad", "S")
 
     def __init__(self, t, ld, requires_grad=True):
         self.t = t
         self.g = None
+        self.S = None      # per-(n,c) fp64 {sum, sum^2} if a producer kernel already computed them
         self.N, self.C, self.D, self.H, self.W = t.shape
         self.ld = ld
         self.requires_grad = requires_grad
@@ -357,7 +358,7 @@ def gn_term(ctx, x, norm, relu):
     if norm.num_channels != x.C:
         raise ValueError("GroupNorm expects %d channels, got %d" % (norm.num_channels, x.C))
     ctx.use(norm.weight, norm.bias)
-    S = moments(ctx, x)
+    S = x.S if x.S is not None else moments(ctx, x)
     G = norm.num_groups
     ab = torch.empty((2, x.N, x.C), device=ctx.device, dtype=torch.float32)
     mr = torch.empty((x.N, G, 2), device=ctx.device, dtype=torch.float32)
@@ -464,7 +465,7 @@ def _umma_packed(ctx, d, m, produce_big):
     return wp
 
 
-def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False):
+def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False, stats=False):
     """y = conv(f(x)) with f = optional relu / per-(n,c) scale prologue; returns the raw Act.
 
     Conv3d forward is the small-from-big gather, ConvTranspose3d forward the big-from-small
@@ -477,16 +478,21 @@ def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False):
                 ctx.device)
     bias = m.bias.data_ptr() if m.bias is not None else None
     plain = not (in_relu or in_scale is not None or sigmoid)
+    S = None
+    if stats:    # GroupNorm follows: let the conv epilogue produce its statistics
+        S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)
+        y.S = S
+    Sp = _tp(S)
     if not spec.transposed:
         d = _desc(spec, x, y)
         wp = _umma_packed(ctx, d, m, 0) if plain else None
         if wp is not None:
-            check(lib.nas3d_umma_conv(C.byref(d), 0, x.ptr, wp.data_ptr(), bias, y.ptr, 0,
+            check(lib.nas3d_umma_conv(C.byref(d), 0, x.ptr, wp.data_ptr(), bias, y.ptr, 0, Sp,
                                       ctx.stream), "umma_conv fwd")
         else:
             check(lib.nas3d_conv_small_from_big(C.byref(d), x.ptr, m.weight.data_ptr(), bias,
                                                 _tp(in_scale), 1 if in_relu else 0,
-                                                1 if sigmoid else 0, y.ptr, 0, ctx.stream),
+                                                1 if sigmoid else 0, y.ptr, 0, Sp, ctx.stream),
                   "conv_small_from_big")
     else:
         if not plain:
@@ -494,11 +500,11 @@ def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False):
         d = _desc(spec, y, x)
         wp = _umma_packed(ctx, d, m, 1)
         if wp is not None:
-            check(lib.nas3d_umma_conv(C.byref(d), 1, x.ptr, wp.data_ptr(), bias, y.ptr, 0,
+            check(lib.nas3d_umma_conv(C.byref(d), 1, x.ptr, wp.data_ptr(), bias, y.ptr, 0, Sp,
                                       ctx.stream), "umma_conv convT fwd")
         else:
             check(lib.nas3d_conv_big_from_small(C.byref(d), x.ptr, m.weight.data_ptr(), bias, None,
-                                                0, None, y.ptr, 0, ctx.stream),
+                                                0, None, y.ptr, 0, Sp, ctx.stream),
                   "conv_big_from_small")
     ctx.push(lambda: _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid))
     return y
@@ -531,11 +537,12 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
             wp = _umma_packed(ctx, d2, m, 1) if not (in_relu or in_scale is not None) else None
             if wp is not None:
                 check(lib.nas3d_umma_conv(C.byref(d2), 1, dy.ptr, wp.data_ptr(), None, gv.ptr, acc,
-                                          st), "umma_conv dgrad")
+                                          None, st), "umma_conv dgrad")
             else:
                 check(lib.nas3d_conv_big_from_small(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
                                                     x.ptr if in_relu else None, x.ld,
-                                                    _tp(in_scale), gv.ptr, acc, st), "conv dgrad")
+                                                    _tp(in_scale), gv.ptr, acc, None, st),
+                      "conv dgrad")
     else:
         d = _desc(spec, dy, x)
         check(lib.nas3d_conv_wgrad(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, st),
@@ -547,10 +554,11 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
             wp = _umma_packed(ctx, d2, m, 0)
             if wp is not None:
                 check(lib.nas3d_umma_conv(C.byref(d2), 0, dy.ptr, wp.data_ptr(), None, gv.ptr, acc,
-                                          st), "umma_conv convT dgrad")
+                                          None, st), "umma_conv convT dgrad")
             else:
                 check(lib.nas3d_conv_small_from_big(C.byref(d2), dy.ptr, m.weight.data_ptr(), None,
-                                                    None, 0, 0, gv.ptr, acc, st), "convT dgrad")
+                                                    None, 0, 0, gv.ptr, acc, None, st),
+                      "convT dgrad")
 
 
 # ----------------------------------------------------------------------------------------

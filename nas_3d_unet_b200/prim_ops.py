@@ -99,6 +99,9 @@ class BaseOp(nn.Module):
                     src = engine.materialize(ctx, Term(src, scale, None, in_relu, "coef"))
                     in_relu, scale = False, None
                 last = pos == len(self.ops_list) - 1
+                # GroupNorm right after the weight op: its statistics come out of the conv epilogue
+                self._want_stats = (not last and self.ops_list[pos + 1] == 'norm'
+                                    and self.norm is not None)
                 state = self._weight_run(ctx, src, in_relu, scale, sigmoid and last)
             elif op == 'norm':
                 if self.norm is not None:
@@ -117,6 +120,7 @@ class BaseOp(nn.Module):
         return state
 
     _fuses_prologue = False
+    _want_stats = False
 
 
 class ConvOps(BaseOp):
@@ -153,10 +157,11 @@ class ConvOps(BaseOp):
     def _weight_run(self, ctx, x, in_relu, in_scale, sigmoid):
         if self.depthwised:
             mid = engine.conv(ctx, x, self.depth_conv, self._specs[0])
-            y = engine.conv(ctx, mid, self.point_conv, self._specs[1], sigmoid=sigmoid)
+            y = engine.conv(ctx, mid, self.point_conv, self._specs[1], sigmoid=sigmoid,
+                            stats=self._want_stats)
         else:
             y = engine.conv(ctx, x, self.conv, self._specs[0], in_relu=in_relu, in_scale=in_scale,
-                            sigmoid=sigmoid)
+                            sigmoid=sigmoid, stats=self._want_stats)
         return Term(y)
 
 
@@ -190,7 +195,8 @@ class SEConvOp(BaseOp):
         if self.stride < 2:
             return scaled
         xs = engine.materialize(ctx, scaled)
-        return Term(engine.conv(ctx, xs, self.conv, self._spec, sigmoid=sigmoid))
+        return Term(engine.conv(ctx, xs, self.conv, self._spec, sigmoid=sigmoid,
+                                stats=self._want_stats))
 
 
 class PoolingOp(BaseOp):
