@@ -314,3 +314,35 @@ def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
         assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
         assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
         assert O.max_rel(op.conv.bias.grad, sd['conv.bias'].grad) <= 1e-4, mode
+
+
+def test_cuda_graph_step_matches_eager_steps():
+    """GraphedStep (whole train.py:121-128 step captured in one CUDA graph) reproduces the eager
+    step sequence: same losses step by step (fp32 atomics => tiny tolerance)"""
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    from nas_3d_unet_b200.graph import GraphedStep
+    x, y = O.synthetic_batch(2, 32, seed=21)
+    x, y = x.cuda(), y.cuda()
+
+    def make():
+        m = make_searched().cuda()
+        m.train()
+        m.last_conv[0].dropout.p = 0.0
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+        lossf = WeightedDiceLoss()
+
+        def step(xx, yy):
+            opt.zero_grad(set_to_none=True)
+            loss = lossf(m(xx), yy)
+            loss.backward()
+            opt.step()
+            return loss
+        return m, step
+
+    _, step = make()
+    eager = [step(x, y).item() for _ in range(6)]
+    m2, step2 = make()
+    g = GraphedStep(step2, (x, y), warmup=3)          # 3 real eager steps; capture executes nothing
+    replayed = [g(x, y).item() for _ in range(2)]     # steps 4 and 5
+    assert eager[0] > eager[-1]                        # it trains
+    np.testing.assert_allclose(replayed, eager[3:5], rtol=0, atol=2e-5)
