@@ -50,6 +50,10 @@ static int tiled_kind(const nas3d_conv_desc* d, bool wgrad = false) {
 static bool s2d1_shape(const nas3d_conv_desc* d) {
   return tiled_enabled() && d->k == 3 && d->stride == 2 && d->dil == 1 && d->pad == 1 && !d->depthwise;
 }
+static bool dw3_shape(const nas3d_conv_desc* d) {
+  return tiled_enabled() && d->depthwise && d->k == 3 && d->dil == 1 && d->pad == 1 &&
+         (d->stride == 1 || d->stride == 2) && d->Cb == d->Cs;
+}
 static S2Args s2_args(const nas3d_conv_desc* d, const float* big, const float* small, const float* w) {
   S2Args A{};
   A.big = const_cast<float*>(big); A.small = const_cast<float*>(small); A.w = w;
@@ -560,6 +564,20 @@ int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const 
     if (rc != NAS3D_ERR_UNSUPPORTED)
       return rc ? rc : moments_fallback(moments, small, d->N, Vs, d->Cs, d->ld_small, stream);
   }
+  if (dw3_shape(d) && !big_scale && !big_relu && !out_sigmoid) {
+    if (d->stride == 1) {
+      TiledArgs T{};
+      T.x = big; T.w = w; T.bias = bias; T.y = small; T.accumulate = accumulate;
+      T.N = d->N; T.D = d->Ds; T.H = d->Hs; T.W = d->Ws; T.ldx = d->ld_big; T.ldy = d->ld_small;
+      rc = tiled_dw_s1(false, T, d->Cb, (cudaStream_t)stream);
+    } else {
+      S2Args S = s2_args(d, big, small, w);
+      S.bias = bias; S.accumulate = accumulate;
+      rc = tiled_dw_s2_sfb(S, (cudaStream_t)stream);
+    }
+    if (rc != NAS3D_ERR_UNSUPPORTED)
+      return rc ? rc : moments_fallback(moments, small, d->N, Vs, d->Cs, d->ld_small, stream);
+  }
   if (s2d1_shape(d) && !big_scale && !big_relu && !out_sigmoid) {
     S2Args S = s2_args(d, big, small, w);
     S.bias = bias; S.accumulate = accumulate; S.moments = moments;
@@ -591,6 +609,20 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
   if (pointwise_shape(d)) {
     rc = pointwise_bfs(d, small, w, bias, mask_big, ld_mask, big_scale, big, accumulate,
                        (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED)
+      return rc ? rc : moments_fallback(moments, big, d->N, Vb, d->Cb, d->ld_big, stream);
+  }
+  if (dw3_shape(d) && !big_scale && !mask_big) {
+    if (d->stride == 1) {
+      TiledArgs T{};
+      T.x = small; T.w = w; T.bias = bias; T.y = big; T.accumulate = accumulate;
+      T.N = d->N; T.D = d->Db; T.H = d->Hb; T.W = d->Wb; T.ldx = d->ld_small; T.ldy = d->ld_big;
+      rc = tiled_dw_s1(true, T, d->Cb, (cudaStream_t)stream);
+    } else {
+      S2Args S = s2_args(d, big, small, w);
+      S.bias = bias; S.accumulate = accumulate;
+      rc = tiled_dw_s2_bfs(S, (cudaStream_t)stream);
+    }
     if (rc != NAS3D_ERR_UNSUPPORTED)
       return rc ? rc : moments_fallback(moments, big, d->N, Vb, d->Cb, d->ld_big, stream);
   }
@@ -639,6 +671,14 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
   bool done = false;
   if (pointwise_shape(d)) {
     rc = pointwise_wgrad(d, small, big, big_scale, big_relu, dW, d_bias_small, st);
+    if (rc == NAS3D_OK) done = true;
+    else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    rc = NAS3D_OK;
+  }
+  if (!done && dw3_shape(d) && !big_scale && !big_relu) {
+    S2Args S = s2_args(d, big, small, nullptr);
+    S.dW = dW; S.dbias_small = d_bias_small;
+    rc = tiled_dw_wgrad(S, d->stride, st);
     if (rc == NAS3D_OK) done = true;
     else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
     rc = NAS3D_OK;

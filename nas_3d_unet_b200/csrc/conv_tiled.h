@@ -55,6 +55,12 @@ int tiled_s2_sfb(const S2Args& A, cudaStream_t st);
 int tiled_s2_bfs(const S2Args& A, cudaStream_t st);
 int tiled_s2_wgrad(const S2Args& A, cudaStream_t st);
 
+// depthwise 3x3x3 (conv_tiled_dw.cu); wgrad uses S2Args also for stride 1 (big == small extents)
+int tiled_dw_s1(bool flip, const TiledArgs& A, int C, cudaStream_t st);
+int tiled_dw_s2_sfb(const S2Args& A, cudaStream_t st);
+int tiled_dw_s2_bfs(const S2Args& A, cudaStream_t st);
+int tiled_dw_wgrad(const S2Args& A, int stride, cudaStream_t st);
+
 // return NAS3D_ERR_UNSUPPORTED (without error text) when the shape is not covered
 int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st);
 int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st);

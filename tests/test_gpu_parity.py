@@ -346,3 +346,37 @@ def test_cuda_graph_step_matches_eager_steps():
     replayed = [g(x, y).item() for _ in range(2)]     # steps 4 and 5
     assert eager[0] > eager[-1]                        # it trains
     np.testing.assert_allclose(replayed, eager[3:5], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("c", [4, 8, 16])
+@pytest.mark.parametrize("stride,transposed", [(1, False), (2, False), (2, True)])
+def test_tiled_depthwise_kernels_match_oracle(c, stride, transposed):
+    """depthwise-separable ops (dep_conv / down_dep_conv / up_dep_conv): tiled depthwise kernels
+    (fwd, dgrad, wgrad) + pointwise conv, ragged extents, against the oracle and the generic path"""
+    import os
+    from nas_3d_unet_b200.prim_ops import ConvOps
+    torch.manual_seed(c * 5 + stride + transposed)
+    op = ConvOps(c, c, stride=stride, transposed=transposed, depthwised=True, ops_order='weight')
+    g = torch.Generator().manual_seed(c + stride)
+    shape = (5, 6, 18) if transposed else (10, 12, 36)
+    x = torch.randn(2, c, *shape, generator=g)
+    sd = O.leaf_state(op.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = O.conv_ops(sd, '', xr, 3, stride, 1, transposed, depthwise=True, order='weight')
+    r = torch.randn(yr.shape, generator=g)
+    (yr * r).sum().backward()
+    op = op.cuda()
+    for mode in ("tiled", "generic"):
+        os.environ["NAS3D_DISABLE_TILED"] = "1" if mode == "generic" else "0"
+        try:
+            op.zero_grad()
+            xg = x.cuda().requires_grad_(True)
+            y = op(xg)
+            (y * r.cuda()).sum().backward()
+        finally:
+            os.environ["NAS3D_DISABLE_TILED"] = "0"
+        assert O.max_rel(y, yr) <= 1e-5, mode
+        assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
+        for k in ('depth_conv.weight', 'depth_conv.bias', 'point_conv.weight', 'point_conv.bias'):
+            mod, par = k.split('.')
+            assert O.max_rel(getattr(getattr(op, mod), par).grad, sd[k].grad) <= 1e-4, (mode, k)
