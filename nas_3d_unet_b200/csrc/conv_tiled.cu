@@ -22,6 +22,9 @@
 //   wgrad   : dW[co][ci][tap] += sum_o dy[o,co] * x[o - pad + tap*dil, ci]
 // lanes <-> taps: lane t < 27 owns the 4x4 (ci,co) block of tap t for the warp's voxels, so no
 // cross-lane reduction is needed until the end; lane 27 accumulates the bias gradient.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "conv_tiled.h"
 
@@ -47,15 +50,20 @@ struct TileShape {
   static constexpr size_t SMEM = sizeof(float4) * PLANE * C4 + sizeof(float) * 27 * C * C;
 };
 
-template <int C, int DIL, int HG, int DG, int MD, bool FLIP>
+// TMA = true: the haloed input tile is fetched by ONE elected thread with
+// cp.async.bulk.tensor.5d (box {4 ch, PW, PH, PD, 1 sample} of the NDHWC tensor map, signed start
+// coordinates, hardware zero-fill outside the volume = the conv padding) and lands on an mbarrier;
+// no per-element address arithmetic is left in the instruction stream of this issue-bound kernel.
+template <int C, int DIL, int HG, int DG, int MD, bool FLIP, bool TMA>
 __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
-    conv3_s1_kernel(const TiledArgs A) {
+    conv3_s1_kernel(const TiledArgs A, const __grid_constant__ CUtensorMap tmap) {
   using TS = TileShape<C, DIL, HG, DG, MD>;
   constexpr int C4 = TS::C4, PW = TS::PW, PH = TS::PH, PD = TS::PD, NR = TS::NR;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);
   float* wsm = reinterpret_cast<float*>(smem_raw + sizeof(float4) * TS::PLANE * C4);
   __shared__ double sm_mom[2 * C];
+  __shared__ __align__(8) unsigned long long tma_bar;
   if (threadIdx.x < 2 * C) sm_mom[threadIdx.x] = 0.0;
 
   int b = blockIdx.x;
@@ -74,21 +82,52 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
     wsm[i] = __ldg(A.w + gi);
   }
   // ---- stage the input tile + halo ------------------------------------------------------
-  const float* xb = A.x + (long long)n * A.Dx * A.Hx * A.Wx * A.ldx;
-  for (int i = threadIdx.x; i < TS::PLANE * C4; i += TS::THREADS) {
-    const int cc = i % C4;
-    int r = i / C4;
-    const int pw = r % PW; r /= PW;
-    const int ph = r % PH;
-    const int pd = r / PH;
-    const int gd = d0 - DIL + pd, gh = h0 - DIL + ph, gw = w0 - DIL + pw;
-    const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
-    const float* src =
-        ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx + cc * 4 : A.x;
-    cp_async16(&tile[cc * TS::PLANE + (pd * PH + ph) * PW + pw], src, ok);
+  if constexpr (TMA) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                   "r"((unsigned)(sizeof(float4) * TS::PLANE * C4))
+                   : "memory");
+#pragma unroll
+      for (int cc = 0; cc < C4; ++cc) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + cc * TS::PLANE);
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
+            "l"(&tmap), "r"(cc * 4), "r"(w0 - DIL), "r"(h0 - DIL), "r"(d0 - DIL), "r"(n), "r"(bar)
+            : "memory");
+      }
+    }
+    __syncthreads();     // barrier init visible to the waiters; weights staged
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TMA_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra TMA_DONE;\n\t"
+        "bra TMA_WAIT;\n\t"
+        "TMA_DONE:\n\t"
+        "}\n" ::"r"(bar)
+        : "memory");
+  } else {
+    const float* xb = A.x + (long long)n * A.Dx * A.Hx * A.Wx * A.ldx;
+    for (int i = threadIdx.x; i < TS::PLANE * C4; i += TS::THREADS) {
+      const int cc = i % C4;
+      int r = i / C4;
+      const int pw = r % PW; r /= PW;
+      const int ph = r % PH;
+      const int pd = r / PH;
+      const int gd = d0 - DIL + pd, gh = h0 - DIL + ph, gw = w0 - DIL + pw;
+      const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
+      const float* src =
+          ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx + cc * 4 : A.x;
+      cp_async16(&tile[cc * TS::PLANE + (pd * PH + ph) * PW + pw], src, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
   }
-  cp_async_wait_all();
-  __syncthreads();
 
   // ---- compute ----------------------------------------------------------------------------
   const int tx = threadIdx.x & 31;
@@ -355,6 +394,41 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP>::THREADS)
   if (A.dbias && cic == 0 && threadIdx.x < 4) atomicAdd(A.dbias + coc * 4 + threadIdx.x, red[27 * 16 + threadIdx.x]);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    const char* e = getenv("NAS3D_DISABLE_TMA");
+    if (e && e[0] == '1') fn = nullptr;
+  }
+  return fn;
+}
+
+// 5-D map of an NDHWC fp32 tensor {C, W, H, D, N} with voxel pitch ld, box {4, bw, bh, bd, 1}
+static bool make_ndhwc_map(CUtensorMap* m, const float* base, int C, int W, int H, int D, int N,
+                           int ld, int bw, int bh, int bd) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4,
+                                 (cuuint64_t)D * H * W * ld * 4};
+  const cuuint32_t box[5] = {4, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int C, int DIL, int HG, int DG, int MD, bool FLIP>
 static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   using TS = TileShape<C, DIL, HG, DG, MD>;
@@ -362,14 +436,21 @@ static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   A.tiles_w = (A.W + TS::TW - 1) / TS::TW;
   A.tiles_h = (A.H + TS::TH - 1) / TS::TH;
   A.tiles_d = (A.D + TS::TD - 1) / TS::TD;
-  auto kern = conv3_s1_kernel<C, DIL, HG, DG, MD, FLIP>;
+  auto kern_tma = conv3_s1_kernel<C, DIL, HG, DG, MD, FLIP, true>;
+  auto kern_cp = conv3_s1_kernel<C, DIL, HG, DG, MD, FLIP, false>;
   static bool attr_done = false;
   if (!attr_done) {
-    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM));
+    NAS3D_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM));
+    NAS3D_CUDA(cudaFuncSetAttribute(kern_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM));
     attr_done = true;
   }
   const long long blocks = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
-  kern<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const bool tma = A.xs == 1 && (TS::PLANE % 8 == 0 || TS::C4 == 1) &&
+                   make_ndhwc_map(&tmap, A.x, C, A.W, A.H, A.D, A.N, A.ldx, TS::PW, TS::PH, TS::PD);
+  if (tma) kern_tma<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A, tmap);
+  else kern_cp<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A, tmap);
   return launched("conv3_s1");
 }
 
