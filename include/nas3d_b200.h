@@ -99,6 +99,24 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
                      float* d_bias_big, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * 1x1x1 convolutions over a VIRTUAL CONCAT: the big tensor is `nparts` (<= 4) dense parts of
+ * Cb/nparts channels each (the node outputs of a cell, cell.py:82) that are never copied into
+ * one buffer.  Consumers of a cell output are always 1x1x1 convs (cell.py:47-50, nas.py:50).
+ * Host arrays of length nparts: part pointers, pitches, per-part accumulate flags.
+ * ------------------------------------------------------------------------------------- */
+int nas3d_conv1x1_cat_fwd(const nas3d_conv_desc* d, int nparts, const float* const* big_parts,
+                          const int* part_ld, const float* w, const float* bias,
+                          const float* big_scale, int big_relu, int out_sigmoid, float* small,
+                          double* moments, void* stream);
+int nas3d_conv1x1_cat_dgrad(const nas3d_conv_desc* d, int nparts, float* const* dbig_parts,
+                            const int* part_ld, const int* accumulate, const float* small,
+                            const float* w, const float* const* mask_parts, const int* mask_ld,
+                            const float* big_scale, void* stream);
+int nas3d_conv1x1_cat_wgrad(const nas3d_conv_desc* d, int nparts, const float* const* big_parts,
+                            const int* part_ld, const float* small, const float* big_scale,
+                            int big_relu, float* dW, float* d_bias_small, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Tensor-core path (tcgen05.mma kind::tf32, fp32 accumulators in TMEM, 3xTF32 error
  * compensation => fp32-grade results) for dense 3x3x3 convolutions with Cb == Cs in {16,32,64},
  * any stride / dilation, both gather directions (same conv view as above).

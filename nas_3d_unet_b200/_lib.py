@@ -38,6 +38,12 @@ _SIGNATURES = {
     "nas3d_conv_big_from_small": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
                                   c_int, c_vp, c_vp],
     "nas3d_conv_wgrad": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_conv1x1_cat_fwd": [C.POINTER(ConvDesc), c_int, _PP, _PI, c_vp, c_vp, c_vp, c_int, c_int,
+                              c_vp, c_vp, c_vp],
+    "nas3d_conv1x1_cat_dgrad": [C.POINTER(ConvDesc), c_int, _PP, _PI, _PI, c_vp, c_vp, _PP, _PI, c_vp,
+                                c_vp],
+    "nas3d_conv1x1_cat_wgrad": [C.POINTER(ConvDesc), c_int, _PP, _PI, c_vp, c_vp, c_int, c_vp, c_vp,
+                                c_vp],
     "nas3d_umma_packed_floats": [C.POINTER(ConvDesc), c_int],
     "nas3d_umma_pack_weights": [C.POINTER(ConvDesc), c_vp, c_int, c_vp, c_vp],
     "nas3d_umma_conv": [C.POINTER(ConvDesc), c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],

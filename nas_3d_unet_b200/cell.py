@@ -89,7 +89,7 @@ class Cell(nn.Module):
     def forward(self, x0, x1, alpha1, alpha2):
         return engine.run_module(self, (x0, x1), (alpha1, alpha2))
 
-    def _run(self, ctx, x0, x1, alpha1, alpha2):
+    def _run(self, ctx, x0, x1, alpha1, alpha2, virtual_cat=False):
         states = [engine.materialize(ctx, self.preprocess0._run(ctx, x0)),
                   engine.materialize(ctx, self.preprocess1._run(ctx, x1))]
         out = None
@@ -100,14 +100,21 @@ class Cell(nn.Module):
             for x in states:
                 terms += self._ops[edge]._terms(ctx, x, alpha1, alpha2, edge)
                 edge += 1
-            if out is None:
-                t0 = terms[0].x
-                out = engine.new_act(t0.N, self.out_channels, t0.D, t0.H, t0.W, ctx.device)
-            node = out.slice(j * self.c_node, (j + 1) * self.c_node)
+            t0 = terms[0].x
+            if virtual_cat:
+                # inside a net the concat is never materialised: the node is its own dense tensor
+                # and the next 1x1x1 conv reads the nodes as parts (engine.CatAct)
+                node = engine.new_act(t0.N, self.c_node, t0.D, t0.H, t0.W, ctx.device)
+            else:
+                if out is None:
+                    out = engine.new_act(t0.N, self.out_channels, t0.D, t0.H, t0.W, ctx.device)
+                node = out.slice(j * self.c_node, (j + 1) * self.c_node)
             engine.affine_sum(ctx, terms, node)
             nodes.append(node)
             states.append(node)
         if len(states) - 2 != self.n_nodes:
             raise AssertionError
+        if virtual_cat:
+            return engine.CatAct(nodes)
         engine.bind_concat(ctx, out, nodes, self.c_node)
         return out

@@ -16,16 +16,6 @@
 
 namespace nas3d {
 
-// conv_pointwise.cu
-int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
-                  const float* scale, int relu, int sigmoid, float* small, int accumulate,
-                  double* moments, cudaStream_t st);
-int pointwise_bfs(const nas3d_conv_desc* d, const float* small, const float* w, const float* bias,
-                  const float* mask_big, int ld_mask, const float* scale, float* big,
-                  int accumulate, cudaStream_t st);
-int pointwise_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,
-                    const float* scale, int relu, float* dW, float* dbias_small, cudaStream_t st);
-
 static bool tiled_enabled() {
   const char* e = getenv("NAS3D_DISABLE_TILED");   // read per call so tests can A/B the paths
   return !(e && e[0] == '1');
@@ -729,6 +719,57 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
         big, nvb, A.Cb, A.ldb, d_bias_big);
     rc = launched("colsum");
   }
+  return rc;
+}
+
+
+// ---- virtual-concat 1x1x1 convolutions (cell.py:82 without materialising the concat) ----------
+static int cat_check(const nas3d_conv_desc* d, int nparts) {
+  NAS3D_REQUIRE(d && d->k == 1 && d->pad == 0 && !d->depthwise, "conv1x1_cat: needs a dense 1x1x1 conv");
+  NAS3D_REQUIRE(nparts >= 1 && nparts <= 4 && d->Cb % nparts == 0 && (d->Cb / nparts) % 4 == 0,
+                "conv1x1_cat: %d parts of %d channels unsupported", nparts, d->Cb);
+  for (int ax = 0; ax < 3; ++ax) {
+    const int b = ax == 0 ? d->Db : ax == 1 ? d->Hb : d->Wb;
+    const int s = ax == 0 ? d->Ds : ax == 1 ? d->Hs : d->Ws;
+    NAS3D_REQUIRE(s == (b - 1) / d->stride + 1, "conv1x1_cat: extents %d / %d", b, s);
+  }
+  return NAS3D_OK;
+}
+
+int nas3d_conv1x1_cat_fwd(const nas3d_conv_desc* d, int nparts, const float* const* big_parts,
+                          const int* part_ld, const float* w, const float* bias,
+                          const float* big_scale, int big_relu, int out_sigmoid, float* small,
+                          double* moments, void* stream) {
+  int rc = cat_check(d, nparts);
+  if (rc) return rc;
+  PwCat cat{nparts, big_parts, nullptr, nullptr, part_ld, nullptr, nullptr};
+  rc = pointwise_sfb(d, nullptr, w, bias, big_scale, big_relu, out_sigmoid, small, 0, nullptr,
+                     (cudaStream_t)stream, &cat);
+  NAS3D_REQUIRE(rc != NAS3D_ERR_UNSUPPORTED, "conv1x1_cat_fwd: unsupported layout");
+  if (rc) return rc;
+  return moments_fallback(moments, small, d->N, (long long)d->Ds * d->Hs * d->Ws, d->Cs, d->ld_small, stream);
+}
+
+int nas3d_conv1x1_cat_dgrad(const nas3d_conv_desc* d, int nparts, float* const* dbig_parts,
+                            const int* part_ld, const int* accumulate, const float* small,
+                            const float* w, const float* const* mask_parts, const int* mask_ld,
+                            const float* big_scale, void* stream) {
+  int rc = cat_check(d, nparts);
+  if (rc) return rc;
+  PwCat cat{nparts, nullptr, dbig_parts, mask_parts, part_ld, mask_ld, accumulate};
+  rc = pointwise_bfs(d, small, w, nullptr, nullptr, 0, big_scale, nullptr, 0, (cudaStream_t)stream, &cat);
+  NAS3D_REQUIRE(rc != NAS3D_ERR_UNSUPPORTED, "conv1x1_cat_dgrad: unsupported layout");
+  return rc;
+}
+
+int nas3d_conv1x1_cat_wgrad(const nas3d_conv_desc* d, int nparts, const float* const* big_parts,
+                            const int* part_ld, const float* small, const float* big_scale,
+                            int big_relu, float* dW, float* d_bias_small, void* stream) {
+  int rc = cat_check(d, nparts);
+  if (rc) return rc;
+  PwCat cat{nparts, big_parts, nullptr, nullptr, part_ld, nullptr, nullptr};
+  rc = pointwise_wgrad(d, small, nullptr, big_scale, big_relu, dW, d_bias_small, (cudaStream_t)stream, &cat);
+  NAS3D_REQUIRE(rc != NAS3D_ERR_UNSUPPORTED, "conv1x1_cat_wgrad: unsupported layout");
   return rc;
 }
 

@@ -1,6 +1,7 @@
 // argument blocks of the tiled 3x3x3 kernels (conv_tiled.cu), shared with conv_direct.cu
 #pragma once
 #include <cuda_runtime.h>
+#include "../../include/nas3d_b200.h"
 
 namespace nas3d {
 
@@ -54,6 +55,26 @@ struct S2Args {
 int tiled_s2_sfb(const S2Args& A, cudaStream_t st);
 int tiled_s2_bfs(const S2Args& A, cudaStream_t st);
 int tiled_s2_wgrad(const S2Args& A, cudaStream_t st);
+
+// 1x1x1 convs (conv_pointwise.cu); cat != NULL: the big tensor is a virtual concat of dense parts
+struct PwCat {
+  int nparts;
+  const float* const* src;     // parts read as the big tensor (fwd, wgrad)
+  float* const* dst;           // parts written as the big gradient (dgrad)
+  const float* const* mask;    // relu-mask parts (dgrad), may be NULL
+  const int* ld;               // pitch of src / dst parts
+  const int* mask_ld;
+  const int* acc;              // per-part accumulate flags (dgrad)
+};
+int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
+                  const float* scale, int relu, int sigmoid, float* small, int accumulate,
+                  double* moments, cudaStream_t st, const PwCat* cat = nullptr);
+int pointwise_bfs(const nas3d_conv_desc* d, const float* small, const float* w, const float* bias,
+                  const float* mask_big, int ld_mask, const float* scale, float* big,
+                  int accumulate, cudaStream_t st, const PwCat* cat = nullptr);
+int pointwise_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,
+                    const float* scale, int relu, float* dW, float* dbias_small, cudaStream_t st,
+                    const PwCat* cat = nullptr);
 
 // depthwise 3x3x3 (conv_tiled_dw.cu); wgrad uses S2Args also for stride 1 (big == small extents)
 int tiled_dw_s1(bool flip, const TiledArgs& A, int C, cudaStream_t st);

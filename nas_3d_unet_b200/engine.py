@@ -79,6 +79,50 @@ class Act:
         return a
 
 
+def virtual_cat_enabled():
+    import os
+    return os.environ.get("NAS3D_VIRTUAL_CAT", "1") != "0"
+
+
+class CatAct:
+    """virtual concat along channels (cell.py:82): equal-width dense parts that are never copied
+    into one buffer.  Only 1x1x1 convolutions consume a cell output, and they read the parts."""
+    __slots__ = ("parts", "N", "C", "D", "H", "W", "requires_grad", "S")
+
+    def __init__(self, parts):
+        self.parts = parts
+        p0 = parts[0]
+        self.N, self.D, self.H, self.W = p0.N, p0.D, p0.H, p0.W
+        self.C = sum(p.C for p in parts)
+        self.requires_grad = any(p.requires_grad for p in parts)
+        self.S = None
+
+    @property
+    def V(self):
+        return self.D * self.H * self.W
+
+
+def materialize_cat(ctx, cat):
+    """copy the parts into one dense (N,C,D,H,W) buffer (module boundary only)"""
+    out = new_act(cat.N, cat.C, cat.D, cat.H, cat.W, ctx.device)
+    c0 = 0
+    slices = []
+    for p in cat.parts:
+        sl = out.slice(c0, c0 + p.C)
+        affine_sum(ctx, [Term(p)], sl)
+        slices.append(sl)
+        c0 += p.C
+    w = cat.parts[0].C
+
+    def bwd():
+        if out.g is None:
+            return
+        for j, sl in enumerate(slices):
+            sl.g = out.g[:, j * w:(j + 1) * w]
+    ctx.push(bwd)
+    return out
+
+
 def alloc(N, Cc, D, H, W, device):
     """logical (N,C,D,H,W) tensor, physical NDHWC dense"""
     return torch.empty((N, D, H, W, Cc), device=device, dtype=torch.float32).permute(0, 4, 1, 2, 3)
@@ -472,6 +516,12 @@ def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False, stats=Fal
     gather of the same conv view (include/nas3d_b200.h)."""
     if x.C != spec.cin:
         raise ValueError("conv expects %d input channels, got %d" % (spec.cin, x.C))
+    if isinstance(x, CatAct):
+        widths = {p.C for p in x.parts}
+        if (spec.k == 1 and not spec.transposed and not spec.depthwise and len(widths) == 1
+                and len(x.parts) <= 4 and x.parts[0].C % 4 == 0):
+            return _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats)
+        x = materialize_cat(ctx, x)
     lib = ctx.lib
     ctx.use(m.weight, m.bias)
     y = new_act(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
@@ -507,6 +557,69 @@ def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False, stats=Fal
                                                 0, None, y.ptr, 0, Sp, ctx.stream),
                   "conv_big_from_small")
     ctx.push(lambda: _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid))
+    return y
+
+
+def _cat_desc(spec, x, small):
+    d = ConvDesc()
+    d.N = x.N
+    d.Db, d.Hb, d.Wb, d.Cb, d.ld_big = x.D, x.H, x.W, x.C, x.C
+    d.Ds, d.Hs, d.Ws, d.Cs, d.ld_small = small.D, small.H, small.W, small.C, small.ld
+    d.k, d.stride, d.dil, d.pad = spec.k, spec.stride, spec.dil, spec.pad
+    d.depthwise = 0
+    return d
+
+
+def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
+    """1x1x1 conv whose input is a virtual concat (preprocess convs of the next cell, the head)"""
+    lib = ctx.lib
+    ctx.use(m.weight, m.bias)
+    y = new_act(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
+                ctx.device)
+    S = None
+    if stats:
+        S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)
+        y.S = S
+    d = _cat_desc(spec, x, y)
+    parts = x.parts
+    check(lib.nas3d_conv1x1_cat_fwd(
+        C.byref(d), len(parts), ptr_array([p.ptr for p in parts]), int_array([p.ld for p in parts]),
+        m.weight.data_ptr(), m.bias.data_ptr() if m.bias is not None else None, _tp(in_scale),
+        1 if in_relu else 0, 1 if sigmoid else 0, y.ptr, _tp(S), ctx.stream), "conv1x1_cat_fwd")
+
+    def bwd():
+        if y.g is None:
+            return
+        st = ctx.stream
+        dy_t = y.g
+        if sigmoid:
+            dl = torch.empty_like(dy_t)
+            check(lib.nas3d_sigmoid_bwd(y.ptr, dy_t.data_ptr(), dl.data_ptr(), y.N * y.V * y.C, st),
+                  "sigmoid_bwd")
+            dy_t = dl
+        dy = _GradView(dy_t, y)
+        d2 = _cat_desc(spec, x, dy)
+        check(lib.nas3d_conv1x1_cat_wgrad(
+            C.byref(d2), len(parts), ptr_array([p.ptr for p in parts]),
+            int_array([p.ld for p in parts]), dy.ptr, _tp(in_scale), 1 if in_relu else 0,
+            ctx.gptr(m.weight), ctx.gptr(m.bias) if m.bias is not None else None, st),
+            "conv1x1_cat_wgrad")
+        live = [p for p in parts if p.requires_grad]
+        if not live:
+            return
+        if len(live) != len(parts):
+            raise NotImplementedError("partial gradient through a virtual concat")
+        gs, accs = [], []
+        for p in parts:
+            g, acc = p.grad_slot()
+            gs.append(g)
+            accs.append(acc)
+        check(lib.nas3d_conv1x1_cat_dgrad(
+            C.byref(d2), len(parts), ptr_array([g.data_ptr() for g in gs]),
+            int_array([_ndhwc_pitch(g) for g in gs]), int_array(accs), dy.ptr, m.weight.data_ptr(),
+            ptr_array([p.ptr if in_relu else None for p in parts]), int_array([p.ld for p in parts]),
+            _tp(in_scale), st), "conv1x1_cat_dgrad")
+    ctx.push(bwd)
     return y
 
 
@@ -603,6 +716,8 @@ class _ModuleFn(torch.autograd.Function):
             out = module._run(ctx, *acts, *extras)
             if isinstance(out, Term):
                 out = materialize(ctx, out)
+            if isinstance(out, CatAct):
+                out = materialize_cat(ctx, out)
         fctx.ectx = ctx
         fctx.acts = acts
         fctx.extras = extras

@@ -73,18 +73,18 @@ class KernelNet(nn.Module):
         s1 = engine.materialize(ctx, self.stem1._run(ctx, x))
         skips = [s0, s1]
         for cell in self.down_cells:
-            s0, s1 = s1, cell._run(ctx, s0, s1, a1d, a2d)
+            s0, s1 = s1, cell._run(ctx, s0, s1, a1d, a2d, virtual_cat=engine.virtual_cat_enabled())
             skips.append(s1)
         if FLAG_DEBUG:
-            print('x.shape = ', tuple(x.t.shape))
+            print('x.shape = ', (x.N, x.C, x.D, x.H, x.W))
             for s in skips:
-                print(tuple(s.t.shape))
+                print((s.N, s.C, s.D, s.H, s.W))
         skips.pop()
         for cell in self.up_cells:
             s0 = skips.pop()
-            s1 = cell._run(ctx, s0, s1, a1u, a2u)
+            s1 = cell._run(ctx, s0, s1, a1u, a2u, virtual_cat=engine.virtual_cat_enabled())
             if FLAG_DEBUG:
-                print(tuple(s1.t.shape))
+                print((s1.N, s1.C, s1.D, s1.H, s1.W))
         return engine.materialize(ctx, self.last_conv[0]._run(ctx, s1, sigmoid=True))
 
 

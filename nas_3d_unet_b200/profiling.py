@@ -36,6 +36,9 @@ def _work(name, args):
     """(algorithmic bytes, flops, tag) of one call"""
     if name in ("nas3d_conv_small_from_big", "nas3d_conv_big_from_small", "nas3d_conv_wgrad"):
         return _conv_work(args[0])
+    if name.startswith("nas3d_conv1x1_cat_"):
+        b, f, tag = _conv_work(args[0])
+        return b, f, tag + " cat"
     if name == "nas3d_umma_conv":
         b, f, tag = _conv_work(args[0])
         return b, f, tag + (" umma-T" if args[1] else " umma")

@@ -32,7 +32,7 @@ class SearchedCell(nn.Module):
     def forward(self, x0, x1):
         return engine.run_module(self, (x0, x1))
 
-    def _run(self, ctx, x0, x1):
+    def _run(self, ctx, x0, x1, virtual_cat=False):
         states = [engine.materialize(ctx, self.preprocess0._run(ctx, x0)),
                   engine.materialize(ctx, self.preprocess1._run(ctx, x1))]
         out = None
@@ -46,12 +46,17 @@ class SearchedCell(nn.Module):
                 if (t.x.C, t.x.D, t.x.H, t.x.W) != (t0.C, t0.D, t0.H, t0.W):
                     raise RuntimeError("genotype mixes resolutions inside node %d: %s vs %s"
                                        % (j, (t0.C, t0.D, t0.H, t0.W), (t.x.C, t.x.D, t.x.H, t.x.W)))
-            if out is None:
-                out = engine.new_act(t0.N, self.out_channels, t0.D, t0.H, t0.W, ctx.device)
-            node = out.slice(j * self.c_node, (j + 1) * self.c_node)
+            if virtual_cat:
+                node = engine.new_act(t0.N, self.c_node, t0.D, t0.H, t0.W, ctx.device)
+            else:
+                if out is None:
+                    out = engine.new_act(t0.N, self.out_channels, t0.D, t0.H, t0.W, ctx.device)
+                node = out.slice(j * self.c_node, (j + 1) * self.c_node)
             engine.affine_sum(ctx, terms, node)
             nodes.append(node)
             states.append(node)
+        if virtual_cat:
+            return engine.CatAct(nodes)
         engine.bind_concat(ctx, out, nodes, self.c_node)
         return out
 
@@ -85,16 +90,16 @@ class SearchedNet(nn.Module):
         s1 = engine.materialize(ctx, self.stem1._run(ctx, x))
         skips = [s0, s1]
         for cell in self.down_cells:
-            s0, s1 = s1, cell._run(ctx, s0, s1)
+            s0, s1 = s1, cell._run(ctx, s0, s1, virtual_cat=engine.virtual_cat_enabled())
             skips.append(s1)
         if FLAG_DEBUG:
-            print('x.shape = ', tuple(x.t.shape))
+            print('x.shape = ', (x.N, x.C, x.D, x.H, x.W))
             for s in skips:
-                print(tuple(s.t.shape))
+                print((s.N, s.C, s.D, s.H, s.W))
         skips.pop()
         for cell in self.up_cells:
             s0 = skips.pop()
-            s1 = cell._run(ctx, s0, s1)
+            s1 = cell._run(ctx, s0, s1, virtual_cat=engine.virtual_cat_enabled())
             if FLAG_DEBUG:
-                print(tuple(s1.t.shape))
+                print((s1.N, s1.C, s1.D, s1.H, s1.W))
         return engine.materialize(ctx, self.last_conv[0]._run(ctx, s1, sigmoid=True))
