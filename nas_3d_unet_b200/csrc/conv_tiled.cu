@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
 // Lanes 27..29 ride along and accumulate the bias gradient (sum of dy) of rows j = 0..2.
 // For C > 4 the (ci-chunk, co-chunk) pairs are looped over the same staged tile.
 // -----------------------------------------------------------------------------------------
-template <int DIL, int TH, int TD, int NWARP>
+template <int DIL, int TH, int TD, int NWARP, int TWT = 32>
 struct WgShape {
-  static constexpr int TW = 32;
+  static constexpr int TW = TWT;      // 32 | 16 | 8: narrow volumes (low-resolution wide layers)
   static constexpr int PW = TW + 2 * DIL, PH = TH + 2 * DIL, PD = TD + 2 * DIL;
   // Row / plane / dy-row pitches (in float4) found by exhaustive search so that every 8-lane
   // phase of the two LDS.128 per step hits 8 distinct 16-byte bank groups (8 wavefronts per
@@ -254,10 +254,10 @@ struct WgShape {
 
 // PERSISTENT: blockIdx.x strides over the tiles, blockIdx.y = (ci-chunk, co-chunk) pair; the
 // 48 partial sums of a lane live in registers across all tiles of the CTA and are flushed once.
-template <int DIL, int TH, int TD, int NWARP>
-__global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP>::THREADS)
+template <int DIL, int TH, int TD, int NWARP, int TWT>
+__global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
     wgrad3_s1_kernel(const WgradArgs A, int C, int ntiles) {
-  using WS = WgShape<DIL, TH, TD, NWARP>;
+  using WS = WgShape<DIL, TH, TD, NWARP, TWT>;
   constexpr int PW = WS::PW, PWP = WS::PWP, PH = WS::PH, TW = WS::TW, WN = WS::WN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* xt = reinterpret_cast<float4*>(smem_raw);
@@ -454,14 +454,14 @@ static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   return launched("conv3_s1");
 }
 
-template <int DIL, int TH, int TD, int NWARP>
+template <int DIL, int TH, int TD, int NWARP, int TWT>
 static int launch_wgrad3(const WgradArgs& A0, int C, cudaStream_t st) {
-  using WS = WgShape<DIL, TH, TD, NWARP>;
+  using WS = WgShape<DIL, TH, TD, NWARP, TWT>;
   WgradArgs A = A0;
   A.tiles_w = (A.W + WS::TW - 1) / WS::TW;
   A.tiles_h = (A.H + TH - 1) / TH;
   A.tiles_d = (A.D + TD - 1) / TD;
-  auto kern = wgrad3_s1_kernel<DIL, TH, TD, NWARP>;
+  auto kern = wgrad3_s1_kernel<DIL, TH, TD, NWARP, TWT>;
   static int occ = 0;
   if (!occ) {
     NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
@@ -515,15 +515,20 @@ int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t s
 }
 
 int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st) {
-  if (A.W < 8 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.dy)) return NAS3D_ERR_UNSUPPORTED;
+  if (A.W < 4 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.dy)) return NAS3D_ERR_UNSUPPORTED;
   if (C % 4 || C > 64) return NAS3D_ERR_UNSUPPORTED;
-  if (A.H >= 12) {
-    if (dil == 1) return launch_wgrad3<1, 12, 4, 8>(A, C, st);
-    if (dil == 2) return launch_wgrad3<2, 12, 4, 8>(A, C, st);
-  } else {
-    if (dil == 1) return launch_wgrad3<1, 6, 4, 8>(A, C, st);
-    if (dil == 2) return launch_wgrad3<2, 6, 4, 8>(A, C, st);
+#define NAS3D_WG(TWT)                                                              \
+  if (A.H >= 12) {                                                                  \
+    if (dil == 1) return launch_wgrad3<1, 12, 4, 8, TWT>(A, C, st);                 \
+    if (dil == 2) return launch_wgrad3<2, 12, 4, 8, TWT>(A, C, st);                 \
+  } else {                                                                          \
+    if (dil == 1) return launch_wgrad3<1, 6, 4, 8, TWT>(A, C, st);                  \
+    if (dil == 2) return launch_wgrad3<2, 6, 4, 8, TWT>(A, C, st);                  \
   }
+  if (A.W <= 8) { NAS3D_WG(8) }
+  else if (A.W <= 16) { NAS3D_WG(16) }
+  else { NAS3D_WG(32) }
+#undef NAS3D_WG
   return NAS3D_ERR_UNSUPPORTED;
 }
 

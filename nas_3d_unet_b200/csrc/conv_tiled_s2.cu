@@ -310,10 +310,11 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
 // =========================================================================================
 // wgrad (persistent, one (cb-chunk, cs-chunk) pair per blockIdx.y)
 // =========================================================================================
+template <int TWT>
 struct WgS2Shape {
-  static constexpr int TW = 32, TH = 6, TD = 2, NWARP = 4;
+  static constexpr int TW = TWT, TH = 6, TD = 2, NWARP = 4;     // TW 32 | 16 | 8 (narrow volumes)
   static constexpr int PD = 2 * TD + 1, PH = 2 * TH + 1, PW = 2 * TW + 1;
-  static constexpr int PWP = 65, PLANE_PAD = 2;        // bank-conflict search (see conv_tiled.cu)
+  static constexpr int PWP = PW, PLANE_PAD = 2;        // bank-conflict search (see conv_tiled.cu)
   static constexpr int XPLANE = PH * PWP + PLANE_PAD;
   static constexpr int XTILE = PD * XPLANE + 8;
   static constexpr int YP = TW + 1;
@@ -324,9 +325,10 @@ struct WgS2Shape {
   static constexpr size_t SMEM = sizeof(float4) * (XTILE + YTILE) + sizeof(float) * (27 * 16 + 4);
 };
 
-__global__ void __launch_bounds__(WgS2Shape::THREADS)
+template <int TWT>
+__global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
     wgrad3_s2_kernel(const S2Args A, int ntiles) {
-  using WS = WgS2Shape;
+  using WS = WgS2Shape<TWT>;
   constexpr int PW = WS::PW, PWP = WS::PWP, PH = WS::PH, TW = WS::TW, TH = WS::TH, TD = WS::TD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* xt = reinterpret_cast<float4*>(smem_raw);
@@ -493,17 +495,16 @@ int tiled_s2_bfs(const S2Args& A, cudaStream_t st) {
   return NAS3D_ERR_UNSUPPORTED;
 }
 
-int tiled_s2_wgrad(const S2Args& A0, cudaStream_t st) {
-  if (!s2_common_ok(A0) || A0.Cb % 4 || A0.Cs % 4 || A0.Cb > 64 || A0.Cs > 64) return NAS3D_ERR_UNSUPPORTED;
-  using WS = WgS2Shape;
-  S2Args A = A0;
+template <int TWT>
+static int launch_s2_wgrad(S2Args A, cudaStream_t st) {
+  using WS = WgS2Shape<TWT>;
   A.tiles_w = (A.Ws + WS::TW - 1) / WS::TW;
   A.tiles_h = (A.Hs + WS::TH - 1) / WS::TH;
   A.tiles_d = (A.Ds + WS::TD - 1) / WS::TD;
   static int occ = 0;
   if (!occ) {
-    NAS3D_CUDA(cudaFuncSetAttribute(wgrad3_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
-    NAS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wgrad3_s2_kernel, WS::THREADS, WS::SMEM));
+    NAS3D_CUDA(cudaFuncSetAttribute(wgrad3_s2_kernel<TWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
+    NAS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wgrad3_s2_kernel<TWT>, WS::THREADS, WS::SMEM));
     if (occ < 1) occ = 1;
   }
   const long long ntiles = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
@@ -511,8 +512,17 @@ int tiled_s2_wgrad(const S2Args& A0, cudaStream_t st) {
   long long gx = (long long)kNumSMs * occ / pairs;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
-  wgrad3_s2_kernel<<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, (int)ntiles);
+  wgrad3_s2_kernel<TWT><<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, (int)ntiles);
   return launched("wgrad3_s2");
+}
+
+int tiled_s2_wgrad(const S2Args& A, cudaStream_t st) {
+  const bool ok = A.ld_big % 4 == 0 && A.ld_small % 4 == 0 && aligned16(A.big) && aligned16(A.small) &&
+                  A.Db == 2 * A.Ds && A.Hb == 2 * A.Hs && A.Wb == 2 * A.Ws && A.Ws >= 2;
+  if (!ok || A.Cb % 4 || A.Cs % 4 || A.Cb > 64 || A.Cs > 64) return NAS3D_ERR_UNSUPPORTED;
+  if (A.Ws <= 8) return launch_s2_wgrad<8>(A, st);
+  if (A.Ws <= 16) return launch_s2_wgrad<16>(A, st);
+  return launch_s2_wgrad<32>(A, st);
 }
 
 }  // namespace nas3d
