@@ -211,7 +211,90 @@ def golden_cells():
     print('cells: done')
 
 
+def main():
+    if '--datapath' not in sys.argv:
+        golden_prims()
+        golden_cells()
+        golden_nets()
+    golden_datapath()
+
+
+def golden_datapath():
+    """integer / data-path KATs from the reference's own patches.py / prediction.py / generator.py
+    (their heavy imports - h5py, nibabel, tqdm.notebook ... - are stubbed; only pure-numpy
+    functions are called)"""
+    import types
+    np.int = int      # removed from numpy >= 1.24 (patches.py:75,188,194)
+    np.bool = bool
+    for name in ("h5py", "nibabel", "nilearn", "nilearn.image", "tqdm.notebook", "ipywidgets"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.tqdm = lambda it=None, **k: it
+            m.new_img_like = None
+            m.resample_to_img = None
+            m.reorder_img = None
+            sys.modules[name] = m
+    import patches as ref_patches
+    out = {}
+    cases = [((240, 240, 155), (128, 128, 128), None), ((240, 240, 155), (64, 64, 64), None),
+             ((240, 240, 155), (128, 128, 128), 64), ((240, 240, 155), (64, 64, 64), 17),
+             ((160, 192, 140), (128, 128, 128), None), ((160, 192, 140), (64, 64, 64), None),
+             ((100, 120, 90), (128, 128, 128), None), ((138, 173, 141), (64, 64, 64), 23)]
+    for i, (img, ps, ov) in enumerate(cases):
+        c = ref_patches.patching(img, ps, overlap=ov)
+        out['patching/%d/corners' % i] = np.asarray(c, dtype=np.int64)
+        out['patching/%d/args' % i] = np.array(list(img) + list(ps) + [-1 if ov is None else ov])
+    # OOB patch extraction (patches.py KAT of SURVEY App. D)
+    data = np.arange(4 * 10 ** 3, dtype=np.float32).reshape(4, 10, 10, 10)
+    out['get_patch/kat'] = ref_patches.get_patch_from_3d_data(data, (8, 8, 8), (-3, 5, 2))
+    # stitch: random fp32 patches on a ragged brain box with autofit corners
+    rng = np.random.default_rng(7)
+    shape = (3, 21, 25, 19)
+    corners = ref_patches.patching(shape[1:], (16, 16, 16))
+    plist = [rng.random((3, 16, 16, 16), dtype=np.float32) for _ in corners]
+    st = ref_patches.stitch(plist, [np.array(c) for c in corners], shape)
+    out['stitch/corners'] = np.asarray(corners, dtype=np.int64)
+    out['stitch/patches'] = np.stack(plist)
+    out['stitch/result'] = st
+    # label assembly both ways
+    sys.modules.setdefault("yaml", __import__("yaml"))
+    import importlib
+    pred_src = open(os.path.join(REF, "prediction.py")).read()
+    gen_src = open(os.path.join(REF, "generator.py")).read()
+
+    def extract(src, name):
+        """exec one method of the reference source as a plain function (the classes themselves
+        need datasets to construct)"""
+        lines = src.splitlines()
+        i0 = next(i for i, l in enumerate(lines) if l.strip().startswith("def %s(" % name))
+        indent = len(lines[i0]) - len(lines[i0].lstrip())
+        body = [lines[i0][indent:]]
+        for l in lines[i0 + 1:]:
+            if l.strip() and (len(l) - len(l.lstrip())) <= indent:
+                break
+            body.append(l[indent:] if len(l) >= indent else l)
+        ns = {"np": np}
+        exec("\n".join(body), ns)
+        return ns[name]
+    get_tumor_pred = extract(pred_src, "get_tumor_pred")
+    get_multi = extract(gen_src, "get_multi_class_labels")
+    p = rng.random((3, 9, 10, 11))
+    p[:, 0, 0, :3] = 0.5            # exact-threshold and tie cases
+    p[0, 1, 1, 1] = p[1, 1, 1, 1] = 0.7
+    p[0, 2, 2, 2] = p[2, 2, 2, 2] = 0.9
+    out['tumor/pred'] = p
+    out['tumor/inclusive'] = get_tumor_pred(None, p, 0.5, True)
+    out['tumor/exclusive'] = get_tumor_pred(None, p, 0.5, False)
+    truth = rng.choice(np.array([0, 1, 2, 4, 3], dtype=np.int16), size=(2, 1, 5, 6, 7))
+
+    class _S:
+        labels = (1, 2, 4)
+    out['labels/truth'] = truth
+    out['labels/inclusive'] = get_multi(_S(), truth, True)
+    out['labels/exclusive'] = get_multi(_S(), truth, False)
+    np.savez_compressed(os.path.join(HERE, 'datapath.npz'), **out)
+    print('datapath: done;', {k: v.shape for k, v in out.items() if k.startswith('patching') and 'corners' in k})
+
+
 if __name__ == '__main__':
-    golden_prims()
-    golden_cells()
-    golden_nets()
+    main()
