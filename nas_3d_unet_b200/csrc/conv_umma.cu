@@ -33,6 +33,7 @@ struct UmmaArgs {
   int accumulate;
   long long nvox;
   double* moments;         // optional fused GN statistics (host guarantees V % 128 == 0)
+  int splits;              // split-K over the tap stages (gridDim.y); > 1: atomic epilogue
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -227,16 +228,21 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
       for (int c = 0; c < CRED / 4; ++c) xv[tp][c] = ldg4_pred(px + c * 4, ok);
     }
   };
-  gather(0);
+  // split-K: this CTA reduces the K stages [it0, it1) (small problems have too few voxel tiles to
+  // fill 148 SMs and would serialise 27 gather->MMA round trips per tile)
+  const int it0 = (int)((long long)blockIdx.y * NIT / A.splits);
+  const int it1 = (int)((long long)(blockIdx.y + 1) * NIT / A.splits);
+  gather(it0);
 
 #pragma unroll 1
-  for (int it = 0; it < NIT; ++it) {
-    const int s = it & 1;
+  for (int it = it0; it < it1; ++it) {
+    const int j = it - it0;
+    const int s = j & 1;
     unsigned char* stage = smem + s * US::STAGE_BYTES;
     unsigned char* a_hi = stage;
     unsigned char* a_lo = stage + US::A_BYTES;
     unsigned char* b_sm = stage + 2 * US::A_BYTES;
-    if (it >= 2) mbar_wait(&bars[s], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of it-2 drained
+    if (j >= 2) mbar_wait(&bars[s], (uint32_t)(((j >> 1) - 1) & 1));   // MMAs of stage j-2 drained
 
     // ---- B: packed weights of this stage (contiguous), asynchronous copy ----
     {
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
       }
     }
     // next stage's gather goes in flight now; it lands while this stage's MMAs are issued
-    if (it + 1 < NIT) gather(it + 1);
+    if (it + 1 < it1) gather(it + 1);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
         const uint64_t da_hi = make_smem_desc(a_hi_s + kk * 256, 128, KCH * 128);
         const uint64_t da_lo = make_smem_desc(a_lo_s + kk * 256, 128, KCH * 128);
         const uint64_t db = make_smem_desc(b_s + kk * 256, 128, KCH * 128);
-        umma_tf32(tmem_base, da_hi, db, IDESC1, (it | kk) ? 1u : 0u);   // hi*[hi|lo] -> cols [0,2N)
+        umma_tf32(tmem_base, da_hi, db, IDESC1, (j | kk) ? 1u : 0u);    // hi*[hi|lo] -> cols [0,2N)
         umma_tf32(tmem_base, da_lo, db, IDESC2, 1u);                    // lo*hi      -> cols [0,N)
       }
       umma_commit(&bars[s]);
@@ -285,7 +291,8 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   }
 
   // ---- epilogue: all MMAs done when the last stage's commit lands ----
-  mbar_wait(&bars[(NIT - 1) & 1], (uint32_t)(((NIT - 1) >> 1) & 1));
+  const int jl = it1 - it0 - 1;
+  mbar_wait(&bars[jl & 1], (uint32_t)((jl >> 1) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
   float* pd = A.dst + o * A.ldd;
@@ -300,23 +307,29 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         v[i] = hi[i] + lo[i];
-        if (A.bias) v[i] += __ldg(A.bias + c8 * 8 + i);
+        if (A.bias && blockIdx.y == 0) v[i] += __ldg(A.bias + c8 * 8 + i);
       }
-      float4 v0 = make_float4(v[0], v[1], v[2], v[3]), v1 = make_float4(v[4], v[5], v[6], v[7]);
-      if (A.accumulate) {
-        const float4 o0 = *reinterpret_cast<const float4*>(pd + c8 * 8);
-        const float4 o1 = *reinterpret_cast<const float4*>(pd + c8 * 8 + 4);
-        v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
-        v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
-      }
-      st4(pd + c8 * 8, v0);
-      st4(pd + c8 * 8 + 4, v1);
-      if (A.moments) {
-        const float s0[4] = {v0.x, v0.y, v0.z, v0.w}, s1[4] = {v1.x, v1.y, v1.z, v1.w};
-        const float q0[4] = {v0.x * v0.x, v0.y * v0.y, v0.z * v0.z, v0.w * v0.w};
-        const float q1[4] = {v1.x * v1.x, v1.y * v1.y, v1.z * v1.z, v1.w * v1.w};
-        warp_moments_add(sm_mom, c8 * 8, s0, q0);
-        warp_moments_add(sm_mom, c8 * 8 + 4, s1, q1);
+      if (A.splits > 1) {
+        // partial sums of this K split: dst was zero-initialised (or holds the running gradient)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(pd + c8 * 8 + i, v[i]);
+      } else {
+        float4 v0 = make_float4(v[0], v[1], v[2], v[3]), v1 = make_float4(v[4], v[5], v[6], v[7]);
+        if (A.accumulate) {
+          const float4 o0 = *reinterpret_cast<const float4*>(pd + c8 * 8);
+          const float4 o1 = *reinterpret_cast<const float4*>(pd + c8 * 8 + 4);
+          v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+          v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
+        }
+        st4(pd + c8 * 8, v0);
+        st4(pd + c8 * 8 + 4, v1);
+        if (A.moments) {
+          const float s0[4] = {v0.x, v0.y, v0.z, v0.w}, s1[4] = {v1.x, v1.y, v1.z, v1.w};
+          const float q0[4] = {v0.x * v0.x, v0.y * v0.y, v0.z * v0.z, v0.w * v0.w};
+          const float q1[4] = {v1.x * v1.x, v1.y * v1.y, v1.z * v1.z, v1.w * v1.w};
+          warp_moments_add(sm_mom, c8 * 8, s0, q0);
+          warp_moments_add(sm_mom, c8 * 8 + 4, s1, q1);
+        }
       }
     }
   }
@@ -343,7 +356,7 @@ static int launch_umma(const UmmaArgs& A, cudaStream_t st) {
     attr_done = true;
   }
   const unsigned blocks = (unsigned)((A.nvox + 127) / 128);
-  kern<<<blocks, 128, US::SMEM, st>>>(A);
+  kern<<<dim3(blocks, (unsigned)A.splits), 128, US::SMEM, st>>>(A);
   return launched("umma_conv");
 }
 
@@ -411,9 +424,21 @@ int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
   A.accumulate = accumulate;
   A.nvox = (long long)d->N * A.Dd * A.Hd * A.Wd;
   const long long V = (long long)A.Dd * A.Hd * A.Wd;
-  const bool fuse = moments != nullptr && V % 128 == 0;
-  A.moments = fuse ? moments : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  // split-K when the voxel tiles alone cannot fill the machine (dense destination required)
+  const long long tiles = (A.nvox + 127) / 128;
+  const int Cprod = produce_big ? d->Cb : d->Cs;
+  int splits = 1;
+  if (tiles < kNumSMs && A.ldd == Cprod) {
+    splits = (int)(kNumSMs / tiles);
+    if (splits > 9) splits = 9;
+    if (splits < 1) splits = 1;
+  }
+  A.splits = splits;
+  if (splits > 1 && !accumulate)
+    NAS3D_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)A.nvox * Cprod, st));
+  const bool fuse = moments != nullptr && V % 128 == 0 && splits == 1;
+  A.moments = fuse ? moments : nullptr;
   if (fuse)
     NAS3D_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)d->N * (produce_big ? d->Cb : d->Cs), st));
   int rc;
