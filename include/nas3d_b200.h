@@ -216,13 +216,17 @@ int nas3d_pool2_bwd(int kind, const float* x, int ld_x, const float* dy, int ld_
  * NDHWC model outputs and NCDHW label tensors are read in place.
  * sums [N,C,3] fp64 = {sum p*t, sum p, sum t} (zeroed inside); loss: 1 float.
  * ------------------------------------------------------------------------------------- */
+/* truth: fp32, or int8 {0,1} masks when truth_is_int8 (what generator.py:230-248 produces; a
+ * quarter of the host->device bytes of an fp32 upload) */
 int nas3d_dice_fwd(const float* pred, long long p_sn, long long p_sc, long long p_sv,
-                   const float* truth, long long t_sn, long long t_sc, long long t_sv, int N,
-                   int C, long long V, float smooth, double* sums, float* loss, void* stream);
+                   const void* truth, int truth_is_int8, long long t_sn, long long t_sc,
+                   long long t_sv, int N, int C, long long V, float smooth, double* sums, float* loss,
+                   void* stream);
 /* dpred[n,c,v] = gout * d loss / d pred, written with pred's addressing. */
-int nas3d_dice_bwd(const double* sums, const float* gout, const float* truth, long long t_sn,
-                   long long t_sc, long long t_sv, float* dpred, long long p_sn, long long p_sc,
-                   long long p_sv, int N, int C, long long V, float smooth, void* stream);
+int nas3d_dice_bwd(const double* sums, const float* gout, const void* truth, int truth_is_int8,
+                   long long t_sn, long long t_sc, long long t_sv, float* dpred, long long p_sn,
+                   long long p_sc, long long p_sv, int N, int C, long long V, float smooth,
+                   void* stream);
 
 /* dlogit = dprob * prob * (1-prob)   (backward of nn.Sigmoid, nas.py:52); n contiguous floats */
 int nas3d_sigmoid_bwd(const float* prob, const float* dprob, float* dlogit, long long n,

@@ -64,9 +64,9 @@ _SIGNATURES = {
     "nas3d_pool2_fwd": [c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp],
     "nas3d_pool2_bwd": [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_int, c_vp],
-    "nas3d_dice_fwd": [c_vp, c_ll, c_ll, c_ll, c_vp, c_ll, c_ll, c_ll, c_int, c_int, c_ll, C.c_float,
-                       c_vp, c_vp, c_vp],
-    "nas3d_dice_bwd": [c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_vp, c_ll, c_ll, c_ll, c_int, c_int,
+    "nas3d_dice_fwd": [c_vp, c_ll, c_ll, c_ll, c_vp, c_int, c_ll, c_ll, c_ll, c_int, c_int, c_ll,
+                       C.c_float, c_vp, c_vp, c_vp],
+    "nas3d_dice_bwd": [c_vp, c_vp, c_vp, c_int, c_ll, c_ll, c_ll, c_vp, c_ll, c_ll, c_ll, c_int, c_int,
                        c_ll, C.c_float, c_vp],
     "nas3d_extract_patches": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp,
                               c_int, c_vp],

@@ -102,9 +102,13 @@ __global__ void __launch_bounds__(256)
 constexpr int DB = 256;
 constexpr int DITER = 16;
 
+__device__ __forceinline__ float ld_truth(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_truth(const signed char* p) { return (float)__ldg(p); }
+
+template <typename TT>
 __global__ void __launch_bounds__(DB)
     dice_sums_kernel(const float* __restrict__ pred, long long p_sn, long long p_sc, long long p_sv,
-                     const float* __restrict__ truth, long long t_sn, long long t_sc,
+                     const TT* __restrict__ truth, long long t_sn, long long t_sc,
                      long long t_sv, int C, long long V, double* __restrict__ sums) {
   const int n = blockIdx.y;
   const int c0 = blockIdx.z * 4;
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(DB)
 #pragma unroll
   for (int e = 0; e < 4; ++e) s[e][0] = s[e][1] = s[e][2] = 0.f;
   const float* pb = pred + n * p_sn + c0 * p_sc;
-  const float* tb = truth + n * t_sn + c0 * t_sc;
+  const TT* tb = truth + n * t_sn + c0 * t_sc;
   for (int it = 0; it < DITER; ++it) {
     const long long v = ((long long)blockIdx.x * DITER + it) * DB + threadIdx.x;
     if (v >= V) break;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(DB)
     for (int e = 0; e < 4; ++e)
       if (e < cn) {
         const float p = __ldg(pb + v * p_sv + e * p_sc);
-        const float t = __ldg(tb + v * t_sv + e * t_sc);
+        const float t = ld_truth(tb + v * t_sv + e * t_sc);
         s[e][0] += p * t; s[e][1] += p; s[e][2] += t;
       }
   }
@@ -155,9 +159,10 @@ __global__ void dice_finish_kernel(const double* __restrict__ sums, int NC, floa
   if (threadIdx.x == 0) loss[0] = 1.f - (float)(part / NC);
 }
 
+template <typename TT>
 __global__ void __launch_bounds__(DB)
     dice_bwd_kernel(const double* __restrict__ sums, const float* __restrict__ gout,
-                    const float* __restrict__ truth, long long t_sn, long long t_sc, long long t_sv,
+                    const TT* __restrict__ truth, long long t_sn, long long t_sc, long long t_sv,
                     float* __restrict__ dpred, long long p_sn, long long p_sc, long long p_sv,
                     int N, int C, long long V, float smooth) {
   const int n = blockIdx.y;
@@ -172,14 +177,14 @@ __global__ void __launch_bounds__(DB)
     cB[threadIdx.x] = (float)(g * (2.0 * s[0] + (double)smooth) / (D * D));
   }
   __syncthreads();
-  const float* tb = truth + n * t_sn + c0 * t_sc;
+  const TT* tb = truth + n * t_sn + c0 * t_sc;
   float* pb = dpred + n * p_sn + c0 * p_sc;
   for (int it = 0; it < DITER; ++it) {
     const long long v = ((long long)blockIdx.x * DITER + it) * DB + threadIdx.x;
     if (v >= V) break;
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (e < cn) pb[v * p_sv + e * p_sc] = cA[e] * __ldg(tb + v * t_sv + e * t_sc) + cB[e];
+      if (e < cn) pb[v * p_sv + e * p_sc] = cA[e] * ld_truth(tb + v * t_sv + e * t_sc) + cB[e];
   }
 }
 
@@ -228,25 +233,36 @@ int nas3d_pool2_bwd(int kind, const float* x, int ld_x, const float* dy, int ld_
 }
 
 int nas3d_dice_fwd(const float* pred, long long p_sn, long long p_sc, long long p_sv,
-                   const float* truth, long long t_sn, long long t_sc, long long t_sv, int N,
-                   int C, long long V, float smooth, double* sums, float* loss, void* stream) {
+                   const void* truth, int truth_is_int8, long long t_sn, long long t_sc,
+                   long long t_sv, int N, int C, long long V, float smooth, double* sums, float* loss,
+                   void* stream) {
   NAS3D_REQUIRE(N > 0 && C > 0 && V > 0, "dice_fwd: empty input");
   cudaStream_t st = (cudaStream_t)stream;
   NAS3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * (size_t)N * C, st));
   dim3 grid((unsigned)((V + DB * DITER - 1) / (DB * DITER)), N, (C + 3) / 4);
-  dice_sums_kernel<<<grid, DB, 0, st>>>(pred, p_sn, p_sc, p_sv, truth, t_sn, t_sc, t_sv, C, V, sums);
+  if (truth_is_int8)
+    dice_sums_kernel<signed char><<<grid, DB, 0, st>>>(pred, p_sn, p_sc, p_sv, (const signed char*)truth,
+                                                       t_sn, t_sc, t_sv, C, V, sums);
+  else
+    dice_sums_kernel<float><<<grid, DB, 0, st>>>(pred, p_sn, p_sc, p_sv, (const float*)truth, t_sn,
+                                                 t_sc, t_sv, C, V, sums);
   int rc = launched("dice_sums");
   if (rc) return rc;
   dice_finish_kernel<<<1, 32, 0, st>>>(sums, N * C, smooth, loss);
   return launched("dice_finish");
 }
 
-int nas3d_dice_bwd(const double* sums, const float* gout, const float* truth, long long t_sn,
-                   long long t_sc, long long t_sv, float* dpred, long long p_sn, long long p_sc,
-                   long long p_sv, int N, int C, long long V, float smooth, void* stream) {
+int nas3d_dice_bwd(const double* sums, const float* gout, const void* truth, int truth_is_int8,
+                   long long t_sn, long long t_sc, long long t_sv, float* dpred, long long p_sn,
+                   long long p_sc, long long p_sv, int N, int C, long long V, float smooth,
+                   void* stream) {
   dim3 grid((unsigned)((V + DB * DITER - 1) / (DB * DITER)), N, (C + 3) / 4);
-  dice_bwd_kernel<<<grid, DB, 0, (cudaStream_t)stream>>>(sums, gout, truth, t_sn, t_sc, t_sv, dpred,
-                                                         p_sn, p_sc, p_sv, N, C, V, smooth);
+  if (truth_is_int8)
+    dice_bwd_kernel<signed char><<<grid, DB, 0, (cudaStream_t)stream>>>(
+        sums, gout, (const signed char*)truth, t_sn, t_sc, t_sv, dpred, p_sn, p_sc, p_sv, N, C, V, smooth);
+  else
+    dice_bwd_kernel<float><<<grid, DB, 0, (cudaStream_t)stream>>>(
+        sums, gout, (const float*)truth, t_sn, t_sc, t_sv, dpred, p_sn, p_sc, p_sv, N, C, V, smooth);
   return launched("dice_bwd");
 }
 

@@ -34,7 +34,8 @@ class _DiceFn(torch.autograd.Function):
         loss = torch.empty((), device=y_pred.device, dtype=torch.float32)
         with torch.cuda.device(y_pred.device):
             _lib.check(lib.nas3d_dice_fwd(y_pred.data_ptr(), ps[0], ps[1], ps[2],
-                                          y_truth.data_ptr(), ts[0], ts[1], ts[2], N, C, V,
+                                          y_truth.data_ptr(), 0 if y_truth.dtype == torch.float32 else 1,
+                                          ts[0], ts[1], ts[2], N, C, V,
                                           smooth, sums.data_ptr(), loss.data_ptr(), _stream()),
                        "dice_fwd")
         ctx.save_for_backward(y_truth, sums)
@@ -50,6 +51,7 @@ class _DiceFn(torch.autograd.Function):
         dpred = torch.empty_strided(shape, stride, device=y_truth.device, dtype=torch.float32)
         with torch.cuda.device(y_truth.device):
             _lib.check(lib.nas3d_dice_bwd(sums.data_ptr(), gout.data_ptr(), y_truth.data_ptr(),
+                                          0 if y_truth.dtype == torch.float32 else 1,
                                           ts[0], ts[1], ts[2], dpred.data_ptr(), ps[0], ps[1],
                                           ps[2], N, C, V, smooth, _stream()), "dice_bwd")
         return dpred, None, None
@@ -68,7 +70,9 @@ class WeightedDiceLoss(nn.Module):
             raise ValueError("y_pred %s and y_truth %s must be equal 5-D shapes"
                              % (tuple(y_pred.shape), tuple(y_truth.shape)))
         _require_cuda(y_pred, "y_pred")
-        if y_truth.dtype != torch.float32:
-            y_truth = y_truth.float()
-        _require_cuda(y_truth, "y_truth")
+        if not y_truth.is_cuda:
+            _require_cuda(y_truth.float(), "y_truth")      # raises: there is no CPU path
+        if y_truth.dtype not in (torch.float32, torch.int8):
+            # int8 {0,1} masks (generator.py:230-248) are read as they are; anything else -> fp32
+            y_truth = y_truth.to(torch.int8) if y_truth.dtype in (torch.uint8, torch.bool) else y_truth.float()
         return _DiceFn.apply(y_pred, y_truth, float(self.smooth))

@@ -64,10 +64,10 @@ def _work(name, args):
         N, Do, Ho, Wo, Cc = args[8:13]
         return 4.0 * (9 + (8 if args[0] == 1 else 0)) * N * Do * Ho * Wo * Cc, 0.0, "C=%d" % Cc
     if name == "nas3d_dice_fwd":
-        N, Cc, V = args[8], args[9], args[10]
+        N, Cc, V = args[9], args[10], args[11]
         return 8.0 * N * Cc * V, 0.0, ""
     if name == "nas3d_dice_bwd":
-        N, Cc, V = args[10], args[11], args[12]
+        N, Cc, V = args[11], args[12], args[13]
         return 8.0 * N * Cc * V, 0.0, ""
     if name == "nas3d_sigmoid_bwd":
         return 12.0 * args[3], 0.0, ""

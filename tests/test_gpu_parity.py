@@ -380,3 +380,19 @@ def test_tiled_depthwise_kernels_match_oracle(c, stride, transposed):
         for k in ('depth_conv.weight', 'depth_conv.bias', 'point_conv.weight', 'point_conv.bias'):
             mod, par = k.split('.')
             assert O.max_rel(getattr(getattr(op, mod), par).grad, sd[k].grad) <= 1e-4, (mode, k)
+
+
+def test_dice_accepts_int8_masks():
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    g = torch.Generator().manual_seed(4)
+    p = torch.rand(2, 3, 9, 8, 10, generator=g)
+    t = (torch.rand(2, 3, 9, 8, 10, generator=g) > 0.6)
+    pr = p.clone().requires_grad_(True)
+    ref = O.dice_loss(pr, t.float())
+    ref.backward()
+    for tt in (t.to(torch.int8), t.to(torch.uint8), t):
+        pg = p.cuda().requires_grad_(True)
+        out = WeightedDiceLoss()(pg, tt.cuda())
+        out.backward()
+        assert abs(out.item() - ref.item()) <= 1e-6
+        assert rel_err(pg.grad.cpu().numpy(), pr.grad.numpy()) <= 1e-5
