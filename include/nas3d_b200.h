@@ -174,11 +174,13 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
 
 /* GroupNorm backward coefficients from R (one term):
  *   dx = p*m*dout + q*x + r ;  dgamma[c] += .. ; dbeta[c] += .. ; dw += <dout, y>  (if dw!=NULL)
- * w: device scalar weight of the term (NULL = 1).  p,q,r: [N,C] fp32 out. */
+ * w: device scalar weight of the term (NULL = 1).  p,q,r: [N,C] fp32 out.
+ * dbias_prev (optional, with the forward moments S of x): += the bias gradient of the convolution
+ * that produced x, obtained analytically as sum_v dx = p*R1 + q*sum(x) + r*V. */
 int nas3d_gn_bwd_coef(const double* R, const float* mean_rstd, const float* gamma,
                       const float* a, const float* b, const float* w, int N, int C, int G,
                       long long V, float* p, float* q, float* r, float* dgamma, float* dbeta,
-                      float* dw, void* stream);
+                      float* dw, const double* S, float* dbias_prev, void* stream);
 
 /* SE backward coefficients from R (term x*s): p = w*s, q = 0, r = dmean/V; parameter grads of
  * the two Linear layers are accumulated (atomics).  S = forward moments of x. */

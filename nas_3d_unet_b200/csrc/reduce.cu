@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(TB)
                        const float* __restrict__ b, const float* __restrict__ w, int C, int G,
                        double inv_m, float* __restrict__ p, float* __restrict__ q,
                        float* __restrict__ r, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float* __restrict__ dw) {
+                       float* __restrict__ dbeta, float* __restrict__ dw,
+                       const double* __restrict__ S, double V, float* __restrict__ dbias) {
   const int n = blockIdx.x;
   const int cg = C / G;
   const double wv = w ? (double)w[0] : 1.0;
@@ -272,6 +273,13 @@ __global__ void __launch_bounds__(TB)
     r[(long long)n * C + c] = (float)(wv * (-qq * mu - rho * shA[g] * inv_m));
     atomicAdd(&dgamma[c], (float)(wv * rho * (r2 - mu * r1)));
     atomicAdd(&dbeta[c], (float)(wv * r1));
+    if (dbias) {
+      // bias gradient of the conv that produced x:  sum_v dx = p*R1 + q*sum(x) + r*V  (analytic,
+      // saves a pass over the gradient tensor)
+      const double pp = wv * rho * (double)gamma[c];
+      const double rr = wv * (-qq * mu - rho * shA[g] * inv_m);
+      atomicAdd(&dbias[c], (float)(pp * r1 + wv * qq * S[((long long)n * C + c) * 2] + rr * V));
+    }
     dwp += (double)a[(long long)n * C + c] * r2 + (double)b[(long long)n * C + c] * r1;
   }
   if (dw) {
@@ -415,11 +423,13 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
 int nas3d_gn_bwd_coef(const double* R, const float* mean_rstd, const float* gamma,
                       const float* a, const float* b, const float* w, int N, int C, int G,
                       long long V, float* p, float* q, float* r, float* dgamma, float* dbeta,
-                      float* dw, void* stream) {
+                      float* dw, const double* S, float* dbias_prev, void* stream) {
   NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "gn_bwd_coef: bad groups %d for C=%d", G, C);
+  NAS3D_REQUIRE(dbias_prev == nullptr || S != nullptr, "gn_bwd_coef: dbias_prev needs the moments S");
   double inv_m = 1.0 / ((double)(C / G) * (double)V);
   gn_bwd_coef_kernel<<<N, TB, 0, (cudaStream_t)stream>>>(R, mean_rstd, gamma, a, b, w, C, G,
-                                                         inv_m, p, q, r, dgamma, dbeta, dw);
+                                                         inv_m, p, q, r, dgamma, dbeta, dw, S,
+                                                         (double)V, dbias_prev);
   return launched("gn_bwd_coef");
 }
 

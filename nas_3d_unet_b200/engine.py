@@ -49,12 +49,15 @@ def _require_cuda(t, what):
 # activations
 # ----------------------------------------------------------------------------------------
 class Act:
-    __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad", "S")
+    __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad", "S", "bias_param",
+                 "bias_done")
 
     def __init__(self, t, ld, requires_grad=True):
         self.t = t
         self.g = None
         self.S = None      # per-(n,c) fp64 {sum, sum^2} if a producer kernel already computed them
+        self.bias_param = None   # bias of the conv that produced this tensor (GN-bwd yields its grad)
+        self.bias_done = False
         self.N, self.C, self.D, self.H, self.W = t.shape
         self.ld = ld
         self.requires_grad = requires_grad
@@ -307,11 +310,16 @@ def _affine_sum_bwd(ctx, terms, out):
             aux = t.aux
             pq = torch.empty((3, N, Cc), device=dev, dtype=torch.float32)
             P[id(t)], Q[id(t)], Rr[id(t)] = pq[0], pq[1], pq[2]
+            # the conv that produced x (if any) gets its bias gradient from the same sums
+            bp = t.x.bias_param if (t.x.bias_param is not None and not t.x.bias_done) else None
+            if bp is not None:
+                t.x.bias_done = True
             rc = lib.nas3d_gn_bwd_coef(
                 R[id(t)].data_ptr(), aux["mean_rstd"].data_ptr(), aux["gamma"].data_ptr(),
                 t.a.data_ptr(), t.b.data_ptr(), wptr, N, Cc, aux["G"], V,
                 pq[0].data_ptr(), pq[1].data_ptr(), pq[2].data_ptr(),
-                ctx.gptr(aux["gamma"]), ctx.gptr(aux["beta"]), dwptr, st)
+                ctx.gptr(aux["gamma"]), ctx.gptr(aux["beta"]), dwptr,
+                aux["S"].data_ptr(), ctx.gptr(bp) if bp is not None else None, st)
             check(rc, "gn_bwd_coef")
         elif t.kind == "se":
             aux = t.aux
@@ -403,13 +411,14 @@ def gn_term(ctx, x, norm, relu):
         raise ValueError("GroupNorm expects %d channels, got %d" % (norm.num_channels, x.C))
     ctx.use(norm.weight, norm.bias)
     S = x.S if x.S is not None else moments(ctx, x)
+    x.S = S        # identity / se_conv candidates of other MixedOps reuse the statistics of x
     G = norm.num_groups
     ab = torch.empty((2, x.N, x.C), device=ctx.device, dtype=torch.float32)
     mr = torch.empty((x.N, G, 2), device=ctx.device, dtype=torch.float32)
     check(ctx.lib.nas3d_gn_coef(S.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), x.N,
                                 x.C, G, x.V, float(norm.eps), ab[0].data_ptr(), ab[1].data_ptr(),
                                 mr.data_ptr(), ctx.stream), "gn_coef")
-    aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G}
+    aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G, "S": S}
     return Term(x, ab[0], ab[1], relu, "gn", aux)
 
 
@@ -417,7 +426,8 @@ def se_term(ctx, x, fc):
     """x * sigmoid(fc(mean(x))) as a lazy Term (prim_ops.py:133-139,149-152)"""
     fc0, fc2 = fc[0], fc[2]
     ctx.use(fc0.weight, fc0.bias, fc2.weight, fc2.bias)
-    S = moments(ctx, x)
+    S = x.S if x.S is not None else moments(ctx, x)
+    x.S = S
     s = torch.empty((x.N, x.C), device=ctx.device, dtype=torch.float32)
     hz = torch.empty((x.N, 2), device=ctx.device, dtype=torch.float32)
     check(ctx.lib.nas3d_se_excite(S.data_ptr(), fc0.weight.data_ptr(), fc0.bias.data_ptr(),
@@ -532,6 +542,7 @@ def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False, stats=Fal
     if stats:    # GroupNorm follows: let the conv epilogue produce its statistics
         S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)
         y.S = S
+        y.bias_param = m.bias        # GroupNorm is y's only consumer: its backward emits d(bias)
     Sp = _tp(S)
     if not spec.transposed:
         d = _desc(spec, x, y)
@@ -580,6 +591,7 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
     if stats:
         S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)
         y.S = S
+        y.bias_param = m.bias
     d = _cat_desc(spec, x, y)
     parts = x.parts
     check(lib.nas3d_conv1x1_cat_fwd(
@@ -602,7 +614,8 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
         check(lib.nas3d_conv1x1_cat_wgrad(
             C.byref(d2), len(parts), ptr_array([p.ptr for p in parts]),
             int_array([p.ld for p in parts]), dy.ptr, _tp(in_scale), 1 if in_relu else 0,
-            ctx.gptr(m.weight), ctx.gptr(m.bias) if m.bias is not None else None, st),
+            ctx.gptr(m.weight),
+            ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None, st),
             "conv1x1_cat_wgrad")
         live = [p for p in parts if p.requires_grad]
         if not live:
@@ -638,7 +651,7 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
         dy_t = dl
     dy = _GradView(dy_t, y)
     dW = ctx.gptr(m.weight)
-    db = ctx.gptr(m.bias) if m.bias is not None else None
+    db = ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None
     if not spec.transposed:
         d = _desc(spec, x, dy)
         check(lib.nas3d_conv_wgrad(C.byref(d), dy.ptr, x.ptr, _tp(in_scale), 1 if in_relu else 0,
