@@ -182,6 +182,18 @@ int nas3d_gn_bwd_coef(const double* R, const float* mean_rstd, const float* gamm
                       long long V, float* p, float* q, float* r, float* dgamma, float* dbeta,
                       float* dw, const double* S, float* dbias_prev, void* stream);
 
+/* Batched forms of nas3d_gn_coef / nas3d_gn_bwd_coef: all GroupNorm terms of one node (same N, C,
+ * G, V) in one launch.  Arrays are HOST arrays of nterms device pointers. */
+int nas3d_gn_coef_batch(int nterms, const double* const* S, const float* const* gamma,
+                        const float* const* beta, int N, int C, int G, long long V, float eps,
+                        float* const* a, float* const* b, float* const* mean_rstd, void* stream);
+int nas3d_gn_bwd_coef_batch(int nterms, const double* const* R, const float* const* mean_rstd,
+                            const float* const* gamma, const float* const* a,
+                            const float* const* b, const float* const* w, int N, int C, int G,
+                            long long V, float* const* p, float* const* q, float* const* r,
+                            float* const* dgamma, float* const* dbeta, float* const* dw,
+                            const double* const* S, float* const* dbias_prev, void* stream);
+
 /* SE backward coefficients from R (term x*s): p = w*s, q = 0, r = dmean/V; parameter grads of
  * the two Linear layers are accumulated (atomics).  S = forward moments of x. */
 int nas3d_se_bwd_coef(const double* R, const double* S, const float* s, const float* hz,

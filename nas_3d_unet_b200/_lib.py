@@ -49,6 +49,10 @@ _SIGNATURES = {
     "nas3d_umma_conv": [C.POINTER(ConvDesc), c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "nas3d_moments_nc": [c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp],
     "nas3d_gn_coef": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, C.c_float, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_gn_coef_batch": [c_int, _PP, _PP, _PP, c_int, c_int, c_int, c_ll, C.c_float, _PP, _PP, _PP,
+                            c_vp],
+    "nas3d_gn_bwd_coef_batch": [c_int, _PP, _PP, _PP, _PP, _PP, _PP, c_int, c_int, c_int, c_ll, _PP,
+                                _PP, _PP, _PP, _PP, _PP, _PP, _PP, c_vp],
     "nas3d_se_excite": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp],
     "nas3d_affine_sum_fwd": [c_int, _PP, _PI, _PP, _PP, _PP, _PI, c_vp, c_int, c_int, c_ll, c_int,
                              c_vp],

@@ -333,6 +333,108 @@ __global__ void __launch_bounds__(TB)
   if (threadIdx.x == 0) atomicAdd(dw, (float)tot);
 }
 
+// ---- batched variants: all GroupNorm terms of one node in a single launch (grid = N x nterms);
+// the supernet has up to 22 terms per node and these tiny kernels are pure launch latency ----
+struct GnFwdBatch {
+  const double* S[NAS3D_MAX_TERMS];
+  const float* gamma[NAS3D_MAX_TERMS];
+  const float* beta[NAS3D_MAX_TERMS];
+  float* a[NAS3D_MAX_TERMS];
+  float* b[NAS3D_MAX_TERMS];
+  float* mr[NAS3D_MAX_TERMS];
+};
+struct GnBwdBatch {
+  const double* R[NAS3D_MAX_TERMS];
+  const float* mr[NAS3D_MAX_TERMS];
+  const float* gamma[NAS3D_MAX_TERMS];
+  const float* a[NAS3D_MAX_TERMS];
+  const float* b[NAS3D_MAX_TERMS];
+  const float* w[NAS3D_MAX_TERMS];
+  float* p[NAS3D_MAX_TERMS];
+  float* q[NAS3D_MAX_TERMS];
+  float* r[NAS3D_MAX_TERMS];
+  float* dgamma[NAS3D_MAX_TERMS];
+  float* dbeta[NAS3D_MAX_TERMS];
+  float* dw[NAS3D_MAX_TERMS];
+  const double* S[NAS3D_MAX_TERMS];
+  float* dbias[NAS3D_MAX_TERMS];
+};
+
+__global__ void __launch_bounds__(TB)
+    gn_coef_batch_kernel(const __grid_constant__ GnFwdBatch B, int C, int G, double inv_m, float eps) {
+  const int n = blockIdx.x, k = blockIdx.y;
+  const int cg = C / G;
+  __shared__ float sh_mean[64], sh_rstd[64];
+  const double* Sn = B.S[k] + (long long)n * C * 2;
+  for (int g = threadIdx.x; g < G; g += TB) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { s += Sn[c * 2]; q += Sn[c * 2 + 1]; }
+    double mean = s * inv_m;
+    double var = q * inv_m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sh_mean[g] = (float)mean;
+    sh_rstd[g] = rstd;
+    B.mr[k][((long long)n * G + g) * 2 + 0] = (float)mean;
+    B.mr[k][((long long)n * G + g) * 2 + 1] = rstd;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TB) {
+    int g = c / cg;
+    float av = sh_rstd[g] * B.gamma[k][c];
+    B.a[k][(long long)n * C + c] = av;
+    B.b[k][(long long)n * C + c] = B.beta[k][c] - sh_mean[g] * av;
+  }
+}
+
+__global__ void __launch_bounds__(TB)
+    gn_bwd_coef_batch_kernel(const __grid_constant__ GnBwdBatch B, int C, int G, double inv_m,
+                             double V) {
+  const int n = blockIdx.x, k = blockIdx.y;
+  const int cg = C / G;
+  const float* mean_rstd = B.mr[k];
+  const float* gamma = B.gamma[k];
+  const double wv = B.w[k] ? (double)B.w[k][0] : 1.0;
+  __shared__ double shA[64], shB[64];
+  __shared__ double sh[TB / 32];
+  const double* Rn = B.R[k] + (long long)n * C * 2;
+  for (int g = threadIdx.x; g < G; g += TB) {
+    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+    double A = 0.0, Bq = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
+      A += (double)gamma[c] * r1;
+      Bq += (double)gamma[c] * rho * (r2 - mu * r1);
+    }
+    shA[g] = A;
+    shB[g] = Bq;
+  }
+  __syncthreads();
+  double dwp = 0.0;
+  for (int c = threadIdx.x; c < C; c += TB) {
+    int g = c / cg;
+    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+    double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
+    double qq = -rho * rho * shB[g] * inv_m;
+    const double pp = wv * rho * (double)gamma[c];
+    const double rr = wv * (-qq * mu - rho * shA[g] * inv_m);
+    B.p[k][(long long)n * C + c] = (float)pp;
+    B.q[k][(long long)n * C + c] = (float)(wv * qq);
+    B.r[k][(long long)n * C + c] = (float)rr;
+    atomicAdd(&B.dgamma[k][c], (float)(wv * rho * (r2 - mu * r1)));
+    atomicAdd(&B.dbeta[k][c], (float)(wv * r1));
+    if (B.dbias[k])
+      atomicAdd(&B.dbias[k][c], (float)(pp * r1 + wv * qq * B.S[k][((long long)n * C + c) * 2] + rr * V));
+    dwp += (double)B.a[k][(long long)n * C + c] * r2 + (double)B.b[k][(long long)n * C + c] * r1;
+  }
+  if (B.dw[k]) {
+    double tot = block_sum(dwp, sh);
+    if (threadIdx.x == 0) atomicAdd(B.dw[k], (float)tot);
+  }
+}
+
 static int check_channels(int C, int ld, int* U, int* P, int* logP) {
   NAS3D_REQUIRE(C > 0 && C % 4 == 0 && ld % 4 == 0 && ld >= C,
                 "channel count %d / pitch %d must be multiples of 4", C, ld);
@@ -377,6 +479,42 @@ int nas3d_gn_coef(const double* S, const float* gamma, const float* beta, int N,
   gn_coef_kernel<<<N, TB, 0, (cudaStream_t)stream>>>(S, gamma, beta, C, G, inv_m, eps, a, b,
                                                      mean_rstd);
   return launched("gn_coef");
+}
+
+int nas3d_gn_coef_batch(int nterms, const double* const* S, const float* const* gamma,
+                        const float* const* beta, int N, int C, int G, long long V, float eps,
+                        float* const* a, float* const* b, float* const* mean_rstd, void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "gn_coef_batch: nterms=%d", nterms);
+  NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "gn_coef_batch: bad groups %d for C=%d", G, C);
+  GnFwdBatch B;
+  for (int k = 0; k < nterms; ++k) {
+    B.S[k] = S[k]; B.gamma[k] = gamma[k]; B.beta[k] = beta[k];
+    B.a[k] = a[k]; B.b[k] = b[k]; B.mr[k] = mean_rstd[k];
+  }
+  const double inv_m = 1.0 / ((double)(C / G) * (double)V);
+  gn_coef_batch_kernel<<<dim3(N, nterms), TB, 0, (cudaStream_t)stream>>>(B, C, G, inv_m, eps);
+  return launched("gn_coef_batch");
+}
+
+int nas3d_gn_bwd_coef_batch(int nterms, const double* const* R, const float* const* mean_rstd,
+                            const float* const* gamma, const float* const* a,
+                            const float* const* b, const float* const* w, int N, int C, int G,
+                            long long V, float* const* p, float* const* q, float* const* r,
+                            float* const* dgamma, float* const* dbeta, float* const* dw,
+                            const double* const* S, float* const* dbias_prev, void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "gn_bwd_coef_batch: nterms=%d", nterms);
+  NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "gn_bwd_coef_batch: bad groups %d for C=%d", G, C);
+  GnBwdBatch B;
+  for (int k = 0; k < nterms; ++k) {
+    B.R[k] = R[k]; B.mr[k] = mean_rstd[k]; B.gamma[k] = gamma[k]; B.a[k] = a[k]; B.b[k] = b[k];
+    B.w[k] = w ? w[k] : nullptr; B.p[k] = p[k]; B.q[k] = q[k]; B.r[k] = r[k];
+    B.dgamma[k] = dgamma[k]; B.dbeta[k] = dbeta[k]; B.dw[k] = dw ? dw[k] : nullptr;
+    B.S[k] = S ? S[k] : nullptr; B.dbias[k] = dbias_prev ? dbias_prev[k] : nullptr;
+    NAS3D_REQUIRE(B.dbias[k] == nullptr || B.S[k] != nullptr, "gn_bwd_coef_batch: dbias needs S");
+  }
+  const double inv_m = 1.0 / ((double)(C / G) * (double)V);
+  gn_bwd_coef_batch_kernel<<<dim3(N, nterms), TB, 0, (cudaStream_t)stream>>>(B, C, G, inv_m, (double)V);
+  return launched("gn_bwd_coef_batch");
 }
 
 int nas3d_se_excite(const double* S, const float* W1, const float* b1, const float* W2,

@@ -213,6 +213,7 @@ class ExecCtx:
         self.lib = get_lib()
         self.stream = _stream()
         self.packed = {}
+        self.pending_gn = []
 
     def use(self, *params):
         for p in params:
@@ -267,6 +268,7 @@ def affine_sum(ctx, terms, out):
     """out = sum_k w_k act_k(a_k x_k + b_k)   (cell.py:30,32,81 / prim_ops.py:75-80,152)"""
     n = len(terms)
     lib = ctx.lib
+    flush_gn(ctx)
     rc = lib.nas3d_affine_sum_fwd(
         n, ptr_array([t.x.ptr for t in terms]), int_array([t.x.ld for t in terms]),
         ptr_array([_tp(t.a) for t in terms]), ptr_array([_tp(t.b) for t in terms]),
@@ -301,26 +303,47 @@ def _affine_sum_bwd(ctx, terms, out):
             dout.data_ptr(), ld_dout, ptr_array([R[id(t)].data_ptr() for t in need]),
             N, V, Cc, st)
         check(rc, "affine_sum_bwd_reduce")
-    # per-term coefficient kernels
+    # per-term coefficient kernels (all GroupNorm terms of the node in one batched launch)
     P, Q, Rr = {}, {}, {}
-    for t in terms:
-        wptr = t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None
-        dwptr = t.alpha[0].gptr(t.alpha[1], t.alpha[2]) if t.alpha else None
-        if t.kind == "gn":
-            aux = t.aux
-            pq = torch.empty((3, N, Cc), device=dev, dtype=torch.float32)
-            P[id(t)], Q[id(t)], Rr[id(t)] = pq[0], pq[1], pq[2]
+    gn_terms = [t for t in terms if t.kind == "gn"]
+    if gn_terms:
+        pq_all = torch.empty((len(gn_terms), 3, N, Cc), device=dev, dtype=torch.float32)
+        wps, dwps, bps = [], [], []
+        for i, t in enumerate(gn_terms):
+            P[id(t)], Q[id(t)], Rr[id(t)] = pq_all[i, 0], pq_all[i, 1], pq_all[i, 2]
+            wps.append(t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None)
+            dwps.append(t.alpha[0].gptr(t.alpha[1], t.alpha[2]) if t.alpha else None)
             # the conv that produced x (if any) gets its bias gradient from the same sums
             bp = t.x.bias_param if (t.x.bias_param is not None and not t.x.bias_done) else None
             if bp is not None:
                 t.x.bias_done = True
-            rc = lib.nas3d_gn_bwd_coef(
-                R[id(t)].data_ptr(), aux["mean_rstd"].data_ptr(), aux["gamma"].data_ptr(),
-                t.a.data_ptr(), t.b.data_ptr(), wptr, N, Cc, aux["G"], V,
-                pq[0].data_ptr(), pq[1].data_ptr(), pq[2].data_ptr(),
-                ctx.gptr(aux["gamma"]), ctx.gptr(aux["beta"]), dwptr,
-                aux["S"].data_ptr(), ctx.gptr(bp) if bp is not None else None, st)
-            check(rc, "gn_bwd_coef")
+            bps.append(ctx.gptr(bp) if bp is not None else None)
+        by_g = {}
+        for i, t in enumerate(gn_terms):
+            by_g.setdefault(t.aux["G"], []).append(i)
+        for G, idxs in by_g.items():
+            for c0 in range(0, len(idxs), 32):
+                ii = idxs[c0:c0 + 32]
+                tt = [gn_terms[i] for i in ii]
+                check(lib.nas3d_gn_bwd_coef_batch(
+                    len(tt), ptr_array([R[id(t)].data_ptr() for t in tt]),
+                    ptr_array([t.aux["mean_rstd"].data_ptr() for t in tt]),
+                    ptr_array([t.aux["gamma"].data_ptr() for t in tt]),
+                    ptr_array([t.a.data_ptr() for t in tt]), ptr_array([t.b.data_ptr() for t in tt]),
+                    ptr_array([wps[i] for i in ii]), N, Cc, G, V,
+                    ptr_array([pq_all[i, 0].data_ptr() for i in ii]),
+                    ptr_array([pq_all[i, 1].data_ptr() for i in ii]),
+                    ptr_array([pq_all[i, 2].data_ptr() for i in ii]),
+                    ptr_array([ctx.gptr(t.aux["gamma"]) for t in tt]),
+                    ptr_array([ctx.gptr(t.aux["beta"]) for t in tt]),
+                    ptr_array([dwps[i] for i in ii]),
+                    ptr_array([t.aux["S"].data_ptr() for t in tt]),
+                    ptr_array([bps[i] for i in ii]), st), "gn_bwd_coef_batch")
+    for t in terms:
+        wptr = t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None
+        dwptr = t.alpha[0].gptr(t.alpha[1], t.alpha[2]) if t.alpha else None
+        if t.kind == "gn":
+            continue
         elif t.kind == "se":
             aux = t.aux
             pq = torch.empty((2, N, Cc), device=dev, dtype=torch.float32)
@@ -415,11 +438,30 @@ def gn_term(ctx, x, norm, relu):
     G = norm.num_groups
     ab = torch.empty((2, x.N, x.C), device=ctx.device, dtype=torch.float32)
     mr = torch.empty((x.N, G, 2), device=ctx.device, dtype=torch.float32)
-    check(ctx.lib.nas3d_gn_coef(S.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), x.N,
-                                x.C, G, x.V, float(norm.eps), ab[0].data_ptr(), ab[1].data_ptr(),
-                                mr.data_ptr(), ctx.stream), "gn_coef")
+    # the coefficient kernel is deferred: affine_sum() flushes all pending ones of a node at once
+    ctx.pending_gn.append((S, norm, x.N, x.C, G, x.V, float(norm.eps), ab, mr))
     aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G, "S": S}
     return Term(x, ab[0], ab[1], relu, "gn", aux)
+
+
+def flush_gn(ctx):
+    """launch the deferred GroupNorm coefficient kernels, batched per (N, C, G, V, eps)"""
+    if not ctx.pending_gn:
+        return
+    groups = {}
+    for job in ctx.pending_gn:
+        groups.setdefault(job[2:7], []).append(job)
+    ctx.pending_gn = []
+    for (N, Cc, G, V, eps), jobs in groups.items():
+        for i in range(0, len(jobs), 32):
+            chunk = jobs[i:i + 32]
+            check(ctx.lib.nas3d_gn_coef_batch(
+                len(chunk), ptr_array([j[0].data_ptr() for j in chunk]),
+                ptr_array([j[1].weight.data_ptr() for j in chunk]),
+                ptr_array([j[1].bias.data_ptr() for j in chunk]), N, Cc, G, V, eps,
+                ptr_array([j[7][0].data_ptr() for j in chunk]),
+                ptr_array([j[7][1].data_ptr() for j in chunk]),
+                ptr_array([j[8].data_ptr() for j in chunk]), ctx.stream), "gn_coef_batch")
 
 
 def se_term(ctx, x, fc):
