@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--patch", type=int, default=128)
     ap.add_argument("--batch", type=int, default=8, help="patches per GPU per step")
     ap.add_argument("--workload", default="searched", choices=["searched", "supernet"])
+    ap.add_argument("--optimizer", choices=["flat", "torch"], default="flat",
+                    help="flat = nas_3d_unet_b200.optim.FlatAdam (one launch); torch = torch fused Adam")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -211,18 +213,23 @@ def run_ours(args):
         engine.enable_data_parallel()
     _lib.load()
 
+    def make_adam(params):
+        if args.optimizer == "flat":   # our one-launch flat-arena Adam
+            from nas_3d_unet_b200.optim import FlatAdam
+            return FlatAdam(params, lr=1e-3)
+        return torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+
     torch.manual_seed(0)
     lossf = WeightedDiceLoss().to(dev)
     if args.workload == "searched":
         from nas_3d_unet_b200.searched import SearchedNet
         from nas_3d_unet_b200.genotype import Genotype
         model = SearchedNet(4, 4, 3, 4, 3, True, Genotype(down=O.G0.down, up=O.G0.up)).to(dev)
-        opts = [torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)]
+        opts = [make_adam(model.parameters())]
     else:
         from nas_3d_unet_b200.nas import ShellNet
         model = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True).to(dev)
-        opts = [torch.optim.Adam(model.alphas(), lr=1e-3, fused=True, capturable=True),
-                torch.optim.Adam(model.kernel.parameters(), lr=1e-3, fused=True, capturable=True)]
+        opts = [make_adam(model.alphas()), make_adam(model.kernel.parameters())]
     model.train()
 
     B, P = args.batch, args.patch
@@ -278,7 +285,7 @@ def run_ours(args):
     if args.graph == "on":
         from nas_3d_unet_b200.graph import GraphedStep
         ex = (dx, dy) if args.workload == "searched" else (dx, dy, dvx, dvy)
-        graphed = GraphedStep(step_fn, ex, warmup=max(args.warmup, 3))
+        graphed = GraphedStep(step_fn, ex, warmup=max(args.warmup, 3), optimizers=opts)
 
     def host_batches(n):
         """what a data pipeline hands the step loop: pinned host tensors"""

@@ -268,6 +268,20 @@ int nas3d_stitch_labels(const float* preds, int ld_pred, const int* corners_dev,
                         unsigned char* labels, double* stitched, void* stream);
 int nas3d_seg_to_masks(const short* seg, int N, long long V, int inclusive, float* masks, void* stream);
 
+/* ---- flat-buffer Adam (replaces torch.optim.Adam of search.py:103-104,228,237; train.py:58,127) ----
+ * param / exp_avg / exp_avg_sq: flat fp32 arenas holding every tensor of one param group at offsets
+ * that are multiples of 4 floats.  grad_ptrs: HOST array of ntensors device pointers, one gradient
+ * per tensor (NULL = no gradient this step, tensor left untouched); they travel as kernel
+ * parameters, so a captured graph keeps them.  chunks_dev: DEVICE array of int4 {tensor index, flat
+ * offset, offset inside the tensor, length <= nas3d_adam_chunk_floats()}, sorted by tensor;
+ * tensor_first_chunk: HOST int[ntensors+1], first chunk of each tensor.  hyper_dev: DEVICE float[16]
+ * = {lr, beta1, beta2, eps, weight_decay, step, -, -, maximize, 1-beta1, 1-beta2}; the call increments step and
+ * derives the bias corrections on the device (graph-capturable). */
+int nas3d_adam_chunk_floats(void);
+int nas3d_adam_flat_step(float* param, float* exp_avg, float* exp_avg_sq,
+                         const float* const* grad_ptrs, int ntensors, const int* tensor_first_chunk,
+                         const int* chunks_dev, float* hyper_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,8 @@ kernels per step (5 900 for a supernet search step); at batch 1 the host cannot 
 as a B200 retires them.  `GraphedStep` records one full step - forward, Dice loss, backward, the
 NCCL gradient all-reduce if data parallelism is enabled, and the optimizer update - into a CUDA
 graph once and replays it with a single launch per step.  Everything the step touches stays at
-fixed addresses: parameters are updated in place (the optimizer must be `capturable=True`),
+fixed addresses: parameters are updated in place (optim.FlatAdam, or a torch optimizer built with
+`capturable=True`),
 activations come from the graph's private memory pool, inputs are copied into static buffers.
 
     step = GraphedStep(lambda x, y: train_step(model, lossf, optim, x, y), (x0, y0))
@@ -16,9 +17,12 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, warmup=3):
+    def __init__(self, step_fn, example_inputs, warmup=3, optimizers=()):
         """step_fn(*tensors) -> tensor or tuple of tensors; it must do the COMPLETE step
-        (zero_grad ... optimizer.step).  `warmup` eager steps run first (they are real steps)."""
+        (zero_grad ... optimizer.step).  `warmup` eager steps run first (they are real steps).
+        `optimizers`: optim.FlatAdam instances whose lr etc. are re-read before every replay, so
+        ReduceLROnPlateau keeps working on a captured step."""
+        self.optimizers = [o for o in optimizers if hasattr(o, "sync")]
         try:   # warm-up runs on a side stream, which torch would flag for every AccumulateGrad node
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
@@ -43,6 +47,8 @@ class GraphedStep:
                 s.copy_(t, non_blocking=True)
 
     def replay(self):
+        for o in self.optimizers:
+            o.sync()
         self.graph.replay()
         return self.static_out
 

@@ -130,3 +130,21 @@ def test_dropin_shims_import():
         for k in ('nas', 'searched', 'loss', 'genotype', 'prim_ops', 'cell'):
             sys.modules.pop(k, None)
         sys.modules.update(saved_mods)
+
+
+def test_flat_adam_chunk_table_and_cpu_refusal():
+    """optim.FlatAdam: chunk table layout; no CPU fallback (step on CPU parameters raises)"""
+    import torch
+    from nas_3d_unet_b200.optim import FlatAdam, chunk_table
+    rows, total, offs = chunk_table([5, 4096, 9000, 0, 3], 4096)
+    assert offs == [0, 8, 4104, 13104, 13104] and total == 13108
+    assert rows == [(0, 0, 0, 5), (1, 8, 0, 4096), (2, 4104, 0, 4096), (2, 8200, 4096, 4096),
+                    (2, 12296, 8192, 808), (4, 13104, 0, 3)]
+    assert all(o % 4 == 0 for o in offs)
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = FlatAdam([p], lr=1e-3)
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    with pytest.raises(NotImplementedError):
+        FlatAdam([p], amsgrad=True)
