@@ -268,6 +268,16 @@ int nas3d_stitch_labels(const float* preds, int ld_pred, const int* corners_dev,
                         unsigned char* labels, double* stitched, void* stream);
 int nas3d_seg_to_masks(const short* seg, int N, long long V, int inclusive, float* masks, void* stream);
 
+/* Batch staging on the device (generator.py:195-248, augment.py:105-132): x [N][C][D*H*W] planar fp32
+ * -> x_out NDHWC (voxel pitch ld_out) with a per-sample index map, seg int16 [N][D*H*W] -> y_out
+ * int8 [N][3][D*H*W] region masks (get_multi_class_labels incl. its logical_or quirk).  index_map:
+ * HOST int[N][4] = {base, stride_d, stride_h, stride_w}: output voxel (d,h,w) reads source voxel
+ * base + stride_d*d + stride_h*h + stride_w*w (signed; identity = {0, H*W, W, 1}).  N <= 64.
+ * seg / y_out may both be NULL. */
+int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, int H, int W,
+                        const int* index_map, int inclusive, float* x_out, int ld_out,
+                        signed char* y_out, void* stream);
+
 /* ---- flat-buffer Adam (replaces torch.optim.Adam of search.py:103-104,228,237; train.py:58,127) ----
  * param / exp_avg / exp_avg_sq: flat fp32 arenas holding every tensor of one param group at offsets
  * that are multiples of 4 floats.  grad_ptrs: HOST array of ntensors device pointers, one gradient

@@ -113,6 +113,54 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Batch staging after the H2D copy (generator.py:195-248): per-sample cube permutation (one of the
+// 48 keys of augment.permute_data, given as a signed-stride index map) of the 4-modality patch into
+// the NDHWC layout the stem reads, and int16 segmentation -> three int8 region masks.
+constexpr int kStageMaxN = 64;
+struct StageArgs {
+  const float* x;        // [N][C][V] planar (what np.asarray(x_list) uploads)
+  const short* seg;      // [N][V] or NULL
+  float* xo;             // [N][V][ld]
+  signed char* yo;       // [N][3][V] or NULL
+  int N, C, D, H, W, ld, inclusive;
+  int base[kStageMaxN];
+  int sd[kStageMaxN][3];
+};
+
+__global__ void __launch_bounds__(256) stage_patches_kernel(const __grid_constant__ StageArgs a) {
+  const long long V = (long long)a.D * a.H * a.W;
+  const long long total = V * a.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    long long v = i - (long long)n * V;
+    const int w = (int)(v % a.W);
+    const int h = (int)((v / a.W) % a.H);
+    const int d = (int)(v / ((long long)a.W * a.H));
+    const long long src = (long long)a.base[n] + (long long)a.sd[n][0] * d +
+                          (long long)a.sd[n][1] * h + (long long)a.sd[n][2] * w;
+    float* o = a.xo + i * a.ld;
+    const float* xs = a.x + (long long)n * a.C * V + src;
+    if (a.C == 4 && a.ld == 4) {
+      st4(o, make_float4(__ldg(xs), __ldg(xs + V), __ldg(xs + 2 * V), __ldg(xs + 3 * V)));
+    } else {
+      for (int c = 0; c < a.C; ++c) o[c] = __ldg(xs + (long long)c * V);
+      for (int c = a.C; c < a.ld; ++c) o[c] = 0.f;
+    }
+    if (a.seg != nullptr) {
+      const short t = __ldg(a.seg + (long long)n * V + src);
+      signed char c0, c1, c2;
+      if (a.inclusive) {
+        c0 = (t == 1 || t == 4); c1 = (t == 1 || t == 2); c2 = (t == 4);   // WT quirk, see below
+      } else {
+        c0 = (t == 1); c1 = (t == 2); c2 = (t == 4);
+      }
+      signed char* y = a.yo + (long long)n * 3 * V + v;
+      y[0] = c0; y[V] = c1; y[2 * V] = c2;
+    }
+  }
+}
+
 static inline unsigned g1d(long long total) {
   long long b = (total + 255) / 256, cap = (long long)kNumSMs * 16;
   return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
@@ -123,6 +171,37 @@ static inline unsigned g1d(long long total) {
 using namespace nas3d;
 
 extern "C" {
+
+int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, int H, int W,
+                        const int* index_map, int inclusive, float* x_out, int ld_out,
+                        signed char* y_out, void* stream) {
+  NAS3D_REQUIRE(x && x_out && index_map, "stage_patches: null pointer");
+  NAS3D_REQUIRE(N >= 1 && N <= kStageMaxN, "stage_patches: batch %d outside [1,%d]", N, kStageMaxN);
+  NAS3D_REQUIRE(C >= 1 && ld_out >= C && D > 0 && H > 0 && W > 0, "stage_patches: bad shape");
+  NAS3D_REQUIRE((seg == nullptr) == (y_out == nullptr), "stage_patches: seg and y_out go together");
+  const long long V = (long long)D * H * W;
+  NAS3D_REQUIRE(V < (1ll << 31), "stage_patches: patch too large");
+  StageArgs a;
+  a.x = x; a.seg = seg; a.xo = x_out; a.yo = y_out;
+  a.N = N; a.C = C; a.D = D; a.H = H; a.W = W; a.ld = ld_out; a.inclusive = inclusive;
+  for (int n = 0; n < N; ++n) {
+    const int* m = index_map + 4 * n;
+    // the map must stay inside the source patch: check its two extreme corners
+    long long lo = m[0], hi = m[0];
+    const int ext[3] = {D - 1, H - 1, W - 1};
+    for (int k = 0; k < 3; ++k) {
+      const long long span = (long long)m[1 + k] * ext[k];
+      if (span < 0) lo += span; else hi += span;
+    }
+    NAS3D_REQUIRE(lo >= 0 && hi < V, "stage_patches: index map of sample %d leaves the patch", n);
+    a.base[n] = m[0];
+    a.sd[n][0] = m[1]; a.sd[n][1] = m[2]; a.sd[n][2] = m[3];
+  }
+  NAS3D_REQUIRE(!(C == 4 && ld_out == 4) || aligned16(x_out),
+                "stage_patches: x_out must be 16-byte aligned");
+  stage_patches_kernel<<<g1d(V * N), 256, 0, (cudaStream_t)stream>>>(a);
+  return launched("stage_patches");
+}
 
 int nas3d_extract_patches(const float* volume, int C, int D, int H, int W, const int* corners_dev,
                           int B, int Pd, int Ph, int Pw, float* out, int ld_out, void* stream) {

@@ -14,8 +14,86 @@ unchanged step loop:
     for x, y in DevicePrefetcher(train_generator.epoch(), device):
         optim.zero_grad(); loss = lossf(model(x), y); loss.backward(); optim.step()
 """
+import itertools
+import random
+
 import numpy as np
 import torch
+
+from . import _lib
+
+
+def permutation_keys():
+    """the 48 cube symmetries as the reference names them (augment.py:78-93):
+    ((rotate_y, rotate_z), flip_x, flip_y, flip_z, transpose)"""
+    rots = list(itertools.combinations_with_replacement(range(2), 2))
+    return sorted(itertools.product(rots, range(2), range(2), range(2), range(2)))
+
+
+def random_permutation_key(rng=random):
+    """augment.random_permutation_key (augment.py:96-101)"""
+    return rng.choice(permutation_keys())
+
+
+def index_map(key, shape):
+    """(base, stride_d, stride_h, stride_w): output voxel (d,h,w) of augment.permute_data(data, key)
+    (augment.py:105-132) is source voxel base + stride_d*d + stride_h*h + stride_w*w.  Derived by
+    pushing a cube of linear indices through the same numpy view operations (host, 3 ints/axis)."""
+    D, H, W = (int(s) for s in shape)
+    if key is None:
+        return (0, H * W, W, 1)
+    (rot_y, rot_z), flip_x, flip_y, flip_z, transpose = key
+    if (rot_y or rot_z or transpose) and not D == H == W:
+        raise AssertionError("Not a cubic patch!")       # generator.py:213
+    idx = np.arange(D * H * W, dtype=np.int64).reshape(1, D, H, W)
+    # strided views only - nothing the size of the patch is copied
+    if rot_y:
+        idx = np.rot90(idx, rot_y, axes=(1, 3))
+    if rot_z:
+        idx = np.rot90(idx, rot_z, axes=(2, 3))
+    if flip_x:
+        idx = idx[:, ::-1]
+    if flip_y:
+        idx = idx[:, :, ::-1]
+    if flip_z:
+        idx = idx[:, :, :, ::-1]
+    v = idx[0].T if transpose else idx[0]
+    base = int(v[0, 0, 0])
+    step = lambda ax: int(v[tuple(1 if a == ax else 0 for a in range(3))]) - base if v.shape[ax] > 1 else 0
+    return (base, step(0), step(1), step(2))
+
+
+def stage_batch(x, seg=None, keys=None, inclusive_label=True):
+    """device-side batch assembly: x (N,C,D,H,W) float32 CUDA (planar, as uploaded), seg (N,1,D,H,W)
+    int16 CUDA or None, keys = one permutation key per sample (or None = no permutation).
+    Returns (x in channels_last_3d memory - what the stem reads without a layout pass,
+             y (N,3,D,H,W) int8 region masks or None)  [generator.py:195-248]"""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise TypeError("stage_batch expects a CUDA float32 batch (no CPU path)")
+    x = x.contiguous()
+    N, C, D, H, W = x.shape
+    if seg is not None:
+        if not seg.is_cuda or seg.dtype != torch.int16 or seg.numel() != N * D * H * W:
+            raise TypeError("stage_batch: seg must be CUDA int16 of shape (N,1,D,H,W)")
+        seg = seg.contiguous()
+    if keys is None:
+        keys = [None] * N
+    if len(keys) != N:
+        raise ValueError("stage_batch: one permutation key per sample")
+    maps = []
+    for k in keys:
+        maps += index_map(k, (D, H, W))
+    ld = (C + 3) // 4 * 4
+    xo = torch.empty((N, D, H, W, ld), device=x.device, dtype=torch.float32)
+    yo = torch.empty((N, 3, D, H, W), device=x.device, dtype=torch.int8) if seg is not None else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.nas3d_stage_patches(
+            x.data_ptr(), seg.data_ptr() if seg is not None else None, N, C, D, H, W,
+            _lib.int_array(maps), 1 if inclusive_label else 0, xo.data_ptr(), ld,
+            yo.data_ptr() if yo is not None else None, st), "stage_patches")
+    return xo[..., :C].permute(0, 4, 1, 2, 3), yo
 
 
 class DevicePrefetcher:

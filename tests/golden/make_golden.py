@@ -212,11 +212,41 @@ def golden_cells():
 
 
 def main():
+    if '--permute' in sys.argv:
+        golden_permute()
+        return
     if '--datapath' not in sys.argv:
         golden_prims()
         golden_cells()
         golden_nets()
     golden_datapath()
+
+
+def _stub_heavy_imports():
+    import types
+    for name in ("h5py", "nibabel", "nilearn", "nilearn.image", "tqdm.notebook", "ipywidgets"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.tqdm = lambda it=None, **k: it
+            m.new_img_like = None
+            m.resample_to_img = None
+            m.reorder_img = None
+            m.Nifti1Image = None
+            sys.modules[name] = m
+
+
+def golden_permute():
+    """all 48 cube permutations of the reference's augment.permute_data (augment.py:105-132) on a
+    labelled (2,5,5,5) cube, keys in sorted order -> tests/golden/permute.npz"""
+    _stub_heavy_imports()
+    import augment as ref_augment
+    keys = sorted(ref_augment.generate_permutation_keys())
+    assert len(keys) == 48
+    data = np.arange(2 * 125, dtype=np.int16).reshape(2, 5, 5, 5)
+    out = np.stack([np.ascontiguousarray(ref_augment.permute_data(data, k)) for k in keys])
+    flat = np.array([[k[0][0], k[0][1], k[1], k[2], k[3], k[4]] for k in keys], dtype=np.int8)
+    np.savez_compressed(os.path.join(HERE, 'permute.npz'), keys=flat, data=data, out=out)
+    print('permute: done', out.shape)
 
 
 def golden_datapath():

@@ -61,3 +61,28 @@ def test_label_assembly_matches_reference(G):
     tt = np.array([0, 1, 2, 4, 3], dtype=np.int16).reshape(1, 1, 5, 1, 1)
     y = O.multi_class_labels(tt, True)[0, :, :, 0, 0]
     assert y.tolist() == [[0, 1, 0, 1, 0], [0, 1, 1, 0, 0], [0, 0, 0, 1, 0]]
+
+
+def test_permutation_matches_reference_all_48_keys():
+    """augment.permute_data (augment.py:105-132): oracle restatement and the host index map of the
+    CUDA staging kernel against the reference's outputs for every key (tests/golden/permute.npz)"""
+    import os
+    from conftest import ROOT
+    from nas_3d_unet_b200.data import index_map, permutation_keys
+    z = np.load(os.path.join(ROOT, "tests", "golden", "permute.npz"))
+    keys = O.permutation_keys()
+    assert keys == permutation_keys() and len(keys) == 48
+    assert [[k[0][0], k[0][1], k[1], k[2], k[3], k[4]] for k in keys] == z["keys"].tolist()
+    data = z["data"]
+    i, j, l = np.meshgrid(range(5), range(5), range(5), indexing="ij")
+    for n, k in enumerate(keys):
+        np.testing.assert_array_equal(O.permute_data(data, k), z["out"][n])
+        b, s0, s1, s2 = index_map(k, (5, 5, 5))
+        np.testing.assert_array_equal(data.reshape(2, -1)[:, b + s0 * i + s1 * j + s2 * l], z["out"][n])
+    # SURVEY App. D KAT
+    kat = O.permute_data(np.arange(54).reshape(2, 3, 3, 3), ((0, 1), 0, 1, 0, 1))[0, 0]
+    assert kat.tolist() == [[0, 9, 18], [1, 10, 19], [2, 11, 20]]
+    # flips alone are defined for non-cubic patches; rotations are not (generator.py:213)
+    assert index_map(((0, 0), 1, 0, 1, 0), (4, 6, 8)) == (151, -48, 8, -1)
+    with pytest.raises(AssertionError):
+        index_map(((0, 1), 0, 0, 0, 0), (4, 6, 8))
