@@ -148,3 +148,47 @@ def test_flat_adam_chunk_table_and_cpu_refusal():
         opt.step()
     with pytest.raises(NotImplementedError):
         FlatAdam([p], amsgrad=True)
+
+
+def test_compat_layer(tmp_path):
+    """SURVEY App. F shims: verbose= on ReduceLROnPlateau, torch.load of pickled containers,
+    np.int, tqdm.notebook, genotype file round trip in the drivers' (str, count) format"""
+    import collections
+    import pickle
+    import torch
+    from nas_3d_unet_b200 import compat
+    from nas_3d_unet_b200.genotype import Genotype
+    from oracle import nas3d_oracle as O
+    orig_load, orig_sched = torch.load, torch.optim.lr_scheduler.ReduceLROnPlateau
+    try:
+        compat.install()
+        compat.install()        # idempotent
+        assert np.int is int
+        from tqdm.notebook import tqdm as nb_tqdm
+        assert list(nb_tqdm(range(3), disable=True)) == [0, 1, 2]
+        from torch.optim.lr_scheduler import ReduceLROnPlateau
+        w = torch.nn.Parameter(torch.zeros(2))
+        opt = torch.optim.Adam([w])
+        sch = ReduceLROnPlateau(opt, verbose=True, factor=0.5)     # search.py:105
+        for _ in range(12):
+            sch.step(1.0)
+        assert opt.param_groups[0]["lr"] == 5e-4
+        sd = sch.state_dict()
+        ReduceLROnPlateau(opt, factor=0.5).load_state_dict(sd)
+        ck = tmp_path / "last.pt"
+        torch.save({"geno_count": collections.Counter(a=2), "hist": collections.defaultdict(list),
+                    "w": w.detach()}, ck)
+        back = torch.load(ck, map_location="cpu")                   # search.py:112
+        assert back["geno_count"]["a"] == 2 and torch.equal(back["w"], w.detach())
+    finally:
+        compat.uninstall()
+    assert torch.load is orig_load and torch.optim.lr_scheduler.ReduceLROnPlateau is orig_sched
+    gene = Genotype(down=O.G0.down, up=O.G0.up)
+    path = tmp_path / "best_genotype.pkl"
+    compat.save_genotype(gene, path, count=7)
+    text, count = pickle.load(open(path, "rb"))
+    assert count == 7 and eval(text, {"Genotype": Genotype}) == gene        # what train.py:38 does
+    g2, c2 = compat.load_genotype(path)
+    assert g2 == gene and c2 == 7
+    with pytest.raises(ValueError):
+        compat.parse_genotype("__import__('os').system('true')")
