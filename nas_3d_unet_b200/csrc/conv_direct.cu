@@ -547,12 +547,16 @@ int nas3d_conv_small_from_big(const nas3d_conv_desc* d, const float* big, const 
   A.src = big; A.w = w; A.bias = bias; A.scale = big_scale; A.relu = big_relu;
   A.sigmoid = out_sigmoid; A.dst = small; A.accumulate = accumulate;
   if (pointwise_shape(d)) {
-    // measured: per-voxel warp reductions cost more than a separate streaming statistics pass for
-    // these 1-voxel-per-thread kernels, so the 1x1 path does not fuse the moments
+    // GroupNorm statistics are fused when the tiles do not straddle samples, else a separate pass
     rc = pointwise_sfb(d, big, w, bias, big_scale, big_relu, out_sigmoid, small, accumulate,
-                       nullptr, (cudaStream_t)stream);
-    if (rc != NAS3D_ERR_UNSUPPORTED)
-      return rc ? rc : moments_fallback(moments, small, d->N, Vs, d->Cs, d->ld_small, stream);
+                       moments, (cudaStream_t)stream);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    if (moments) {
+      rc = pointwise_sfb(d, big, w, bias, big_scale, big_relu, out_sigmoid, small, accumulate,
+                         nullptr, (cudaStream_t)stream);
+      if (rc != NAS3D_ERR_UNSUPPORTED)
+        return rc ? rc : moments_fallback(moments, small, d->N, Vs, d->Cs, d->ld_small, stream);
+    }
   }
   if (dw3_shape(d) && !big_scale && !big_relu && !out_sigmoid) {
     if (d->stride == 1) {
@@ -743,6 +747,14 @@ int nas3d_conv1x1_cat_fwd(const nas3d_conv_desc* d, int nparts, const float* con
   int rc = cat_check(d, nparts);
   if (rc) return rc;
   PwCat cat{nparts, big_parts, nullptr, nullptr, part_ld, nullptr, nullptr};
+  if (moments)
+    NAS3D_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)d->N * d->Cs, (cudaStream_t)stream));
+  rc = pointwise_sfb(d, nullptr, w, bias, big_scale, big_relu, out_sigmoid, small, 0, moments,
+                     (cudaStream_t)stream, &cat);
+  if (rc != NAS3D_ERR_UNSUPPORTED || !moments) {
+    NAS3D_REQUIRE(rc != NAS3D_ERR_UNSUPPORTED, "conv1x1_cat_fwd: unsupported layout");
+    return rc;
+  }
   rc = pointwise_sfb(d, nullptr, w, bias, big_scale, big_relu, out_sigmoid, small, 0, nullptr,
                      (cudaStream_t)stream, &cat);
   NAS3D_REQUIRE(rc != NAS3D_ERR_UNSUPPORTED, "conv1x1_cat_fwd: unsupported layout");

@@ -48,9 +48,16 @@ __device__ __forceinline__ T pick4(const T (&a)[4], int i) {
 constexpr int PW_T = 128;
 constexpr int PW_MAX_W = 4096;   // floats of weights per (Cin x CO tile) in smem
 
-// BIGDST: the thread's voxel index runs over the small lattice; src/dst voxel addressing differs
-template <int CO, bool SRC_IS_BIG>
-__global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__ PwArgs A) {
+// Persistent forward / dgrad kernel.  A CTA owns a contiguous range of tiles of PW_T*VPT voxels (the
+// thread's voxels are tile + v*PW_T + tid, so every warp access is one contiguous span); the weight
+// tile is staged in shared memory once per CTA; the VPT independent 128-bit loads of a channel group
+// are issued back to back before the FMAs that consume them.  Optional fused GroupNorm statistics:
+// per tile the thread sums its VPT voxels, the warp reduces in fp32 (<=128 values per partial sum),
+// partial sums go to a per-CTA fp64 array that is flushed with one atomic per (channel, moment)
+// when the CTA crosses a sample boundary or ends (host guarantees tiles do not straddle samples).
+template <int CO, bool SRC_IS_BIG, int VPT>
+__global__ void __launch_bounds__(PW_T)
+    pointwise_kernel(const __grid_constant__ PwArgs A, unsigned tiles_per_cta) {
   __shared__ __align__(16) float Wsm[PW_MAX_W];
   __shared__ double sm_mom[2 * CO];
   if (threadIdx.x < 2 * CO) sm_mom[threadIdx.x] = 0.0;
@@ -61,172 +68,225 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__
     Wsm[i] = (co0 + j < A.Cout) ? __ldg(A.w + (long long)ci * A.w_stride_in + (long long)(co0 + j) * A.w_stride_out) : 0.f;
   }
   __syncthreads();
-  const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
-  const long long o = (long long)blockIdx.x * PW_T + threadIdx.x;
-  if (o >= nvox) return;     // never taken when moments are fused (host guarantees V % PW_T == 0)
-  long long big_idx = o;
-  int n;
-  {
-    long long t = o;
-    const int ow = (int)(t % A.Ws); t /= A.Ws;
-    const int oh = (int)(t % A.Hs); t /= A.Hs;
-    const int od = (int)(t % A.Ds);
-    n = (int)(t / A.Ds);
-    if (A.stride != 1)
-      big_idx = (((long long)n * A.Db + od * A.stride) * A.Hb + oh * A.stride) * A.Wb + ow * A.stride;
-  }
-  const long long src_idx = SRC_IS_BIG ? big_idx : o;
-  const long long dst_idx = SRC_IS_BIG ? o : big_idx;
-  const float* px = A.src + src_idx * A.ld_src;
+  constexpr unsigned TILE = PW_T * VPT;
+  const unsigned Vs = (unsigned)(A.Ds * A.Hs * A.Ws);
+  const unsigned nvox = (unsigned)A.N * Vs;
+  const unsigned ntiles = (nvox + TILE - 1) / TILE;
+  const unsigned t0 = blockIdx.x * tiles_per_cta;
+  const unsigned t1 = min(ntiles, t0 + tiles_per_cta);
   const bool vec_in = (A.Cin % 4 == 0) && (A.ld_src % 4 == 0);
-
-  float acc[CO];
-#pragma unroll
-  for (int j = 0; j < CO; ++j) acc[j] = 0.f;
-
-  for (int c4 = 0; c4 < A.Cin; c4 += 4) {
-    const int nv = min(4, A.Cin - c4);
-    float xv[4];
-    if (SRC_IS_BIG && A.nseg > 1) {
-      const int sg = (c4 >= A.seg_w) + (c4 >= 2 * A.seg_w) + (c4 >= 3 * A.seg_w);
-      const float4 t = ldg4(pick4(A.seg_src, sg) + src_idx * pick4(A.seg_ld, sg) + (c4 - sg * A.seg_w));
-      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-    } else if (vec_in) {
-      const float4 t = ldg4(px + c4);
-      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) xv[e] = e < nv ? __ldg(px + c4 + e) : 0.f;
-    }
-    if (SRC_IS_BIG) {
-      if (A.relu) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) xv[e] = fmaxf(xv[e], 0.f);
-      }
-      if (A.scale) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < nv) xv[e] *= __ldg(A.scale + (long long)n * A.Cin + c4 + e);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (e < nv) {
-        const float* wr = Wsm + (c4 + e) * CO;
-#pragma unroll
-        for (int j4 = 0; j4 < CO / 4; ++j4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wr + j4 * 4);
-          acc[j4 * 4 + 0] += xv[e] * w4.x; acc[j4 * 4 + 1] += xv[e] * w4.y;
-          acc[j4 * 4 + 2] += xv[e] * w4.z; acc[j4 * 4 + 3] += xv[e] * w4.w;
-        }
-      }
-    }
-  }
-
-  float* pd = A.dst + dst_idx * A.ld_dst + co0;
   const bool vec_out = (A.ld_dst % 4 == 0) && (co0 + CO <= A.Cout);
-  // fast path: whole float4 channel groups, all per-channel operands fetched as float4
+  // fast epilogue: whole float4 channel groups, all per-channel operands fetched as float4
   const bool fast = (A.Cout % 4 == 0) && (A.nseg > 1 || vec_out) &&
                     (A.mask == nullptr || A.ld_mask % 4 == 0);
+  const bool need_n = A.stride != 1 || A.scale != nullptr;
+  int mom_n = -1;
+
+  for (unsigned tile = t0; tile < t1; ++tile) {
+    unsigned o[VPT];
+    long long sidx[VPT], didx[VPT];
+    int n[VPT];
+    bool ok[VPT];
 #pragma unroll
-  for (int j4 = 0; j4 < CO / 4; ++j4) {
-    const int c = co0 + j4 * 4;
-    float v[4] = {acc[j4 * 4 + 0], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]};
-    if (fast) {
-      if (c >= A.Cout) continue;
-      // segment of this channel group (equal widths, multiples of 4): no integer division
-      const int sg = (A.nseg > 1) ? (c >= A.seg_w) + (c >= 2 * A.seg_w) + (c >= 3 * A.seg_w) : 0;
-      const int off = c - sg * A.seg_w;
-      if (A.bias) {
-        const float4 b4 = ldg4(A.bias + c);
-        v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
-      }
-      if (!SRC_IS_BIG) {
-        const float* mp = nullptr;
-        if (A.nseg > 1) {
-          const float* mb = pick4(A.seg_mask, sg);
-          if (mb) mp = mb + dst_idx * pick4(A.seg_mask_ld, sg) + off;
-        } else if (A.mask) {
-          mp = A.mask + dst_idx * A.ld_mask + c;
+    for (int v = 0; v < VPT; ++v) {
+      o[v] = tile * TILE + v * PW_T + threadIdx.x;
+      ok[v] = o[v] < nvox;
+      const unsigned oo = ok[v] ? o[v] : 0u;
+      long long big_idx = oo;
+      n[v] = 0;
+      if (need_n) {
+        const unsigned nn = oo / Vs;
+        n[v] = (int)nn;
+        if (A.stride != 1) {
+          unsigned r = oo - nn * Vs;
+          const unsigned ow = r % (unsigned)A.Ws; r /= (unsigned)A.Ws;
+          const unsigned oh = r % (unsigned)A.Hs;
+          const unsigned od = r / (unsigned)A.Hs;
+          big_idx = (((long long)nn * A.Db + od * A.stride) * A.Hb + oh * A.stride) * A.Wb + ow * A.stride;
         }
-        if (mp) {
-          const float4 m4 = ldg4(mp);
-          v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-          v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+      }
+      sidx[v] = SRC_IS_BIG ? big_idx : (long long)oo;
+      didx[v] = SRC_IS_BIG ? (long long)oo : big_idx;
+    }
+
+    float acc[VPT][CO];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v)
+#pragma unroll
+      for (int j = 0; j < CO; ++j) acc[v][j] = 0.f;
+
+#pragma unroll 2
+    for (int c4 = 0; c4 < A.Cin; c4 += 4) {
+      const int nv = min(4, A.Cin - c4);
+      float xv[VPT][4];
+      if (SRC_IS_BIG && A.nseg > 1) {
+        const int sg = (c4 >= A.seg_w) + (c4 >= 2 * A.seg_w) + (c4 >= 3 * A.seg_w);
+        const float* sb = pick4(A.seg_src, sg) + (c4 - sg * A.seg_w);
+        const int sl = pick4(A.seg_ld, sg);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const float4 t = ldg4(sb + sidx[v] * sl);
+          xv[v][0] = t.x; xv[v][1] = t.y; xv[v][2] = t.z; xv[v][3] = t.w;
+        }
+      } else if (vec_in) {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const float4 t = ldg4(A.src + sidx[v] * A.ld_src + c4);
+          xv[v][0] = t.x; xv[v][1] = t.y; xv[v][2] = t.z; xv[v][3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            xv[v][e] = e < nv ? __ldg(A.src + sidx[v] * A.ld_src + c4 + e) : 0.f;
+      }
+      if (SRC_IS_BIG) {
+        if (A.relu) {
+#pragma unroll
+          for (int v = 0; v < VPT; ++v)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xv[v][e] = fmaxf(xv[v][e], 0.f);
         }
         if (A.scale) {
-          const float4 s4 = ldg4(A.scale + (long long)n * A.Cout + c);
-          v[0] *= s4.x; v[1] *= s4.y; v[2] *= s4.z; v[3] *= s4.w;
+#pragma unroll
+          for (int v = 0; v < VPT; ++v)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nv) xv[v][e] *= __ldg(A.scale + (long long)n[v] * A.Cin + c4 + e);
         }
       }
-      if (A.sigmoid) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
-      }
-      if (A.moments) {
-        float ms[4], mq[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { ms[e] = v[e]; mq[e] = v[e] * v[e]; }
-        warp_moments_add(sm_mom, j4 * 4, ms, mq);
-      }
-      float* ps;
-      int do_acc;
-      if (!SRC_IS_BIG && A.nseg > 1) {
-        ps = pick4(A.seg_dst, sg) + dst_idx * pick4(A.seg_ld, sg) + off;
-        do_acc = pick4(A.seg_acc, sg);
-      } else {
-        ps = pd + j4 * 4;
-        do_acc = A.accumulate;
-      }
-      float4 r = make_float4(v[0], v[1], v[2], v[3]);
-      if (do_acc) {
-        const float4 old = *reinterpret_cast<const float4*>(ps);
-        r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
-      }
-      st4(ps, r);
-      continue;
-    }
-    // generic scalar path (Cout not a multiple of 4, e.g. the 12->3 head)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int ce = c + e;
-      float t = v[e];
-      if (ce < A.Cout) {
-        if (A.bias) t += __ldg(A.bias + ce);
-        if (!SRC_IS_BIG) {
-          if (A.mask) t = (__ldg(A.mask + dst_idx * A.ld_mask + ce) > 0.f) ? t : 0.f;
-          if (A.scale) t *= __ldg(A.scale + (long long)n * A.Cout + ce);
-        }
-        if (A.sigmoid) t = 1.f / (1.f + __expf(-t));
-      }
-      v[e] = t;
-    }
-    if (A.moments) {
-      float ms[4], mq[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { ms[e] = v[e]; mq[e] = v[e] * v[e]; }
-      warp_moments_add(sm_mom, j4 * 4, ms, mq);
-    }
-    if (vec_out) {
-      float4 r = make_float4(v[0], v[1], v[2], v[3]);
-      if (A.accumulate) {
-        const float4 old = *reinterpret_cast<const float4*>(pd + j4 * 4);
-        r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
-      }
-      st4(pd + j4 * 4, r);
-    } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int ce = c + e;
-        if (ce < A.Cout) pd[j4 * 4 + e] = A.accumulate ? pd[j4 * 4 + e] + v[e] : v[e];
+        if (e < nv) {
+          const float* wr = Wsm + (c4 + e) * CO;
+#pragma unroll
+          for (int j4 = 0; j4 < CO / 4; ++j4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wr + j4 * 4);
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+              acc[v][j4 * 4 + 0] += xv[v][e] * w4.x; acc[v][j4 * 4 + 1] += xv[v][e] * w4.y;
+              acc[v][j4 * 4 + 2] += xv[v][e] * w4.z; acc[v][j4 * 4 + 3] += xv[v][e] * w4.w;
+            }
+          }
+        }
+      }
+    }
+
+    if (A.moments) {   // uniform per CTA: all voxels of a tile belong to one sample
+      const int tn = (int)((tile * TILE) / Vs);
+      if (tn != mom_n) {
+        if (mom_n >= 0) {
+          __syncthreads();
+          for (int i = threadIdx.x; i < 2 * CO; i += PW_T)
+            if (co0 + i / 2 < A.Cout) {
+              atomicAdd(&A.moments[((long long)mom_n * A.Cout + co0) * 2 + i], sm_mom[i]);
+              sm_mom[i] = 0.0;
+            }
+          __syncthreads();
+        }
+        mom_n = tn;
+      }
+    }
+
+#pragma unroll
+    for (int j4 = 0; j4 < CO / 4; ++j4) {
+      const int c = co0 + j4 * 4;
+      if (fast && c >= A.Cout) continue;
+      float ms[4] = {0.f, 0.f, 0.f, 0.f}, mq[4] = {0.f, 0.f, 0.f, 0.f};
+      // per-channel operands shared by the thread's voxels
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int sg = 0, off = c;
+      if (fast) {
+        // segment of this channel group (equal widths, multiples of 4): no integer division
+        sg = (A.nseg > 1) ? (c >= A.seg_w) + (c >= 2 * A.seg_w) + (c >= 3 * A.seg_w) : 0;
+        off = c - sg * A.seg_w;
+        if (A.bias) b4 = ldg4(A.bias + c);
+      }
+#pragma unroll
+      for (int vv = 0; vv < VPT; ++vv) {
+        if (!ok[vv]) continue;
+        float v[4] = {acc[vv][j4 * 4 + 0], acc[vv][j4 * 4 + 1], acc[vv][j4 * 4 + 2], acc[vv][j4 * 4 + 3]};
+        const long long dst_idx = didx[vv];
+        float* pd = A.dst + dst_idx * A.ld_dst + co0;
+        if (fast) {
+          v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+          if (!SRC_IS_BIG) {
+            const float* mp = nullptr;
+            if (A.nseg > 1) {
+              const float* mb = pick4(A.seg_mask, sg);
+              if (mb) mp = mb + dst_idx * pick4(A.seg_mask_ld, sg) + off;
+            } else if (A.mask) {
+              mp = A.mask + dst_idx * A.ld_mask + c;
+            }
+            if (mp) {
+              const float4 m4 = ldg4(mp);
+              v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+              v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+            }
+            if (A.scale) {
+              const float4 s4 = ldg4(A.scale + (long long)n[vv] * A.Cout + c);
+              v[0] *= s4.x; v[1] *= s4.y; v[2] *= s4.z; v[3] *= s4.w;
+            }
+          }
+          if (A.sigmoid) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { ms[e] += v[e]; mq[e] += v[e] * v[e]; }
+          float* ps;
+          int do_acc;
+          if (!SRC_IS_BIG && A.nseg > 1) {
+            ps = pick4(A.seg_dst, sg) + dst_idx * pick4(A.seg_ld, sg) + off;
+            do_acc = pick4(A.seg_acc, sg);
+          } else {
+            ps = pd + j4 * 4;
+            do_acc = A.accumulate;
+          }
+          float4 r = make_float4(v[0], v[1], v[2], v[3]);
+          if (do_acc) {
+            const float4 old = *reinterpret_cast<const float4*>(ps);
+            r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+          }
+          st4(ps, r);
+          continue;
+        }
+        // generic scalar path (Cout not a multiple of 4, e.g. the 12->3 head)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ce = c + e;
+          float t = v[e];
+          if (ce < A.Cout) {
+            if (A.bias) t += __ldg(A.bias + ce);
+            if (!SRC_IS_BIG) {
+              if (A.mask) t = (__ldg(A.mask + dst_idx * A.ld_mask + ce) > 0.f) ? t : 0.f;
+              if (A.scale) t *= __ldg(A.scale + (long long)n[vv] * A.Cout + ce);
+            }
+            if (A.sigmoid) t = 1.f / (1.f + __expf(-t));
+            ms[e] += t; mq[e] += t * t;
+            pd[j4 * 4 + e] = A.accumulate ? pd[j4 * 4 + e] + t : t;
+          }
+        }
+      }
+      if (A.moments) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = warp_sum(ms[e]);
+          const float b = warp_sum(mq[e]);
+          if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&sm_mom[(j4 * 4 + e) * 2 + 0], (double)a);
+            atomicAdd(&sm_mom[(j4 * 4 + e) * 2 + 1], (double)b);
+          }
+        }
       }
     }
   }
-  if (A.moments) {
+  if (A.moments && mom_n >= 0) {
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * CO; i += PW_T)
       if (co0 + i / 2 < A.Cout)
-        atomicAdd(&A.moments[((long long)n * A.Cout + co0) * 2 + i], sm_mom[i]);
+        atomicAdd(&A.moments[((long long)mom_n * A.Cout + co0) * 2 + i], sm_mom[i]);
   }
 }
 
@@ -238,7 +298,7 @@ template <int TS, int TB>
 __global__ void __launch_bounds__(PWG_T)
     pointwise_wgrad_kernel(const __grid_constant__ PwArgs A, const float* __restrict__ small,
                            const float* __restrict__ big, int Cs, int Cb, int lds, int ldb,
-                           float* __restrict__ dW, float* __restrict__ dbias_small) {
+                           float* __restrict__ dW, float* __restrict__ dbias_small, int iters) {
   const int cs0 = blockIdx.y * TS, cb0 = blockIdx.z * TB;
   const int ns = min(TS, Cs - cs0), nb = min(TB, Cb - cb0);
   const bool vec_s = (lds % 4 == 0) && (ns == TS) && (TS % 4 == 0);
@@ -253,8 +313,9 @@ __global__ void __launch_bounds__(PWG_T)
     for (int j = 0; j < TB; ++j) acc[i][j] = 0.f;
   }
   const bool do_bias = dbias_small != nullptr && blockIdx.z == 0;
-  for (int it = 0; it < PWG_ITER; ++it) {
-    const long long o = ((long long)blockIdx.x * PWG_ITER + it) * PWG_T + threadIdx.x;
+#pragma unroll 2
+  for (int it = 0; it < iters; ++it) {
+    const long long o = ((long long)blockIdx.x * iters + it) * PWG_T + threadIdx.x;
     if (o >= nvox) break;
     long long bidx = o;
     int n;
@@ -344,18 +405,36 @@ __global__ void __launch_bounds__(PWG_T)
   }
 }
 
+static inline bool pointwise_big(long long nvox) { return nvox >= (long long)kNumSMs * 8 * PW_T * 4; }
+
+template <int CO, bool SRC_IS_BIG>
+static void launch_pointwise_co(const PwArgs& A, unsigned gy, cudaStream_t st) {
+  const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
+  // big tensors: 4 voxels per thread and ~8 CTAs per SM, each walking a contiguous range of tiles;
+  // small (deep-level) tensors: 1 voxel per thread, one tile per CTA - they are latency-bound
+  if (pointwise_big(nvox)) {
+    const unsigned ntiles = (unsigned)((nvox + PW_T * 4 - 1) / (PW_T * 4));
+    unsigned per = (ntiles + kNumSMs * 8 - 1) / (kNumSMs * 8);
+    const unsigned gx = (ntiles + per - 1) / per;
+    pointwise_kernel<CO, SRC_IS_BIG, 4><<<dim3(gx, gy), PW_T, 0, st>>>(A, per);
+  } else {
+    const unsigned ntiles = (unsigned)((nvox + PW_T - 1) / PW_T);
+    pointwise_kernel<CO, SRC_IS_BIG, 1><<<dim3(ntiles, gy), PW_T, 0, st>>>(A, 1u);
+  }
+}
+
 template <bool SRC_IS_BIG>
 static int launch_pointwise(const PwArgs& A, cudaStream_t st) {
   const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
-  const unsigned gx = (unsigned)((nvox + PW_T - 1) / PW_T);
+  if (nvox >= (1ll << 31) - PW_T * 4) return NAS3D_ERR_UNSUPPORTED;   // 32-bit voxel indices
   int co_t = A.Cout <= 4 ? 4 : A.Cout <= 8 ? 8 : A.Cout <= 12 ? 12 : 16;
   if (A.Cin * co_t > PW_MAX_W) return NAS3D_ERR_UNSUPPORTED;
   const unsigned gy = (unsigned)((A.Cout + co_t - 1) / co_t);
   switch (co_t) {
-    case 4: pointwise_kernel<4, SRC_IS_BIG><<<dim3(gx, gy), PW_T, 0, st>>>(A); break;
-    case 8: pointwise_kernel<8, SRC_IS_BIG><<<dim3(gx, gy), PW_T, 0, st>>>(A); break;
-    case 12: pointwise_kernel<12, SRC_IS_BIG><<<dim3(gx, gy), PW_T, 0, st>>>(A); break;
-    default: pointwise_kernel<16, SRC_IS_BIG><<<dim3(gx, gy), PW_T, 0, st>>>(A); break;
+    case 4: launch_pointwise_co<4, SRC_IS_BIG>(A, gy, st); break;
+    case 8: launch_pointwise_co<8, SRC_IS_BIG>(A, gy, st); break;
+    case 12: launch_pointwise_co<12, SRC_IS_BIG>(A, gy, st); break;
+    default: launch_pointwise_co<16, SRC_IS_BIG>(A, gy, st); break;
   }
   return launched("pointwise");
 }
@@ -384,8 +463,12 @@ static bool fill_segments(PwArgs* A, const PwCat* cat, int Cb) {
 int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
                   const float* scale, int relu, int sigmoid, float* small, int accumulate,
                   double* moments, cudaStream_t st, const PwCat* cat) {
-  if (moments && (((long long)d->Ds * d->Hs * d->Ws) % PW_T != 0 || accumulate || sigmoid))
-    return NAS3D_ERR_UNSUPPORTED;
+  // fused statistics need tiles that do not straddle samples
+  if (moments) {
+    const long long Vs = (long long)d->Ds * d->Hs * d->Ws;
+    const long long tile = pointwise_big(Vs * d->N) ? PW_T * 4 : PW_T;
+    if (Vs % tile != 0 || accumulate || sigmoid) return NAS3D_ERR_UNSUPPORTED;
+  }
   if (!cat && d->Cb % 4 == 0 && d->ld_big % 4 == 0 && !aligned16(big)) return NAS3D_ERR_UNSUPPORTED;
   PwArgs A{};
   if (!fill_segments(&A, cat, d->Cb)) return NAS3D_ERR_UNSUPPORTED;
@@ -439,17 +522,31 @@ int pointwise_wgrad(const nas3d_conv_desc* d, const float* small, const float* b
   A.N = d->N; A.Ds = d->Ds; A.Hs = d->Hs; A.Ws = d->Ws; A.Db = d->Db; A.Hb = d->Hb; A.Wb = d->Wb;
   A.stride = d->stride; A.relu = relu; A.scale = scale;
   const long long nvox = (long long)d->N * d->Ds * d->Hs * d->Ws;
-  const long long per_block = (long long)PWG_T * PWG_ITER;
-  const unsigned gx = (unsigned)((nvox + per_block - 1) / per_block);
   const int Cs = d->Cs, Cb = d->Cb;
-  const unsigned gy = (unsigned)((Cs + 3) / 4);
-  if (Cb % 12 == 0 && Cb <= 48) {
-    pointwise_wgrad_kernel<4, 12><<<dim3(gx, gy, Cb / 12), PWG_T, 0, st>>>(A, small, big, Cs, Cb, d->ld_small, d->ld_big, dW, dbias_small);
-  } else if (Cb % 8 == 0) {
-    pointwise_wgrad_kernel<4, 8><<<dim3(gx, gy, Cb / 8), PWG_T, 0, st>>>(A, small, big, Cs, Cb, d->ld_small, d->ld_big, dW, dbias_small);
-  } else {
-    pointwise_wgrad_kernel<4, 4><<<dim3(gx, gy, (Cb + 3) / 4), PWG_T, 0, st>>>(A, small, big, Cs, Cb, d->ld_small, d->ld_big, dW, dbias_small);
-  }
+  // register tile over (small, big) channels: cover the whole matrix when it is small so each
+  // tensor is read once; voxels per thread shrink for small (deep-level) tensors so that at least
+  // ~4 CTAs per SM share the reduction
+  int ts, tb;
+  if (Cs % 12 == 0 && Cb == 4) { ts = 12; tb = 4; }
+  else if (Cb % 12 == 0 && Cb <= 48) { ts = 4; tb = 12; }
+  else if (Cs % 8 == 0 && Cb % 8 == 0) { ts = 8; tb = 8; }
+  else if (Cb % 8 == 0) { ts = 4; tb = 8; }
+  else { ts = 4; tb = 4; }
+  const unsigned gy = (unsigned)((Cs + ts - 1) / ts), gz = (unsigned)((Cb + tb - 1) / tb);
+  long long it = nvox * gy * gz / ((long long)kNumSMs * 4 * PWG_T);
+  const int iters = (int)(it < 1 ? 1 : (it > PWG_ITER ? PWG_ITER : it));
+  const long long per_block = (long long)PWG_T * iters;
+  const unsigned gx = (unsigned)((nvox + per_block - 1) / per_block);
+  const dim3 grid(gx, gy, gz);
+#define NAS3D_PWG(TS_, TB_)                                                                       \
+  pointwise_wgrad_kernel<TS_, TB_><<<grid, PWG_T, 0, st>>>(A, small, big, Cs, Cb, d->ld_small,     \
+                                                           d->ld_big, dW, dbias_small, iters)
+  if (ts == 12) NAS3D_PWG(12, 4);
+  else if (tb == 12) NAS3D_PWG(4, 12);
+  else if (ts == 8) NAS3D_PWG(8, 8);
+  else if (tb == 8) NAS3D_PWG(4, 8);
+  else NAS3D_PWG(4, 4);
+#undef NAS3D_PWG
   return launched("pointwise_wgrad");
 }
 

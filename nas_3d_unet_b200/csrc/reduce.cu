@@ -22,10 +22,10 @@ constexpr int RITER = 32;   // super-elements per thread
 template <int U>
 __global__ void __launch_bounds__(RB) moments_nc_kernel(const float* __restrict__ x, long long V,
                                                          int C, int ld, int P, int logP,
-                                                         double* __restrict__ S) {
+                                                         double* __restrict__ S, int iters) {
   const int n = blockIdx.y;
   const long long total = V << logP;  // super-elements in this sample
-  const long long j0 = (long long)blockIdx.x * (RB * RITER) + threadIdx.x;
+  const long long j0 = (long long)blockIdx.x * (RB * iters) + threadIdx.x;
   const int p = threadIdx.x & (P - 1);
   const float* xb = x + (long long)n * V * ld + (long long)p * U * 4;
 
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(RB) moments_nc_kernel(const float* __restrict_
     for (int e = 0; e < 4; ++e) s[u][e] = q[u][e] = 0.f;
 
 #pragma unroll 4
-  for (int it = 0; it < RITER; ++it) {
+  for (int it = 0; it < iters; ++it) {
     long long j = j0 + (long long)it * RB;
     if (j < total) {
       const float* px = xb + (j >> logP) * ld;
@@ -90,11 +90,11 @@ struct ReduceTerms {
 template <int U, int TG>
 __global__ void __launch_bounds__(RB)
     bwd_reduce_kernel(const __grid_constant__ ReduceTerms T, const float* __restrict__ dout,
-                      int ld_dout, long long V, int C, int P, int logP) {
+                      int ld_dout, long long V, int C, int P, int logP, int iters) {
   const int n = blockIdx.y;
   const int k0 = blockIdx.z * TG;
   const long long total = V << logP;
-  const long long j0 = (long long)blockIdx.x * (RB * RITER) + threadIdx.x;
+  const long long j0 = (long long)blockIdx.x * (RB * iters) + threadIdx.x;
   const int p = threadIdx.x & (P - 1);
   const int cbase = p * U * 4;
   const float* db = dout + (long long)n * V * ld_dout + cbase;
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(RB)
 #pragma unroll
       for (int e = 0; e < 4; ++e) r1[t][u][e] = r2[t][u][e] = 0.f;
 
-  for (int it = 0; it < RITER; ++it) {
+#pragma unroll 2
+  for (int it = 0; it < iters; ++it) {
     long long j = j0 + (long long)it * RB;
     if (j >= total) break;
     const long long vox = j >> logP;
@@ -435,6 +436,16 @@ __global__ void __launch_bounds__(TB)
   }
 }
 
+// super-elements per thread: RITER for big tensors (fewest atomics), fewer when the tensor is small
+// so that at least ~4 CTAs per SM share the work (deep U-Net levels are latency-, not HBM-bound)
+static int reduce_iters(long long total_per_sample, int N, int zdim) {
+  const long long want_ctas = (long long)kNumSMs * 4;
+  long long it = total_per_sample * N * zdim / (want_ctas * RB);
+  if (it < 1) it = 1;
+  if (it > RITER) it = RITER;
+  return (int)it;
+}
+
 static int check_channels(int C, int ld, int* U, int* P, int* logP) {
   NAS3D_REQUIRE(C > 0 && C % 4 == 0 && ld % 4 == 0 && ld >= C,
                 "channel count %d / pitch %d must be multiples of 4", C, ld);
@@ -466,9 +477,10 @@ int nas3d_moments_nc(const float* x, int N, long long V, int C, int ld, double* 
   cudaStream_t st = (cudaStream_t)stream;
   NAS3D_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * (size_t)N * C, st));
   long long total = V * P;
-  dim3 grid((unsigned)((total + RB * RITER - 1) / (RB * RITER)), N);
-  if (U == 1) moments_nc_kernel<1><<<grid, RB, 0, st>>>(x, V, C, ld, P, logP, S);
-  else moments_nc_kernel<3><<<grid, RB, 0, st>>>(x, V, C, ld, P, logP, S);
+  const int iters = reduce_iters(total, N, 1);
+  dim3 grid((unsigned)((total + RB * iters - 1) / (RB * iters)), N);
+  if (U == 1) moments_nc_kernel<1><<<grid, RB, 0, st>>>(x, V, C, ld, P, logP, S, iters);
+  else moments_nc_kernel<3><<<grid, RB, 0, st>>>(x, V, C, ld, P, logP, S, iters);
   return launched("moments_nc");
 }
 
@@ -535,25 +547,35 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
   cudaStream_t st = (cudaStream_t)stream;
   ReduceTerms T;
   T.nterms = nterms;
+  // R buffers carved from one allocation are cleared with a single memset node
+  const size_t rbytes = sizeof(double) * 2 * (size_t)N * C;
+  bool contiguous = true;
   for (int k = 0; k < nterms; ++k) {
     NAS3D_REQUIRE(ld_x[k] % 4 == 0 && aligned16(x[k]), "bwd_reduce: term %d misaligned", k);
     T.x[k] = x[k]; T.a[k] = a ? a[k] : nullptr; T.b[k] = b ? b[k] : nullptr;
     T.R[k] = R[k]; T.ld[k] = ld_x[k]; T.relu[k] = relu ? relu[k] : 0;
-    NAS3D_CUDA(cudaMemsetAsync(R[k], 0, sizeof(double) * 2 * (size_t)N * C, st));
+    if (k > 0 && (const char*)R[k] != (const char*)R[k - 1] + rbytes) contiguous = false;
+  }
+  if (contiguous) {
+    NAS3D_CUDA(cudaMemsetAsync(R[0], 0, rbytes * nterms, st));
+  } else {
+    for (int k = 0; k < nterms; ++k) NAS3D_CUDA(cudaMemsetAsync(R[k], 0, rbytes, st));
   }
   long long total = V * P;
-  unsigned gx = (unsigned)((total + RB * RITER - 1) / (RB * RITER));
   // TG=2 keeps the fp64 staging array (TG*C*2 doubles) inside 48 KB static smem for C<=768/..;
   // wide tensors are tiny in this network so TG=1 there.
   if (U == 1 && C <= 256) {
-    dim3 grid(gx, N, (nterms + 1) / 2);
-    bwd_reduce_kernel<1, 2><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP);
+    const int zd = (nterms + 1) / 2, iters = reduce_iters(total, N, zd);
+    dim3 grid((unsigned)((total + RB * iters - 1) / (RB * iters)), N, zd);
+    bwd_reduce_kernel<1, 2><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP, iters);
   } else if (U == 1) {
-    dim3 grid(gx, N, nterms);
-    bwd_reduce_kernel<1, 1><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP);
+    const int iters = reduce_iters(total, N, nterms);
+    dim3 grid((unsigned)((total + RB * iters - 1) / (RB * iters)), N, nterms);
+    bwd_reduce_kernel<1, 1><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP, iters);
   } else {
-    dim3 grid(gx, N, nterms);
-    bwd_reduce_kernel<3, 1><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP);
+    const int iters = reduce_iters(total, N, nterms);
+    dim3 grid((unsigned)((total + RB * iters - 1) / (RB * iters)), N, nterms);
+    bwd_reduce_kernel<3, 1><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP, iters);
   }
   return launched("affine_sum_bwd_reduce");
 }
