@@ -9,6 +9,7 @@
 //   BFS  big[o*s,cb] (+)= sum_cs small[o,cs] W[cs][cb]              (Conv3d dgrad; stride 2 only
 //                                                                    touches the even voxels)
 //   WG   dW[cs][cb]  += sum_o small[o,cs] f(big[o*s,cb])
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_tiled.h"
 
@@ -48,16 +49,16 @@ __device__ __forceinline__ T pick4(const T (&a)[4], int i) {
 constexpr int PW_T = 128;
 constexpr int PW_MAX_W = 4096;   // floats of weights per (Cin x CO tile) in smem
 
-// Persistent forward / dgrad kernel.  A CTA owns a contiguous range of tiles of PW_T*VPT voxels (the
+// Persistent forward / dgrad kernel.  The grid is exactly the resident capacity (occupancy x SMs) and
+// strides over tiles of PW_T*VPT voxels, so there is no partial last wave (the
 // thread's voxels are tile + v*PW_T + tid, so every warp access is one contiguous span); the weight
 // tile is staged in shared memory once per CTA; the VPT independent 128-bit loads of a channel group
 // are issued back to back before the FMAs that consume them.  Optional fused GroupNorm statistics:
 // per tile the thread sums its VPT voxels, the warp reduces in fp32 (<=128 values per partial sum),
 // partial sums go to a per-CTA fp64 array that is flushed with one atomic per (channel, moment)
 // when the CTA crosses a sample boundary or ends (host guarantees tiles do not straddle samples).
-template <int CO, bool SRC_IS_BIG, int VPT>
-__global__ void __launch_bounds__(PW_T)
-    pointwise_kernel(const __grid_constant__ PwArgs A, unsigned tiles_per_cta) {
+template <int CO, bool SRC_IS_BIG, int VPT, bool MOM>
+__global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__ PwArgs A) {
   __shared__ __align__(16) float Wsm[PW_MAX_W];
   __shared__ double sm_mom[2 * CO];
   if (threadIdx.x < 2 * CO) sm_mom[threadIdx.x] = 0.0;
@@ -72,8 +73,6 @@ __global__ void __launch_bounds__(PW_T)
   const unsigned Vs = (unsigned)(A.Ds * A.Hs * A.Ws);
   const unsigned nvox = (unsigned)A.N * Vs;
   const unsigned ntiles = (nvox + TILE - 1) / TILE;
-  const unsigned t0 = blockIdx.x * tiles_per_cta;
-  const unsigned t1 = min(ntiles, t0 + tiles_per_cta);
   const bool vec_in = (A.Cin % 4 == 0) && (A.ld_src % 4 == 0);
   const bool vec_out = (A.ld_dst % 4 == 0) && (co0 + CO <= A.Cout);
   // fast epilogue: whole float4 channel groups, all per-channel operands fetched as float4
@@ -81,8 +80,31 @@ __global__ void __launch_bounds__(PW_T)
                     (A.mask == nullptr || A.ld_mask % 4 == 0);
   const bool need_n = A.stride != 1 || A.scale != nullptr;
   int mom_n = -1;
+  float ms[MOM ? CO : 1], mq[MOM ? CO : 1];   // per-thread partial statistics, carried across tiles
+#pragma unroll
+  for (int j = 0; j < (MOM ? CO : 1); ++j) ms[j] = mq[j] = 0.f;
+  // warp-reduce the partials into the CTA's fp64 array, then one atomic per (channel, moment)
+  auto flush_moments = [&](int n_flush) {
+#pragma unroll
+    for (int j = 0; j < (MOM ? CO : 1); ++j) {
+      const float a = warp_sum(ms[j]);
+      const float b = warp_sum(mq[j]);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sm_mom[j * 2 + 0], (double)a);
+        atomicAdd(&sm_mom[j * 2 + 1], (double)b);
+      }
+      ms[j] = mq[j] = 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CO; i += PW_T)
+      if (co0 + i / 2 < A.Cout) {
+        atomicAdd(&A.moments[((long long)n_flush * A.Cout + co0) * 2 + i], sm_mom[i]);
+        sm_mom[i] = 0.0;
+      }
+    __syncthreads();
+  };
 
-  for (unsigned tile = t0; tile < t1; ++tile) {
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     unsigned o[VPT];
     long long sidx[VPT], didx[VPT];
     int n[VPT];
@@ -173,18 +195,10 @@ __global__ void __launch_bounds__(PW_T)
       }
     }
 
-    if (A.moments) {   // uniform per CTA: all voxels of a tile belong to one sample
+    if (MOM) {   // uniform per CTA: all voxels of a tile belong to one sample
       const int tn = (int)((tile * TILE) / Vs);
       if (tn != mom_n) {
-        if (mom_n >= 0) {
-          __syncthreads();
-          for (int i = threadIdx.x; i < 2 * CO; i += PW_T)
-            if (co0 + i / 2 < A.Cout) {
-              atomicAdd(&A.moments[((long long)mom_n * A.Cout + co0) * 2 + i], sm_mom[i]);
-              sm_mom[i] = 0.0;
-            }
-          __syncthreads();
-        }
+        if (mom_n >= 0) flush_moments(mom_n);
         mom_n = tn;
       }
     }
@@ -193,7 +207,6 @@ __global__ void __launch_bounds__(PW_T)
     for (int j4 = 0; j4 < CO / 4; ++j4) {
       const int c = co0 + j4 * 4;
       if (fast && c >= A.Cout) continue;
-      float ms[4] = {0.f, 0.f, 0.f, 0.f}, mq[4] = {0.f, 0.f, 0.f, 0.f};
       // per-channel operands shared by the thread's voxels
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       int sg = 0, off = c;
@@ -202,6 +215,19 @@ __global__ void __launch_bounds__(PW_T)
         sg = (A.nseg > 1) ? (c >= A.seg_w) + (c >= 2 * A.seg_w) + (c >= 3 * A.seg_w) : 0;
         off = c - sg * A.seg_w;
         if (A.bias) b4 = ldg4(A.bias + c);
+      }
+      // relu-mask operands of the thread's voxels: issued together, consumed below
+      float4 m4[VPT];
+      bool has_mask = false;
+      if (fast && !SRC_IS_BIG) {
+        const float* mb = A.nseg > 1 ? pick4(A.seg_mask, sg) : A.mask;
+        const int ml = A.nseg > 1 ? pick4(A.seg_mask_ld, sg) : A.ld_mask;
+        const int mo = A.nseg > 1 ? off : c;
+        has_mask = mb != nullptr;
+        if (has_mask) {
+#pragma unroll
+          for (int vv = 0; vv < VPT; ++vv) m4[vv] = ldg4(mb + didx[vv] * ml + mo);
+        }
       }
 #pragma unroll
       for (int vv = 0; vv < VPT; ++vv) {
@@ -212,17 +238,9 @@ __global__ void __launch_bounds__(PW_T)
         if (fast) {
           v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
           if (!SRC_IS_BIG) {
-            const float* mp = nullptr;
-            if (A.nseg > 1) {
-              const float* mb = pick4(A.seg_mask, sg);
-              if (mb) mp = mb + dst_idx * pick4(A.seg_mask_ld, sg) + off;
-            } else if (A.mask) {
-              mp = A.mask + dst_idx * A.ld_mask + c;
-            }
-            if (mp) {
-              const float4 m4 = ldg4(mp);
-              v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-              v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+            if (has_mask) {
+              v[0] = m4[vv].x > 0.f ? v[0] : 0.f; v[1] = m4[vv].y > 0.f ? v[1] : 0.f;
+              v[2] = m4[vv].z > 0.f ? v[2] : 0.f; v[3] = m4[vv].w > 0.f ? v[3] : 0.f;
             }
             if (A.scale) {
               const float4 s4 = ldg4(A.scale + (long long)n[vv] * A.Cout + c);
@@ -233,8 +251,10 @@ __global__ void __launch_bounds__(PW_T)
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
           }
+          if (MOM) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { ms[e] += v[e]; mq[e] += v[e] * v[e]; }
+            for (int e = 0; e < 4; ++e) { ms[j4 * 4 + e] += v[e]; mq[j4 * 4 + e] += v[e] * v[e]; }
+          }
           float* ps;
           int do_acc;
           if (!SRC_IS_BIG && A.nseg > 1) {
@@ -264,30 +284,14 @@ __global__ void __launch_bounds__(PW_T)
               if (A.scale) t *= __ldg(A.scale + (long long)n[vv] * A.Cout + ce);
             }
             if (A.sigmoid) t = 1.f / (1.f + __expf(-t));
-            ms[e] += t; mq[e] += t * t;
+            if (MOM) { ms[j4 * 4 + e] += t; mq[j4 * 4 + e] += t * t; }
             pd[j4 * 4 + e] = A.accumulate ? pd[j4 * 4 + e] + t : t;
-          }
-        }
-      }
-      if (A.moments) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float a = warp_sum(ms[e]);
-          const float b = warp_sum(mq[e]);
-          if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&sm_mom[(j4 * 4 + e) * 2 + 0], (double)a);
-            atomicAdd(&sm_mom[(j4 * 4 + e) * 2 + 1], (double)b);
           }
         }
       }
     }
   }
-  if (A.moments && mom_n >= 0) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * CO; i += PW_T)
-      if (co0 + i / 2 < A.Cout)
-        atomicAdd(&A.moments[((long long)mom_n * A.Cout + co0) * 2 + i], sm_mom[i]);
-  }
+  if (MOM && mom_n >= 0) flush_moments(mom_n);
 }
 
 // wgrad: thread register tile TS x TB over (small channels, big channels)
@@ -407,19 +411,46 @@ __global__ void __launch_bounds__(PWG_T)
 
 static inline bool pointwise_big(long long nvox) { return nvox >= (long long)kNumSMs * 8 * PW_T * 4; }
 
-template <int CO, bool SRC_IS_BIG>
+template <int CO, bool SRC_IS_BIG, int VPT, bool MOM>
+static unsigned pointwise_resident_ctas() {
+  static int occ = 0;   // per instantiation; racing initialisers compute the same value
+  if (occ == 0) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, pointwise_kernel<CO, SRC_IS_BIG, VPT, MOM>, PW_T, 0) != cudaSuccess || o < 1)
+      o = 4;
+    occ = o;
+  }
+  return (unsigned)occ * kNumSMs;
+}
+
+template <int CO, bool SRC_IS_BIG, bool MOM, int VPT>
+static void launch_pointwise_vpt(const PwArgs& A, unsigned gy, long long nvox, cudaStream_t st) {
+  const unsigned ntiles = (unsigned)((nvox + PW_T * VPT - 1) / (PW_T * VPT));
+  unsigned gx = pointwise_resident_ctas<CO, SRC_IS_BIG, VPT, MOM>() / gy;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  pointwise_kernel<CO, SRC_IS_BIG, VPT, MOM><<<dim3(gx, gy), PW_T, 0, st>>>(A);
+}
+
+static int pw_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <int CO, bool SRC_IS_BIG, bool MOM>
 static void launch_pointwise_co(const PwArgs& A, unsigned gy, cudaStream_t st) {
   const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
-  // big tensors: 4 voxels per thread and ~8 CTAs per SM, each walking a contiguous range of tiles;
+  // big tensors: several voxels per thread, one resident wave of CTAs striding over the tiles;
   // small (deep-level) tensors: 1 voxel per thread, one tile per CTA - they are latency-bound
   if (pointwise_big(nvox)) {
-    const unsigned ntiles = (unsigned)((nvox + PW_T * 4 - 1) / (PW_T * 4));
-    unsigned per = (ntiles + kNumSMs * 8 - 1) / (kNumSMs * 8);
-    const unsigned gx = (ntiles + per - 1) / per;
-    pointwise_kernel<CO, SRC_IS_BIG, 4><<<dim3(gx, gy), PW_T, 0, st>>>(A, per);
+    static const int vpt_sfb = pw_env("NAS3D_PW_VPT_SFB", 4), vpt_bfs = pw_env("NAS3D_PW_VPT_BFS", 4);
+    const int vpt = MOM ? 4 : (SRC_IS_BIG ? vpt_sfb : vpt_bfs);
+    if (vpt == 1) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 1>(A, gy, nvox, st);
+    else if (vpt == 2) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 2>(A, gy, nvox, st);
+    else launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 4>(A, gy, nvox, st);
   } else {
     const unsigned ntiles = (unsigned)((nvox + PW_T - 1) / PW_T);
-    pointwise_kernel<CO, SRC_IS_BIG, 1><<<dim3(ntiles, gy), PW_T, 0, st>>>(A, 1u);
+    pointwise_kernel<CO, SRC_IS_BIG, 1, MOM><<<dim3(ntiles, gy), PW_T, 0, st>>>(A);
   }
 }
 
@@ -430,11 +461,20 @@ static int launch_pointwise(const PwArgs& A, cudaStream_t st) {
   int co_t = A.Cout <= 4 ? 4 : A.Cout <= 8 ? 8 : A.Cout <= 12 ? 12 : 16;
   if (A.Cin * co_t > PW_MAX_W) return NAS3D_ERR_UNSUPPORTED;
   const unsigned gy = (unsigned)((A.Cout + co_t - 1) / co_t);
+  if (SRC_IS_BIG && A.moments) {
+    switch (co_t) {
+      case 4: launch_pointwise_co<4, SRC_IS_BIG, SRC_IS_BIG>(A, gy, st); break;
+      case 8: launch_pointwise_co<8, SRC_IS_BIG, SRC_IS_BIG>(A, gy, st); break;
+      case 12: launch_pointwise_co<12, SRC_IS_BIG, SRC_IS_BIG>(A, gy, st); break;
+      default: launch_pointwise_co<16, SRC_IS_BIG, SRC_IS_BIG>(A, gy, st); break;
+    }
+    return launched("pointwise");
+  }
   switch (co_t) {
-    case 4: launch_pointwise_co<4, SRC_IS_BIG>(A, gy, st); break;
-    case 8: launch_pointwise_co<8, SRC_IS_BIG>(A, gy, st); break;
-    case 12: launch_pointwise_co<12, SRC_IS_BIG>(A, gy, st); break;
-    default: launch_pointwise_co<16, SRC_IS_BIG>(A, gy, st); break;
+    case 4: launch_pointwise_co<4, SRC_IS_BIG, false>(A, gy, st); break;
+    case 8: launch_pointwise_co<8, SRC_IS_BIG, false>(A, gy, st); break;
+    case 12: launch_pointwise_co<12, SRC_IS_BIG, false>(A, gy, st); break;
+    default: launch_pointwise_co<16, SRC_IS_BIG, false>(A, gy, st); break;
   }
   return launched("pointwise");
 }
