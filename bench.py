@@ -378,7 +378,11 @@ def run_ours(args):
 
     roofline = None
     if not args.no_roofline and rank == 0:
+        # per-kernel timing of rank 0's own replica: the gradient all-reduce must be off here, the
+        # other ranks are not stepping (they wait at the barrier below)
+        engine.enable_data_parallel(enabled=False)
         roofline = roofline_pass(step_resident, profiling, args)
+        engine.enable_data_parallel(enabled=world > 1)
     if world > 1:
         dist.barrier()
 
@@ -400,7 +404,16 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear down in dependency order: the captured graph holds NCCL kernels, and destroying the
+        # communicator under a live graph can block forever - drop the graph, drain, then leave
+        # without the collective teardown (every rank has already passed the last barrier)
+        graphed = None
+        import gc
+        gc.collect()
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def roofline_pass(step, profiling, args):
