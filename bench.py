@@ -178,18 +178,23 @@ def run_reference(args):
 
 
 def workload_config(args, reference=False):
-    return {
+    """same workload description for both arms; the reference arm times a bounded sample of it
+    (one patch per step - GroupNorm and Dice are per-sample, so CPU patches/s is flat in the batch)"""
+    cfg = {
         "workload": ("%s-G0 U-Net training step (fwd + Dice + bwd + Adam), 4x%d^3 patches, "
-                     "batch %d per GPU" % (args.workload, args.patch, 1 if reference else args.batch))
+                     "batch %d per GPU" % (args.workload, args.patch, args.batch))
         if args.workload == "searched" else
         ("supernet search step (alpha step + weight step), 4x%d^3 patches, batch %d per GPU"
-         % (args.patch, 1 if reference else args.batch)),
-        "patch": args.patch, "batch_per_gpu": 1 if reference else args.batch,
-        "global_batch": (1 if reference else args.batch * args.gpus),
+         % (args.patch, args.batch)),
+        "patch": args.patch, "batch_per_gpu": args.batch,
+        "global_batch": args.batch * args.gpus,
         "parallelism": "dp%d" % args.gpus,
         "l2": "inputs larger than L2 (%.0f MB of x (fp32) + y (int8 masks) per step per GPU vs 126 MB L2)"
               % (((4 * 4 + 3) * args.patch ** 3 * args.batch) / 1e6),
     }
+    if reference:
+        cfg["reference_sample"] = "each timed step = 1 patch of this workload on the host cores"
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------
@@ -209,6 +214,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         engine.enable_data_parallel()
     _lib.load()
