@@ -90,16 +90,26 @@ class Cell(nn.Module):
         return engine.run_module(self, (x0, x1), (alpha1, alpha2))
 
     def _run(self, ctx, x0, x1, alpha1, alpha2, virtual_cat=False):
-        states = [engine.materialize(ctx, self.preprocess0._run(ctx, x0)),
-                  engine.materialize(ctx, self.preprocess1._run(ctx, x1))]
+        # independent branches (the two preprocess convs; the edges of a node - each reads a
+        # different state) are spread over stream lanes, forward and backward
+        ctx.join_lanes(mark=True)
+        with ctx.on_lane(0):
+            p0 = engine.materialize(ctx, self.preprocess0._run(ctx, x0))
+        with ctx.on_lane(1 if x0 is not x1 else 0):
+            p1 = engine.materialize(ctx, self.preprocess1._run(ctx, x1))
+        ctx.join_lanes()
+        states = [p0, p1]
         out = None
         nodes = []
         edge = 0
         for j in range(self.n_nodes):
             terms = []
-            for x in states:
-                terms += self._ops[edge]._terms(ctx, x, alpha1, alpha2, edge)
+            ctx.join_lanes(mark=True)
+            for i, x in enumerate(states):
+                with ctx.on_lane(i):
+                    terms += self._ops[edge]._terms(ctx, x, alpha1, alpha2, edge)
                 edge += 1
+            ctx.join_lanes()
             t0 = terms[0].x
             if virtual_cat:
                 # inside a net the concat is never materialised: the node is its own dense tensor

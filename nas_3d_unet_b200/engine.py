@@ -16,6 +16,8 @@ Vocabulary
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -28,6 +30,83 @@ class Nas3dDeviceError(RuntimeError):
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+_side_streams = {}
+
+
+def wgrad_stream_enabled():
+    """weight-gradient kernels run on a second stream, concurrent with the dgrad / node-backward
+    chain that does not depend on them (NAS3D_WGRAD_STREAM=0 puts everything on one stream)"""
+    from . import profiling
+    if profiling._active is not None:     # per-kernel event timing wants one stream
+        return False
+    return os.environ.get("NAS3D_WGRAD_STREAM", "1") != "0"
+
+
+def _side_stream(device, which=0):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), which)
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = torch.cuda.Stream(device=device)
+    return s
+
+
+def n_lanes():
+    """streams the independent edges of a cell node are spread over (NAS3D_LANES, default 3;
+    1 = everything on the caller's stream)"""
+    from . import profiling
+    if profiling._active is not None:
+        return 1
+    return max(1, min(4, int(os.environ.get("NAS3D_LANES", "3"))))
+
+
+class _Laned:
+    """tape entry recorded on lane k > 0: its backward runs on the same lane"""
+    __slots__ = ("fn", "lane")
+
+    def __init__(self, fn, lane):
+        self.fn = fn
+        self.lane = lane
+
+
+class _JoinMarker:
+    """tape entry: all lanes rejoin the caller's stream here"""
+    __slots__ = ()
+
+
+class _Lane:
+    """context manager: run the enclosed launches (ours and torch's) on lane k.  The lane first
+    waits for everything enqueued on the caller's stream so far; ExecCtx.join_lanes() makes the
+    caller's stream wait for the lanes.  Tensors allocated inside belong to the lane's allocator
+    pool; they are only freed when the tape dies, after every stream has been joined."""
+
+    def __init__(self, ctx, k):
+        self.ctx, self.k = ctx, k
+        self.tctx = None
+
+    def __enter__(self):
+        ctx, k = self.ctx, self.k
+        if k == 0 or ctx.lanes <= 1:
+            return self
+        main = torch.cuda.current_stream(ctx.device)
+        lane = _side_stream(ctx.device, k)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        lane.wait_event(ev)
+        self.saved = (ctx.stream, ctx.lane)
+        self.tctx = torch.cuda.stream(lane)
+        self.tctx.__enter__()
+        ctx.stream = lane.cuda_stream
+        ctx.lane = k
+        ctx.dirty_lanes.add(k)
+        return self
+
+    def __exit__(self, *exc):
+        if self.tctx is not None:
+            self.ctx.stream, self.ctx.lane = self.saved
+            self.tctx.__exit__(*exc)
+        return False
 
 
 def get_lib():
@@ -214,6 +293,9 @@ class ExecCtx:
         self.stream = _stream()
         self.packed = {}
         self.pending_gn = []
+        self.lanes = n_lanes()
+        self.lane = 0
+        self.dirty_lanes = set()
 
     def use(self, *params):
         for p in params:
@@ -222,11 +304,30 @@ class ExecCtx:
 
     def push(self, fn):
         if self.record:
-            self.tape.append(fn)
+            self.tape.append(fn if self.lane == 0 else _Laned(fn, self.lane))
+
+    def on_lane(self, k):
+        return _Lane(self, k % self.lanes)
+
+    def join_lanes(self, mark=False):
+        """the caller's stream waits for every lane used since the last join; with mark=True the
+        backward pass joins at the mirror position too"""
+        if self.dirty_lanes:
+            main = torch.cuda.current_stream(self.device)
+            for k in sorted(self.dirty_lanes):
+                ev = torch.cuda.Event()
+                ev.record(_side_stream(self.device, k))
+                main.wait_event(ev)
+            self.dirty_lanes.clear()
+        if mark and self.record and self.lanes > 1:
+            self.tape.append(_JoinMarker())
 
     # ---- backward side -------------------------------------------------------------
     def begin_backward(self):
         self.stream = _stream()
+        self.side = _side_stream(self.device) if wgrad_stream_enabled() else None
+        self.side_used = False
+        self.keep = []
         plist = list(self.params.values())
         total = sum((p.numel() + 3) // 4 * 4 for p in plist)
         self.bucket = torch.zeros(max(total, 4), device=self.device, dtype=torch.float32)
@@ -238,6 +339,28 @@ class ExecCtx:
 
     def gptr(self, p):
         return self.views[id(p)].data_ptr() if p is not None else None
+
+    def fork_wgrad(self, *keep):
+        """stream for a weight-gradient launch: the side stream, ordered after everything enqueued
+        on the main stream so far (its inputs dy / x are complete there).  Nothing on the main
+        stream waits for it until join_wgrad(); `keep` tensors are held until then."""
+        if self.side is None:
+            return self.stream
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        self.side_used = True
+        self.keep.extend(keep)
+        return self.side.cuda_stream
+
+    def join_wgrad(self):
+        if self.side is not None and self.side_used:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self.side_used = False
+        self.keep = []
 
 
 # ----------------------------------------------------------------------------------------
@@ -439,7 +562,7 @@ def gn_term(ctx, x, norm, relu):
     ab = torch.empty((2, x.N, x.C), device=ctx.device, dtype=torch.float32)
     mr = torch.empty((x.N, G, 2), device=ctx.device, dtype=torch.float32)
     # the coefficient kernel is deferred: affine_sum() flushes all pending ones of a node at once
-    ctx.pending_gn.append((S, norm, x.N, x.C, G, x.V, float(norm.eps), ab, mr))
+    ctx.pending_gn.append((S, norm, x.N, x.C, G, x.V, float(norm.eps), ab, mr, ctx.lane))
     aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G, "S": S}
     return Term(x, ab[0], ab[1], relu, "gn", aux)
 
@@ -448,10 +571,16 @@ def flush_gn(ctx):
     """launch the deferred GroupNorm coefficient kernels, batched per (N, C, G, V, eps)"""
     if not ctx.pending_gn:
         return
+    # while lanes are running concurrently only this lane's statistics are known to be complete on
+    # this stream; after a join everything pending is
+    if ctx.dirty_lanes:
+        mine = [j for j in ctx.pending_gn if j[9] == ctx.lane]
+        ctx.pending_gn = [j for j in ctx.pending_gn if j[9] != ctx.lane]
+    else:
+        mine, ctx.pending_gn = ctx.pending_gn, []
     groups = {}
-    for job in ctx.pending_gn:
+    for job in mine:
         groups.setdefault(job[2:7], []).append(job)
-    ctx.pending_gn = []
     for (N, Cc, G, V, eps), jobs in groups.items():
         for i in range(0, len(jobs), 32):
             chunk = jobs[i:i + 32]
@@ -657,8 +786,8 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
             C.byref(d2), len(parts), ptr_array([p.ptr for p in parts]),
             int_array([p.ld for p in parts]), dy.ptr, _tp(in_scale), 1 if in_relu else 0,
             ctx.gptr(m.weight),
-            ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None, st),
-            "conv1x1_cat_wgrad")
+            ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None,
+            ctx.fork_wgrad(dy_t)), "conv1x1_cat_wgrad")
         live = [p for p in parts if p.requires_grad]
         if not live:
             return
@@ -694,10 +823,11 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
     dy = _GradView(dy_t, y)
     dW = ctx.gptr(m.weight)
     db = ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None
+    wst = ctx.fork_wgrad(dy_t)
     if not spec.transposed:
         d = _desc(spec, x, dy)
         check(lib.nas3d_conv_wgrad(C.byref(d), dy.ptr, x.ptr, _tp(in_scale), 1 if in_relu else 0,
-                                   dW, db, None, st), "conv_wgrad")
+                                   dW, db, None, wst), "conv_wgrad")
         if x.requires_grad:
             g, acc = x.grad_slot()
             gv = _GradView(g, x)
@@ -713,7 +843,7 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
                       "conv dgrad")
     else:
         d = _desc(spec, dy, x)
-        check(lib.nas3d_conv_wgrad(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, st),
+        check(lib.nas3d_conv_wgrad(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, wst),
               "convT wgrad")
         if x.requires_grad:
             g, acc = x.grad_slot()
@@ -807,7 +937,15 @@ class _ModuleFn(torch.autograd.Function):
             g, _ = owned_grad(gout, out, force_copy=getattr(fctx.module, "_mutates_out_grad", False))
             out.g = g
             for fn in reversed(ctx.tape):
-                fn()
+                if isinstance(fn, _Laned):
+                    with ctx.on_lane(fn.lane):
+                        fn.fn()
+                elif isinstance(fn, _JoinMarker):
+                    ctx.join_lanes()
+                else:
+                    fn()
+            ctx.join_lanes()
+            ctx.join_wgrad()
             ctx.tape = []
             if _dp_state["enabled"]:
                 _dp_allreduce(ctx, fctx.extras)

@@ -33,14 +33,25 @@ class SearchedCell(nn.Module):
         return engine.run_module(self, (x0, x1))
 
     def _run(self, ctx, x0, x1, virtual_cat=False):
-        states = [engine.materialize(ctx, self.preprocess0._run(ctx, x0)),
-                  engine.materialize(ctx, self.preprocess1._run(ctx, x1))]
+        # independent branches (the two preprocess convs; the edges of a node when they read
+        # different states) are spread over stream lanes, forward and backward
+        ctx.join_lanes(mark=True)
+        with ctx.on_lane(0):
+            p0 = engine.materialize(ctx, self.preprocess0._run(ctx, x0))
+        with ctx.on_lane(1 if x0 is not x1 else 0):
+            p1 = engine.materialize(ctx, self.preprocess1._run(ctx, x1))
+        ctx.join_lanes()
+        states = [p0, p1]
         out = None
         nodes = []
         for j in range(self.n_nodes):
             terms = []
-            for e in (2 * j, 2 * j + 1):
-                terms.append(self._ops[e]._run(ctx, states[self.genolist[e][1]]))
+            srcs = [self.genolist[e][1] for e in (2 * j, 2 * j + 1)]
+            ctx.join_lanes(mark=True)
+            for i, e in enumerate((2 * j, 2 * j + 1)):
+                with ctx.on_lane(i if len(set(srcs)) == len(srcs) else 0):
+                    terms.append(self._ops[e]._run(ctx, states[self.genolist[e][1]]))
+            ctx.join_lanes()
             t0 = terms[0].x
             for t in terms[1:]:
                 if (t.x.C, t.x.D, t.x.H, t.x.W) != (t0.C, t0.D, t0.H, t0.W):
