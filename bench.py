@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--workload", default="searched", choices=["searched", "supernet"])
     ap.add_argument("--optimizer", choices=["flat", "torch"], default="flat",
                     help="flat = nas_3d_unet_b200.optim.FlatAdam (one launch); torch = torch fused Adam")
+    ap.add_argument("--ref-device", choices=["cpu", "cuda"], default="cpu",
+                    help="--impl reference only: cuda = the same torch ops through torch's CUDA "
+                         "kernels (informational second baseline, BASELINE.md section 4)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -114,9 +117,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_steps(workload, patch, steps, warmup, batch=1):
+def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu"):
     """times `steps` training steps of the oracle (CPU restatement of the reference) at batch 1;
-    returns (patches_per_s, seconds_per_step, cores, sample description)"""
+    returns (patches_per_s, seconds_per_step, cores, sample description).
+    device="cuda" runs the same torch-op graph through torch's own CUDA kernels (cuDNN) - the
+    reference's intended GPU path (search.py:66-69); informational only, never the baseline."""
     from oracle import nas3d_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -128,15 +133,18 @@ def cpu_reference_steps(workload, patch, steps, warmup, batch=1):
     else:
         from nas_3d_unet_b200.nas import ShellNet
         m = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True)
+    if device != "cpu":
+        m = m.to(device)
     sd = O.leaf_state(m.state_dict())       # parameters only; the modules themselves never run
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3)
     x, y = synthetic_host_batch(batch, patch, seed=1234)
+    x, y = x.to(device), y.to(device)
     p_drop = 0.5 if workload == "searched" else 0.1
 
     def one():
         opt.zero_grad()
-        mask = torch.empty((batch, 12, 1, 1, 1)).bernoulli_(1 - p_drop).div_(1 - p_drop)
+        mask = torch.empty((batch, 12, 1, 1, 1), device=device).bernoulli_(1 - p_drop).div_(1 - p_drop)
         if workload == "searched":
             pred = O.searched_net(sd, x, 4, 3, O.G0, drop_mask=mask)
         else:
@@ -148,33 +156,50 @@ def cpu_reference_steps(workload, patch, steps, warmup, batch=1):
 
     for _ in range(warmup):
         one()
+    if device != "cpu":
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
+    if device != "cpu":
+        torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    passes = 1 if workload == "searched" else 1
-    return batch * passes / dt, dt, torch.get_num_threads(), (
-        "%s net, %d step(s) of batch %d at %d^3 (fwd+bwd+Adam), oracle port on CPU"
-        % (workload, steps, batch, patch))
+    return batch / dt, dt, torch.get_num_threads(), (
+        "%s net, %d step(s) of batch %d at %d^3 (fwd+bwd+Adam), oracle port on %s"
+        % (workload, steps, batch, patch, "CPU" if device == "cpu" else "torch eager CUDA (cuDNN)"))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: batch 1 per step
-    v, dt, cores, sample = cpu_reference_steps(args.workload, args.patch, args.steps, args.warmup)
+    # bounded sample: batch 1 per step (--ref-device cuda: informational torch-eager GPU run, batch
+    # as given)
+    on_gpu = args.ref_device == "cuda"
+    v, dt, cores, sample = cpu_reference_steps(args.workload, args.patch, args.steps, args.warmup,
+                                               batch=args.batch if on_gpu else 1,
+                                               device=args.ref_device)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": workload_config(args, reference=True),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "device": args.ref_device},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(args):
+    """BASELINE.json's metric for the default workload; the secondary workloads say what they are"""
+    if args.workload == "searched" and args.patch == 128:
+        return METRIC
+    if args.workload == "searched":
+        return "searched-net %d^3 train patches/s" % args.patch
+    return "supernet %d^3 search patches/s (train+val pair = 1 patch)" % args.patch
 
 
 def workload_config(args, reference=False):
@@ -204,7 +229,6 @@ def run_ours(args):
     import torch.distributed as dist
     from nas_3d_unet_b200 import _lib, engine, profiling
     from nas_3d_unet_b200.loss import WeightedDiceLoss
-    from oracle import nas3d_oracle as O   # G0 constant only (bench: cpu_baseline leg below)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,8 +255,8 @@ def run_ours(args):
     lossf = WeightedDiceLoss().to(dev)
     if args.workload == "searched":
         from nas_3d_unet_b200.searched import SearchedNet
-        from nas_3d_unet_b200.genotype import Genotype
-        model = SearchedNet(4, 4, 3, 4, 3, True, Genotype(down=O.G0.down, up=O.G0.up)).to(dev)
+        from nas_3d_unet_b200.genotype import G0
+        model = SearchedNet(4, 4, 3, 4, 3, True, G0).to(dev)
         opts = [make_adam(model.parameters())]
     else:
         from nas_3d_unet_b200.nas import ShellNet
@@ -402,7 +426,7 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args), cuda_graph=(graphed is not None)),

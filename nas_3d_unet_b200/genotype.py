@@ -10,6 +10,14 @@ from .prim_ops import DownOps, UpOps, NormOps
 
 Genotype = namedtuple('Genotype', ['down', 'up'])
 
+# Canonical benchmark genotype "G0" (the reference ships none - its
+# log/best_genotype.pkl is a run artefact).  1 242 760 parameters at the shipped widths.
+G0 = Genotype(
+    down=[('down_conv', 0), ('down_conv', 1), ('conv', 2), ('down_dep_conv', 1), ('dil_conv', 3),
+          ('se_conv', 2)],
+    up=[('up_conv', 1), ('conv', 0), ('up_dep_conv', 1), ('dil_conv', 2), ('up_dil_conv', 1),
+        ('se_conv', 3)])
+
 
 class GenoParser:
     def __init__(self, n_nodes):

@@ -5,14 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from nas_3d_unet_b200.searched import SearchedNet
-from nas_3d_unet_b200.genotype import Genotype
+from nas_3d_unet_b200.genotype import G0
 from nas_3d_unet_b200.infer import SlidingWindowPredictor
-from oracle.nas3d_oracle import G0   # genotype constant only
 
 def main():
     nvol = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     torch.manual_seed(0)
-    model = SearchedNet(4, 4, 3, 4, 3, True, Genotype(down=G0.down, up=G0.up)).cuda().eval()
+    model = SearchedNet(4, 4, 3, 4, 3, True, G0).cuda().eval()
     rng = np.random.default_rng(0)
     vol = (rng.random((4, 240, 240, 155), dtype=np.float32) * 100 + 10)
     hv = torch.as_tensor(vol).pin_memory()
