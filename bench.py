@@ -133,9 +133,10 @@ def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu"):
     else:
         from nas_3d_unet_b200.nas import ShellNet
         m = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True)
-    if device != "cpu":
-        m = m.to(device)
     sd = O.leaf_state(m.state_dict())       # parameters only; the modules themselves never run
+    if device != "cpu":
+        sd = {k: (v.detach().to(device).requires_grad_(True) if v.is_floating_point() else v.to(device))
+              for k, v in sd.items()}
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3)
     x, y = synthetic_host_batch(batch, patch, seed=1234)
@@ -154,12 +155,15 @@ def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu"):
         opt.step()
         return loss.item()
 
+    # a search step is two passes (alpha step on the val batch + weight step on the train batch,
+    # search.py:222-238); both cost the same here, so the same pass is timed twice
+    passes = 2 if workload == "supernet" else 1
     for _ in range(warmup):
         one()
     if device != "cpu":
         torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(steps * passes):
         one()
     if device != "cpu":
         torch.cuda.synchronize()
@@ -448,6 +452,16 @@ def run_ours(args):
         os._exit(0)
 
 
+def ncu_traffic(kernel, shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this (kernel, shape) from the
+    committed ncu --set full capture (profiles/ncu_traffic.json), or None if not captured"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)["%s|%s" % (kernel, shape)]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def roofline_pass(step, profiling, args):
     """2 extra steps with every C-ABI launch bracketed by CUDA events on the launch stream;
     the dominant kernel (largest share of the step) is reported against its binding roof."""
@@ -480,7 +494,7 @@ def roofline_pass(step, profiling, args):
     out = {
         "bound": "hbm", "kernel": top["kernel"], "shape": top["shape"],
         "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac,
-        "peak_source": peaks["src"], "traffic": None,
+        "peak_source": peaks["src"], "traffic": ncu_traffic(top["kernel"], top["shape"]),
         "share_of_step": top["ms"] / total_ms if total_ms else None,
         "avg_launch_ms": top["ms"] / top["launches"],
         "achieved_tflops": ach_tf, "fp32_ffma_peak_tflops": fp32_tflops,
