@@ -53,12 +53,12 @@ def _side_stream(device, which=0):
 
 
 def n_lanes():
-    """streams the independent edges of a cell node are spread over (NAS3D_LANES, default 3;
+    """streams the independent edges of a cell node are spread over (NAS3D_LANES, default 4;
     1 = everything on the caller's stream)"""
     from . import profiling
     if profiling._active is not None:
         return 1
-    return max(1, min(4, int(os.environ.get("NAS3D_LANES", "3"))))
+    return max(1, min(4, int(os.environ.get("NAS3D_LANES", "4"))))
 
 
 class _Laned:
@@ -325,8 +325,11 @@ class ExecCtx:
     # ---- backward side -------------------------------------------------------------
     def begin_backward(self):
         self.stream = _stream()
-        self.side = _side_stream(self.device) if wgrad_stream_enabled() else None
-        self.side_used = False
+        nside = int(os.environ.get("NAS3D_WGRAD_STREAMS", "1")) if wgrad_stream_enabled() else 0
+        # weight-gradient streams (round-robin): keys 100.. keep them apart from the branch lanes
+        self.side = [_side_stream(self.device, 100 + i) for i in range(max(0, min(4, nside)))]
+        self.side_next = 0
+        self.side_used = set()
         self.keep = []
         plist = list(self.params.values())
         total = sum((p.numel() + 3) // 4 * 4 for p in plist)
@@ -344,22 +347,25 @@ class ExecCtx:
         """stream for a weight-gradient launch: the side stream, ordered after everything enqueued
         on the main stream so far (its inputs dy / x are complete there).  Nothing on the main
         stream waits for it until join_wgrad(); `keep` tensors are held until then."""
-        if self.side is None:
+        if not self.side:
             return self.stream
         main = torch.cuda.current_stream(self.device)
+        i = self.side_next
+        self.side_next = (i + 1) % len(self.side)
         ev = torch.cuda.Event()
         ev.record(main)
-        self.side.wait_event(ev)
-        self.side_used = True
+        self.side[i].wait_event(ev)
+        self.side_used.add(i)
         self.keep.extend(keep)
-        return self.side.cuda_stream
+        return self.side[i].cuda_stream
 
     def join_wgrad(self):
-        if self.side is not None and self.side_used:
+        main = torch.cuda.current_stream(self.device)
+        for i in sorted(self.side_used):
             ev = torch.cuda.Event()
-            ev.record(self.side)
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            self.side_used = False
+            ev.record(self.side[i])
+            main.wait_event(ev)
+        self.side_used = set()
         self.keep = []
 
 
