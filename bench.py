@@ -41,6 +41,7 @@ def parse():
                          "kernels (informational second baseline, BASELINE.md section 4)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
+    ap.add_argument("--e2e-probe", action="store_true", help="print an e2e overhead breakdown to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel table (json) here")
@@ -245,6 +246,7 @@ def run_ours(args):
         # stdout carries exactly one JSON line: keep NCCL's version banner off it
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         engine.enable_data_parallel()
     _lib.load()
@@ -402,6 +404,24 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = patches_per_step / (ms_per_step * 1e-3)
+
+    if args.e2e_probe and graphed is not None and rank == 0:
+        # where the gap between `value` and `e2e` goes (stderr only)
+        src = tuple(t.clone() for t in graphed.static_in)
+
+        def b_fn():
+            graphed(*src)
+
+        def c_fn():
+            graphed(*src).reshape(-1)[-1].item()
+        for name, fn in (("replay", graphed.replay), ("d2d+replay", b_fn), ("d2d+replay+item", c_fn)):
+            fn()
+            print("e2e-probe %-18s %.3f ms/step" % (name, timed(lambda: [fn() for _ in range(args.steps)], 1)
+                                                    / args.steps), file=sys.stderr)
+        run_e2e(2)
+        for k in (args.steps, 4 * args.steps):
+            print("e2e-probe full e2e, %3d steps  %.3f ms/step"
+                  % (k, timed(lambda: run_e2e(k), 1) / k), file=sys.stderr)
 
     # end to end: pinned host batch -> device, loss value -> host, every step
     run_e2e(2)
