@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnas3d_b200.so")
+# NAS3D_LIB: alternative build of the SAME library (e.g. the -DNAS3D_NO_FFMA2 variant made by
+# `python -m nas_3d_unet_b200.build --variant noffma2`) for A/B measurements; never a fallback.
+LIB_PATH = os.environ.get("NAS3D_LIB") or os.path.join(_HERE, "lib", "libnas3d_b200.so")
 
 c_float_p = C.c_void_p   # device pointers travel as integers
 c_ll = C.c_longlong

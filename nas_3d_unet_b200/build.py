@@ -34,7 +34,23 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+VARIANTS = {
+    # A/B builds of the same sources (selected at run time with NAS3D_LIB=<path>)
+    "noffma2": ["-DNAS3D_NO_FFMA2"],      # scalar FFMA instead of packed FFMA2 (common.cuh)
+}
+
+
+def build_library(force=False, verbose=False, variant=None):
+    extra = []
+    lib_path, obj_dir = LIB_PATH, OBJ_DIR
+    if variant:
+        extra = VARIANTS[variant]
+        lib_path = os.path.join(LIB_DIR, "libnas3d_b200_%s.so" % variant)
+        obj_dir = os.path.join(HERE, "build", variant)
+    return _build(force, verbose, extra, lib_path, obj_dir)
+
+
+def _build(force, verbose, extra, LIB_PATH, OBJ_DIR):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -46,7 +62,7 @@ def build_library(force=False, verbose=False):
         o = os.path.join(OBJ_DIR, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -70,4 +86,5 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var))

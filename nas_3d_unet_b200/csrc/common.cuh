@@ -49,6 +49,68 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// Packed fp32 FMA (sm_100 FFMA2): one issue slot and one FMA-pipe pass for TWO fused
+// multiply-adds.  A 3-register scalar FFMA issues every other cycle per SM sub-partition on
+// Blackwell, so the FFMA-bound convolution kernels only reach the 128 FMA/clk/SM fp32 peak
+// through this form.  ptxas folds the {s,s} operand into the instruction's scalar-broadcast
+// modifier (FFMA2 Rd, Rs.F32, Rw.F32x2.HI_LO, Rd.F32x2.HI_LO) - no extra MOV.  Each half is an
+// IEEE fma.rn, so results are bit-identical to two fmaf() in the same order.
+// Build with -DNAS3D_NO_FFMA2 to fall back to scalar FFMA (A/B measurements).
+__device__ __forceinline__ void fma2(float2& d, float s, float wx, float wy) {
+#ifndef NAS3D_NO_FFMA2
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "mov.b64 rd, {%0, %1};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rd;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "+f"(d.x), "+f"(d.y)
+      : "f"(s), "f"(wx), "f"(wy));
+#else
+  d.x = fmaf(s, wx, d.x);
+  d.y = fmaf(s, wy, d.y);
+#endif
+}
+// element-wise pair: d += a * b
+__device__ __forceinline__ void fma2v(float2& d, float ax, float ay, float bx, float by) {
+#ifndef NAS3D_NO_FFMA2
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rd, {%0, %1};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rd;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "+f"(d.x), "+f"(d.y)
+      : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+#else
+  d.x = fmaf(ax, bx, d.x);
+  d.y = fmaf(ay, by, d.y);
+#endif
+}
+// 4 accumulators (two pairs) += s * w
+__device__ __forceinline__ void axpy4(float2 (&a)[2], float s, const float4& w) {
+  fma2(a[0], s, w.x, w.y);
+  fma2(a[1], s, w.z, w.w);
+}
+// 4x4 outer product: a[i][0..3] += x[i] * w[0..3]   (wgrad: x = activation, w = dy)
+__device__ __forceinline__ void outer4(float2 (&a)[4][2], const float4& x, const float4& w) {
+  axpy4(a[0], x.x, w);
+  axpy4(a[1], x.y, w);
+  axpy4(a[2], x.z, w);
+  axpy4(a[3], x.w, w);
+}
+// 4-channel contraction: a[0..3] += sum_i x[i] * w[i][0..3]   (fwd / dgrad)
+__device__ __forceinline__ void dot4x4(float2 (&a)[2], const float4& x, const float4 (&w)[4]) {
+  axpy4(a, x.x, w[0]);
+  axpy4(a, x.y, w[1]);
+  axpy4(a, x.z, w[2]);
+  axpy4(a, x.w, w[3]);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -131,11 +131,11 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__
       didx[v] = SRC_IS_BIG ? (long long)oo : big_idx;
     }
 
-    float acc[VPT][CO];
+    float2 acc[VPT][CO / 2];      // channel pairs: FFMA2 accumulators (common.cuh)
 #pragma unroll
     for (int v = 0; v < VPT; ++v)
 #pragma unroll
-      for (int j = 0; j < CO; ++j) acc[v][j] = 0.f;
+      for (int j = 0; j < CO / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
 
 #pragma unroll 2
     for (int c4 = 0; c4 < A.Cin; c4 += 4) {
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__
             const float4 w4 = *reinterpret_cast<const float4*>(wr + j4 * 4);
 #pragma unroll
             for (int v = 0; v < VPT; ++v) {
-              acc[v][j4 * 4 + 0] += xv[v][e] * w4.x; acc[v][j4 * 4 + 1] += xv[v][e] * w4.y;
-              acc[v][j4 * 4 + 2] += xv[v][e] * w4.z; acc[v][j4 * 4 + 3] += xv[v][e] * w4.w;
+              fma2(acc[v][j4 * 2 + 0], xv[v][e], w4.x, w4.y);
+              fma2(acc[v][j4 * 2 + 1], xv[v][e], w4.z, w4.w);
             }
           }
         }
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__
 #pragma unroll
       for (int vv = 0; vv < VPT; ++vv) {
         if (!ok[vv]) continue;
-        float v[4] = {acc[vv][j4 * 4 + 0], acc[vv][j4 * 4 + 1], acc[vv][j4 * 4 + 2], acc[vv][j4 * 4 + 3]};
+        float v[4] = {acc[vv][j4 * 2].x, acc[vv][j4 * 2].y, acc[vv][j4 * 2 + 1].x, acc[vv][j4 * 2 + 1].y};
         const long long dst_idx = didx[vv];
         float* pd = A.dst + dst_idx * A.ld_dst + co0;
         if (fast) {
@@ -308,13 +308,14 @@ __global__ void __launch_bounds__(PWG_T)
   const bool vec_s = (lds % 4 == 0) && (ns == TS) && (TS % 4 == 0);
   const bool vec_b = (ldb % 4 == 0) && (nb == TB);
   const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
-  float acc[TS][TB];
+  static_assert(TB % 2 == 0, "big-channel tile is processed in FFMA2 pairs");
+  float2 acc[TS][TB / 2];
   float bs[TS];
 #pragma unroll
   for (int i = 0; i < TS; ++i) {
     bs[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < TB; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TB / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
   }
   const bool do_bias = dbias_small != nullptr && blockIdx.z == 0;
 #pragma unroll 2
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(PWG_T)
     for (int i = 0; i < TS; ++i) {
       bs[i] += sv[i];
 #pragma unroll
-      for (int j = 0; j < TB; ++j) acc[i][j] += sv[i] * bv[j];
+      for (int j = 0; j < TB / 2; ++j) fma2(acc[i][j], sv[i], bv[2 * j], bv[2 * j + 1]);
     }
   }
   __shared__ float red[PWG_T / 32][TS * TB + TS];
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(PWG_T)
   for (int i = 0; i < TS; ++i) {
 #pragma unroll
     for (int j = 0; j < TB; ++j) {
-      const float v = warp_sum(acc[i][j]);
+      const float v = warp_sum((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x);
       if (lane == 0) red[wid][i * TB + j] = v;
     }
     const float b = warp_sum(bs[i]);

@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
   const int hg = ty % HG;
   const int dg = ty / HG;
 
-  float acc[MD][4][4];
+  float2 acc[MD][4][2];      // [d][h][channel pair]: FFMA2 accumulators (common.cuh)
 #pragma unroll
   for (int a = 0; a < MD; ++a)
 #pragma unroll
     for (int h = 0; h < 4; ++h)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][h][c] = 0.f;
+      for (int c = 0; c < 2; ++c) acc[a][h][c] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
   for (int kd = 0; kd < 3; ++kd) {
@@ -168,17 +168,7 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
 #pragma unroll
           for (int oh = 0; oh < 4; ++oh)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const float4 xv = xin[oh + kh * DIL];
-              acc[od][oh][0] += xv.x * wr[kh][0].x; acc[od][oh][1] += xv.x * wr[kh][0].y;
-              acc[od][oh][2] += xv.x * wr[kh][0].z; acc[od][oh][3] += xv.x * wr[kh][0].w;
-              acc[od][oh][0] += xv.y * wr[kh][1].x; acc[od][oh][1] += xv.y * wr[kh][1].y;
-              acc[od][oh][2] += xv.y * wr[kh][1].z; acc[od][oh][3] += xv.y * wr[kh][1].w;
-              acc[od][oh][0] += xv.z * wr[kh][2].x; acc[od][oh][1] += xv.z * wr[kh][2].y;
-              acc[od][oh][2] += xv.z * wr[kh][2].z; acc[od][oh][3] += xv.z * wr[kh][2].w;
-              acc[od][oh][0] += xv.w * wr[kh][3].x; acc[od][oh][1] += xv.w * wr[kh][3].y;
-              acc[od][oh][2] += xv.w * wr[kh][3].z; acc[od][oh][3] += xv.w * wr[kh][3].w;
-            }
+            for (int kh = 0; kh < 3; ++kh) dot4x4(acc[od][oh], xin[oh + kh * DIL], wr[kh]);
         }
       }
     }
@@ -200,8 +190,8 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
         const int gh = h0 + hg * 4 + oh;
         if (gh >= A.H) break;
         float* p = yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy;
-        float4 v = make_float4(acc[od][oh][0] + bias4.x, acc[od][oh][1] + bias4.y,
-                               acc[od][oh][2] + bias4.z, acc[od][oh][3] + bias4.w);
+        float4 v = make_float4(acc[od][oh][0].x + bias4.x, acc[od][oh][0].y + bias4.y,
+                               acc[od][oh][1].x + bias4.z, acc[od][oh][1].y + bias4.w);
         if (A.accumulate) {
           const float4 o = *reinterpret_cast<const float4*>(p);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -273,13 +263,13 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
   const bool active = lane < 30;
   const int kd = kdkh / 3, kh = kdkh % 3;
 
-  float acc[3][4][4];
+  float2 acc[3][4][2];   // [kw][ci][co pair]: FFMA2 accumulators
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[t][a][c] = 0.f;
+      for (int c = 0; c < 2; ++c) acc[t][a][c] = make_float2(0.f, 0.f);
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int i = threadIdx.x; i < 27 * 16 + 4; i += WS::THREADS) red[i] = 0.f;
@@ -341,13 +331,7 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
           win[(u + WN - 1) % WN] = xq[u + WN - 1];
           const float4 g = yq[u];
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float4 xv = win[(u + kw * DIL) % WN];
-            acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
-            acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
-            acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
-            acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
-          }
+          for (int kw = 0; kw < 3; ++kw) outer4(acc[kw], win[(u + kw * DIL) % WN], g);
           bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
         }
       }
@@ -360,13 +344,7 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
           win[(u + WN - 1) % WN] = xq[u + WN - 1];
           const float4 g = yq[u];
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float4 xv = win[(u + kw * DIL) % WN];
-            acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
-            acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
-            acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
-            acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
-          }
+          for (int kw = 0; kw < 3; ++kw) outer4(acc[kw], win[(u + kw * DIL) % WN], g);
           bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
         }
       }
@@ -380,7 +358,8 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], acc[kw][a][c]);
+        for (int c = 0; c < 4; ++c)
+          atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], (c & 1) ? acc[kw][a][c >> 1].y : acc[kw][a][c >> 1].x);
   } else if (active) {
     atomicAdd(&red[27 * 16 + 0], bsum.x); atomicAdd(&red[27 * 16 + 1], bsum.y);
     atomicAdd(&red[27 * 16 + 2], bsum.z); atomicAdd(&red[27 * 16 + 3], bsum.w);

@@ -16,7 +16,11 @@ __device__ __forceinline__ void dcp_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
-  a.x += x.x * w.x; a.y += x.y * w.y; a.z += x.z * w.z; a.w += x.w * w.w;
+  // two packed FFMA2 (common.cuh) instead of four FFMA
+  float2 lo = make_float2(a.x, a.y), hi = make_float2(a.z, a.w);
+  fma2v(lo, x.x, x.y, w.x, w.y);
+  fma2v(hi, x.z, x.w, w.z, w.w);
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 // stage wsm[tap] = {W[c0+0][tap], .., W[c0+3][tap]} (optionally mirrored taps)
 __device__ __forceinline__ void stage_dw_weights(float4* wsm, const float* w, int c0, bool flip) {

@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
   const int hg = ty % HG;
   const int dg = ty / HG;
 
-  float acc[4][4];
+  float2 acc[4][2];      // [h][channel pair]: FFMA2 accumulators (common.cuh)
 #pragma unroll
   for (int h = 0; h < 4; ++h)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[h][c] = 0.f;
+    for (int c = 0; c < 2; ++c) acc[h][c] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
   for (int kd = 0; kd < 3; ++kd) {
@@ -115,17 +115,7 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
 #pragma unroll
         for (int oh = 0; oh < 4; ++oh)
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const float4 xv = xin[2 * oh + kh];
-            acc[oh][0] += xv.x * wr[kh][0].x; acc[oh][1] += xv.x * wr[kh][0].y;
-            acc[oh][2] += xv.x * wr[kh][0].z; acc[oh][3] += xv.x * wr[kh][0].w;
-            acc[oh][0] += xv.y * wr[kh][1].x; acc[oh][1] += xv.y * wr[kh][1].y;
-            acc[oh][2] += xv.y * wr[kh][1].z; acc[oh][3] += xv.y * wr[kh][1].w;
-            acc[oh][0] += xv.z * wr[kh][2].x; acc[oh][1] += xv.z * wr[kh][2].y;
-            acc[oh][2] += xv.z * wr[kh][2].z; acc[oh][3] += xv.z * wr[kh][2].w;
-            acc[oh][0] += xv.w * wr[kh][3].x; acc[oh][1] += xv.w * wr[kh][3].y;
-            acc[oh][2] += xv.w * wr[kh][3].z; acc[oh][3] += xv.w * wr[kh][3].w;
-          }
+          for (int kh = 0; kh < 3; ++kh) dot4x4(acc[oh], xin[2 * oh + kh], wr[kh]);
       }
     }
   }
@@ -141,8 +131,8 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
       const int gh = h0 + hg * 4 + oh;
       if (gh >= A.Hs) break;
       float* p = yb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small;
-      float4 v = make_float4(acc[oh][0] + bias4.x, acc[oh][1] + bias4.y, acc[oh][2] + bias4.z,
-                             acc[oh][3] + bias4.w);
+      float4 v = make_float4(acc[oh][0].x + bias4.x, acc[oh][0].y + bias4.y, acc[oh][1].x + bias4.z,
+                             acc[oh][1].y + bias4.w);
       if (A.accumulate) {
         const float4 o = *reinterpret_cast<const float4*>(p);
         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -216,13 +206,13 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
   const int dp = ty / (TS::THB / 4);            // big plane inside the tile
   const int pi_d = dp & 1, qd = dp >> 1;
 
-  float acc[4][2][4];   // [big row r][big col e][co]
+  float2 acc[4][2][2];   // [big row r][big col e][co pair]: FFMA2 accumulators
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][e][c] = 0.f;
+      for (int c = 0; c < 2; ++c) acc[r][e][c] = make_float2(0.f, 0.f);
 
   // taps along d for this plane: even plane -> kd = 1 @ qd ; odd plane -> kd = 0 @ qd+1, kd = 2 @ qd
   const int nkd = pi_d ? 2 : 1;
@@ -258,15 +248,7 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
           for (int half = 0; half < 2; ++half) {
             const int r = (kh == 1) ? 2 * half : 2 * half + 1;
             const int sr = (kh == 1) ? half : (kh == 0 ? half + 1 : half);
-            const float4 xv = xs[sr][sc];
-            acc[r][e][0] += xv.x * wv[0].x; acc[r][e][1] += xv.x * wv[0].y;
-            acc[r][e][2] += xv.x * wv[0].z; acc[r][e][3] += xv.x * wv[0].w;
-            acc[r][e][0] += xv.y * wv[1].x; acc[r][e][1] += xv.y * wv[1].y;
-            acc[r][e][2] += xv.y * wv[1].z; acc[r][e][3] += xv.y * wv[1].w;
-            acc[r][e][0] += xv.z * wv[2].x; acc[r][e][1] += xv.z * wv[2].y;
-            acc[r][e][2] += xv.z * wv[2].z; acc[r][e][3] += xv.z * wv[2].w;
-            acc[r][e][0] += xv.w * wv[3].x; acc[r][e][1] += xv.w * wv[3].y;
-            acc[r][e][2] += xv.w * wv[3].z; acc[r][e][3] += xv.w * wv[3].w;
+            dot4x4(acc[r][e], xs[sr][sc], wv);
           }
         }
       }
@@ -288,8 +270,8 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
         const int gw = w0 + 2 * tx + e;
         if (gw >= A.Wb) continue;
         float* p = yb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big;
-        float4 v = make_float4(acc[r][e][0] + bias4.x, acc[r][e][1] + bias4.y,
-                               acc[r][e][2] + bias4.z, acc[r][e][3] + bias4.w);
+        float4 v = make_float4(acc[r][e][0].x + bias4.x, acc[r][e][0].y + bias4.y,
+                               acc[r][e][1].x + bias4.z, acc[r][e][1].y + bias4.w);
         if (A.accumulate) {
           const float4 o = *reinterpret_cast<const float4*>(p);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -345,13 +327,13 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
   const int kd = kdkh / 3, kh = kdkh % 3;
   (void)C4B;
 
-  float acc[3][4][4];   // [kw][cb][cs]
+  float2 acc[3][4][2];   // [kw][cb][cs pair]: FFMA2 accumulators
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[t][a][c] = 0.f;
+      for (int c = 0; c < 2; ++c) acc[t][a][c] = make_float2(0.f, 0.f);
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = threadIdx.x; i < 27 * 16 + 4; i += WS::THREADS) red[i] = 0.f;
 
@@ -404,13 +386,7 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
         const float4 g = yr[w];
         const float4 xv3[3] = {xa, xb2, xc};
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float4 xv = xv3[kw];
-          acc[kw][0][0] += xv.x * g.x; acc[kw][0][1] += xv.x * g.y; acc[kw][0][2] += xv.x * g.z; acc[kw][0][3] += xv.x * g.w;
-          acc[kw][1][0] += xv.y * g.x; acc[kw][1][1] += xv.y * g.y; acc[kw][1][2] += xv.y * g.z; acc[kw][1][3] += xv.y * g.w;
-          acc[kw][2][0] += xv.z * g.x; acc[kw][2][1] += xv.z * g.y; acc[kw][2][2] += xv.z * g.z; acc[kw][2][3] += xv.z * g.w;
-          acc[kw][3][0] += xv.w * g.x; acc[kw][3][1] += xv.w * g.y; acc[kw][3][2] += xv.w * g.z; acc[kw][3][3] += xv.w * g.w;
-        }
+        for (int kw = 0; kw < 3; ++kw) outer4(acc[kw], xv3[kw], g);
         bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
         xa = xc;
       }
@@ -423,7 +399,8 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], acc[kw][a][c]);
+        for (int c = 0; c < 4; ++c)
+          atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], (c & 1) ? acc[kw][a][c >> 1].y : acc[kw][a][c >> 1].x);
   } else if (active) {
     atomicAdd(&red[27 * 16 + 0], bsum.x); atomicAdd(&red[27 * 16 + 1], bsum.y);
     atomicAdd(&red[27 * 16 + 2], bsum.z); atomicAdd(&red[27 * 16 + 3], bsum.w);
