@@ -128,6 +128,16 @@ int nas3d_conv1x1_cat_wgrad(const nas3d_conv_desc* d, int nparts, const float* c
  *                              produce_big = 1: big (+)= bias + convT(small) (ConvT fwd, Conv3d dgrad)
  * ------------------------------------------------------------------------------------- */
 long long nas3d_umma_packed_floats(const nas3d_conv_desc* d, int produce_big);
+/* packing order of the weight operand: 0 = produce_big 0; 1 = produce_big 1 in tap order; 2 =
+ * produce_big 1 in parity-class order (stride-2 transposed gathers with even big extents walk
+ * only the (1+pd)(1+ph)(1+pw) taps that exist for each of the 8 output parity classes). */
+int nas3d_umma_pack_mode(const nas3d_conv_desc* d, int produce_big);
+/* all weight operands of one forward/backward in one launch per 48 entries: host arrays of n
+ * channel counts (16/32/64, Cb == Cs), packing modes (above), W pointers and destinations
+ * (nas3d_umma_packed_floats floats each, 16-byte aligned).  Weights only change in the
+ * optimiser step (search.py:238, train.py:127), so a step needs exactly one such call. */
+int nas3d_umma_pack_weights_batch(int n, const int* channels, const int* modes,
+                                  const float* const* w, float* const* packed, void* stream);
 int nas3d_umma_pack_weights(const nas3d_conv_desc* d, const float* w, int produce_big,
                             float* packed, void* stream);
 int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,

@@ -48,6 +48,8 @@ _SIGNATURES = {
                                 c_vp],
     "nas3d_umma_packed_floats": [C.POINTER(ConvDesc), c_int],
     "nas3d_umma_pack_weights": [C.POINTER(ConvDesc), c_vp, c_int, c_vp, c_vp],
+    "nas3d_umma_pack_mode": [C.POINTER(ConvDesc), c_int],
+    "nas3d_umma_pack_weights_batch": [c_int, _PI, _PI, _PP, _PP, c_vp],
     "nas3d_umma_conv": [C.POINTER(ConvDesc), c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp],
     "nas3d_moments_nc": [c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp],
     "nas3d_gn_coef": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, C.c_float, c_vp, c_vp, c_vp, c_vp],

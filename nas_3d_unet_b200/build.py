@@ -37,6 +37,8 @@ def _stale(target, deps):
 VARIANTS = {
     # A/B builds of the same sources (selected at run time with NAS3D_LIB=<path>)
     "noffma2": ["-DNAS3D_NO_FFMA2"],      # scalar FFMA instead of packed FFMA2 (common.cuh)
+    "pwminb4": ["-DNAS3D_PW_MINB=4"],     # pointwise kernels: register cap for 4 / 6 CTAs per SM
+    "pwminb6": ["-DNAS3D_PW_MINB=6"],
 }
 
 

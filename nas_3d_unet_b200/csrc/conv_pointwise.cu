@@ -58,7 +58,10 @@ constexpr int PW_MAX_W = 4096;   // floats of weights per (Cin x CO tile) in sme
 // partial sums go to a per-CTA fp64 array that is flushed with one atomic per (channel, moment)
 // when the CTA crosses a sample boundary or ends (host guarantees tiles do not straddle samples).
 template <int CO, bool SRC_IS_BIG, int VPT, bool MOM>
-__global__ void __launch_bounds__(PW_T) pointwise_kernel(const __grid_constant__ PwArgs A) {
+#ifndef NAS3D_PW_MINB
+#define NAS3D_PW_MINB 1
+#endif
+__global__ void __launch_bounds__(PW_T, NAS3D_PW_MINB) pointwise_kernel(const __grid_constant__ PwArgs A) {
   __shared__ __align__(16) float Wsm[PW_MAX_W];
   __shared__ double sm_mom[2 * CO];
   if (threadIdx.x < 2 * CO) sm_mom[threadIdx.x] = 0.0;
@@ -444,7 +447,7 @@ static void launch_pointwise_co(const PwArgs& A, unsigned gy, cudaStream_t st) {
   // big tensors: several voxels per thread, one resident wave of CTAs striding over the tiles;
   // small (deep-level) tensors: 1 voxel per thread, one tile per CTA - they are latency-bound
   if (pointwise_big(nvox)) {
-    static const int vpt_sfb = pw_env("NAS3D_PW_VPT_SFB", 4), vpt_bfs = pw_env("NAS3D_PW_VPT_BFS", 4);
+    static const int vpt_sfb = pw_env("NAS3D_PW_VPT_SFB", 4), vpt_bfs = pw_env("NAS3D_PW_VPT_BFS", 2);
     const int vpt = MOM ? 4 : (SRC_IS_BIG ? vpt_sfb : vpt_bfs);
     if (vpt == 1) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 1>(A, gy, nvox, st);
     else if (vpt == 2) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 2>(A, gy, nvox, st);

@@ -90,14 +90,26 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
                    "r"((unsigned)(sizeof(float4) * TS::PLANE * C4))
                    : "memory");
-#pragma unroll
-      for (int cc = 0; cc < C4; ++cc) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + cc * TS::PLANE);
+      if (C == 4 && A.tma_merged) {
+        // dense C = 4: (W, C) merged into one 16*PW-byte inner box row - 18x fewer, 34x longer
+        // TMA row requests than the 16-byte rows of the 5-D box (ncu r1e: 25 % of the warp time
+        // of this kernel was spent waiting for the tile)
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
         asm volatile(
-            "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
-            "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
-            "l"(&tmap), "r"(cc * 4), "r"(w0 - DIL), "r"(h0 - DIL), "r"(d0 - DIL), "r"(n), "r"(bar)
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst),
+            "l"(&tmap), "r"((w0 - DIL) * 4), "r"(h0 - DIL), "r"(d0 - DIL), "r"(n), "r"(bar)
             : "memory");
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < C4; ++cc) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + cc * TS::PLANE);
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
+              "l"(&tmap), "r"(cc * 4), "r"(w0 - DIL), "r"(h0 - DIL), "r"(d0 - DIL), "r"(n), "r"(bar)
+              : "memory");
+        }
       }
     }
     __syncthreads();     // barrier init visible to the waiters; weights staged
@@ -121,9 +133,9 @@ __global__ void __launch_bounds__(TileShape<C, DIL, HG, DG, MD>::THREADS)
       const int pd = r / PH;
       const int gd = d0 - DIL + pd, gh = h0 - DIL + ph, gw = w0 - DIL + pw;
       const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
-      const float* src =
-          ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx + cc * 4 : A.x;
-      cp_async16(&tile[cc * TS::PLANE + (pd * PH + ph) * PW + pw], src, ok);
+      // 32-bit in-sample offset (host guarantees samples < 2^31 floats)
+      const unsigned off = (unsigned)((((gd * A.Hx + gh) * A.Wx + gw) * A.xs) * A.ldx + cc * 4);
+      cp_async16(&tile[cc * TS::PLANE + (pd * PH + ph) * PW + pw], ok ? xb + off : A.x, ok);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -239,20 +251,28 @@ struct WgShape {
   static constexpr int NGROUPS = ROWS / 3;            // 3 adjacent rows per warp step
   static_assert(ROWS % 3 == 0 && NGROUPS % NWARP == 0, "tile rows must split into 3-row groups per warp");
   static_assert(TH == 12 || TH == 6, "bank-conflict-free pitches are tabulated for TH = 12 / 6");
-  static constexpr size_t SMEM = sizeof(float4) * (XTILE + YTILE) + sizeof(float) * (27 * 16 + 4);
+  static constexpr int NBUF = 2;                      // double-buffered tiles (prefetch of tile i+1)
+  static constexpr size_t SMEM = sizeof(float4) * NBUF * (XTILE + YTILE) + sizeof(float) * (27 * 16 + 4);
 };
 
 // PERSISTENT: blockIdx.x strides over the tiles, blockIdx.y = (ci-chunk, co-chunk) pair; the
 // 48 partial sums of a lane live in registers across all tiles of the CTA and are flushed once.
-template <int DIL, int TH, int TD, int NWARP, int TWT>
+// Staging cost matters here (it was 27 % of the instruction stream, ncu r1e): the x tile is
+// staged ROW-wise (a warp owns a (d,h) row: one 64-bit row pointer, then 32-bit per-lane offsets)
+// and the dy tile with 32-bit in-sample offsets (host guarantees samples < 2^31 floats).
+// BIAS = false drops the bias-gradient adds from the hot loop (convs followed by GroupNorm get
+// their bias gradient analytically, engine.py).
+// The tiles are DOUBLE-BUFFERED: the cp.async copies of the CTA's next tile are issued before the
+// FMA loop of the current one (one __syncthreads per tile), so the FMA pipe no longer idles while
+// a whole CTA waits for its tile (ncu r1e: pipe 58 % busy with staging and compute serialised).
+template <int DIL, int TH, int TD, int NWARP, int TWT, bool BIAS>
 __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
     wgrad3_s1_kernel(const WgradArgs A, int C, int ntiles) {
   using WS = WgShape<DIL, TH, TD, NWARP, TWT>;
   constexpr int PW = WS::PW, PWP = WS::PWP, PH = WS::PH, TW = WS::TW, WN = WS::WN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* xt = reinterpret_cast<float4*>(smem_raw);
-  float4* yt = xt + WS::XTILE;
-  float* red = reinterpret_cast<float*>(yt + WS::YTILE);   // [27][4][4] + [4]
+  float4* const tiles = reinterpret_cast<float4*>(smem_raw);   // [NBUF][XTILE + YTILE]
+  float* red = reinterpret_cast<float*>(tiles + WS::NBUF * (WS::XTILE + WS::YTILE));   // [27][4][4] + [4]
 
   const int C4 = C / 4;
   const int cic = blockIdx.y / C4, coc = blockIdx.y % C4;
@@ -274,41 +294,72 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
 
   for (int i = threadIdx.x; i < 27 * 16 + 4; i += WS::THREADS) red[i] = 0.f;
 
+  // ---- staging: THREAD-COLUMN scheme.  A thread owns one w column of the haloed x tile (and one of
+  // the dy tile) for the whole kernel and walks down the (d,h) rows RPI rows at a time, so the
+  // per-copy instruction stream is ~18 integer ops (ncu r1e: with a per-element index
+  // decomposition the staging code issued as many instructions as the FMA loop and the two do
+  // not overlap in the issue slot).  32-bit in-sample offsets (host guarantees < 2^31 floats).
+  constexpr int XROWS = WS::PD * PH, RPI_X = WS::THREADS / PW, XITER = (XROWS + RPI_X - 1) / RPI_X;
+  constexpr int RPI_Y = WS::THREADS / TW, YITER = (WS::ROWS + RPI_Y - 1) / RPI_Y;
+  const int my_pw = threadIdx.x % PW, my_xr0 = threadIdx.x / PW;
+  const bool x_thread = my_xr0 < RPI_X;
+  const int my_yw = threadIdx.x % TW, my_yr0 = threadIdx.x / TW;
+  const int xstep = A.xs * A.ldx;                         // floats between lattice neighbours along w
+  const unsigned xrow = (unsigned)(A.xs * A.Wx * A.ldx);   // ... along h (lattice rows)
+  const unsigned yrow = (unsigned)(A.ys * A.Wy * A.ldy);
+  // issue the cp.async copies of one tile into buffer `buf` (one commit group per thread)
+  auto stage = [&](int tile, int buf) {
+    float4* xt = tiles + buf * (WS::XTILE + WS::YTILE);
+    float4* yt = xt + WS::XTILE;
+    unsigned b = (unsigned)tile;
+    const unsigned tw = b % (unsigned)A.tiles_w; b /= (unsigned)A.tiles_w;
+    const unsigned th = b % (unsigned)A.tiles_h; b /= (unsigned)A.tiles_h;
+    const unsigned td = b % (unsigned)A.tiles_d;
+    const unsigned n = b / (unsigned)A.tiles_d;
+    const int w0 = (int)tw * TW, h0 = (int)th * TH, d0 = (int)td * TD;
+    {
+      const int gw = w0 - DIL + my_pw;
+      const bool cok = (unsigned)gw < (unsigned)A.W;
+      const float* xcol = A.x + (long long)n * A.Dx * A.Hx * A.Wx * A.ldx + cic * 4 + gw * xstep;
+#pragma unroll
+      for (int k = 0; k < XITER; ++k) {
+        const int r = my_xr0 + k * RPI_X;
+        if (x_thread && r < XROWS) {
+          const int pd = r / PH, ph = r - pd * PH;
+          const int gd = d0 - DIL + pd, gh = h0 - DIL + ph;
+          const bool ok = cok && (unsigned)gd < (unsigned)A.D && (unsigned)gh < (unsigned)A.H;
+          cp_async16(xt + pd * WS::XPLANE + ph * PWP + my_pw,
+                     ok ? xcol + (unsigned)(gd * A.Hx + gh) * xrow : A.x, ok);
+        }
+      }
+    }
+    {
+      const int gw = w0 + my_yw;
+      const bool cok = gw < A.W;                           // outside: dy = 0 contributes nothing
+      const float* ycol = A.dy + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + coc * 4 + gw * (A.ys * A.ldy);
+#pragma unroll
+      for (int k = 0; k < YITER; ++k) {
+        const int r = my_yr0 + k * RPI_Y;
+        if (r < WS::ROWS) {
+          const int pd = r / TH, ph = r - pd * TH;
+          const int gd = d0 + pd, gh = h0 + ph;
+          const bool ok = cok && gd < A.D && gh < A.H;
+          cp_async16(yt + r * WS::YP + my_yw, ok ? ycol + (unsigned)(gd * A.Hy + gh) * yrow : A.dy, ok);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+  int buf = 0;
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int b = tile;
-    const int tw = b % A.tiles_w; b /= A.tiles_w;
-    const int th = b % A.tiles_h; b /= A.tiles_h;
-    const int td = b % A.tiles_d;
-    const int n = b / A.tiles_d;
-    const int w0 = tw * TW, h0 = th * TH, d0 = td * TD;
-    __syncthreads();     // previous tile fully consumed
-    const float* xb = A.x + (long long)n * A.Dx * A.Hx * A.Wx * A.ldx + cic * 4;
-    for (int i = threadIdx.x; i < WS::PD * PH * PW; i += WS::THREADS) {
-      int r = i;
-      const int pw = r % PW; r /= PW;
-      const int ph = r % PH;
-      const int pd = r / PH;
-      const int gd = d0 - DIL + pd, gh = h0 - DIL + ph, gw = w0 - DIL + pw;
-      const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
-      const float* src =
-          ok ? xb + (((long long)gd * A.xs * A.Hx + gh * A.xs) * A.Wx + gw * A.xs) * A.ldx : A.x;
-      cp_async16(&xt[pd * WS::XPLANE + ph * PWP + pw], src, ok);
-    }
-    const float* yb = A.dy + (long long)n * A.Dy * A.Hy * A.Wy * A.ldy + coc * 4;
-    for (int i = threadIdx.x; i < TD * TH * TW; i += WS::THREADS) {
-      int r = i;
-      const int pw = r % TW; r /= TW;
-      const int ph = r % TH;
-      const int pd = r / TH;
-      const int gd = d0 + pd, gh = h0 + ph, gw = w0 + pw;
-      const bool ok = gd < A.D && gh < A.H && gw < A.W;   // outside: dy = 0 contributes nothing
-      const float* src =
-          ok ? yb + (((long long)gd * A.ys * A.Hy + gh * A.ys) * A.Wy + gw * A.ys) * A.ldy : A.dy;
-      cp_async16(&yt[(pd * TH + ph) * WS::YP + pw], src, ok);
-    }
-    cp_async_wait_all();
-    __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // my copies of `tile` have landed
+    __syncthreads();   // ... everyone's have, and everyone is done with the other buffer
+    if (tile + (int)gridDim.x < ntiles) stage(tile + gridDim.x, buf ^ 1);   // in flight during the FMAs
+    const float4* xt = tiles + buf * (WS::XTILE + WS::YTILE);
+    const float4* yt = xt + WS::XTILE;
 
 #pragma unroll 1
     for (int grp = warp; grp < WS::NGROUPS; grp += NWARP) {
@@ -332,7 +383,7 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
           const float4 g = yq[u];
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) outer4(acc[kw], win[(u + kw * DIL) % WN], g);
-          bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+          if (BIAS) { bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w; }
         }
       }
       // tail: TW % WN steps
@@ -345,7 +396,7 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
           const float4 g = yq[u];
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) outer4(acc[kw], win[(u + kw * DIL) % WN], g);
-          bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+          if (BIAS) { bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w; }
         }
       }
     }
@@ -360,7 +411,7 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], (c & 1) ? acc[kw][a][c >> 1].y : acc[kw][a][c >> 1].x);
-  } else if (active) {
+  } else if (BIAS && active) {
     atomicAdd(&red[27 * 16 + 0], bsum.x); atomicAdd(&red[27 * 16 + 1], bsum.y);
     atomicAdd(&red[27 * 16 + 2], bsum.z); atomicAdd(&red[27 * 16 + 3], bsum.w);
   }
@@ -370,7 +421,8 @@ __global__ void __launch_bounds__(WgShape<DIL, TH, TD, NWARP, TWT>::THREADS)
     const int co = coc * 4 + i % 4, ci = cic * 4 + (i / 4) % 4, t = i / 16;
     atomicAdd(A.dW + (co * C + ci) * 27 + t, red[i]);
   }
-  if (A.dbias && cic == 0 && threadIdx.x < 4) atomicAdd(A.dbias + coc * 4 + threadIdx.x, red[27 * 16 + threadIdx.x]);
+  if (BIAS && A.dbias && cic == 0 && threadIdx.x < 4)
+    atomicAdd(A.dbias + coc * 4 + threadIdx.x, red[27 * 16 + threadIdx.x]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -408,6 +460,21 @@ static bool make_ndhwc_map(CUtensorMap* m, const float* base, int C, int W, int 
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 4-D map {W*4, H, D, N} of a DENSE 4-channel NDHWC tensor (ld == 4), box {4*bw, bh, bd, 1}
+static bool make_ndhwc4_merged_map(CUtensorMap* m, const float* base, int W, int H, int D, int N,
+                                   int bw, int bh, int bd) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  const char* e = getenv("NAS3D_TMA_MERGED");
+  if (!enc || (e && e[0] == '0') || 4 * bw > 256) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)(4 * bw), (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int C, int DIL, int HG, int DG, int MD, bool FLIP>
 static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   using TS = TileShape<C, DIL, HG, DG, MD>;
@@ -426,21 +493,29 @@ static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   const long long blocks = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  const bool tma = A.xs == 1 && (TS::PLANE % 8 == 0 || TS::C4 == 1) &&
-                   make_ndhwc_map(&tmap, A.x, C, A.W, A.H, A.D, A.N, A.ldx, TS::PW, TS::PH, TS::PD);
+  A.tma_merged = 0;
+  bool tma = false;
+  if (C == 4 && A.xs == 1 && A.ldx == 4 &&
+      make_ndhwc4_merged_map(&tmap, A.x, A.W, A.H, A.D, A.N, TS::PW, TS::PH, TS::PD)) {
+    tma = true;
+    A.tma_merged = 1;
+  } else {
+    tma = A.xs == 1 && (TS::PLANE % 8 == 0 || TS::C4 == 1) &&
+          make_ndhwc_map(&tmap, A.x, C, A.W, A.H, A.D, A.N, A.ldx, TS::PW, TS::PH, TS::PD);
+  }
   if (tma) kern_tma<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A, tmap);
   else kern_cp<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A, tmap);
   return launched("conv3_s1");
 }
 
-template <int DIL, int TH, int TD, int NWARP, int TWT>
-static int launch_wgrad3(const WgradArgs& A0, int C, cudaStream_t st) {
+template <int DIL, int TH, int TD, int NWARP, int TWT, bool BIAS>
+static int launch_wgrad3_b(const WgradArgs& A0, int C, cudaStream_t st) {
   using WS = WgShape<DIL, TH, TD, NWARP, TWT>;
   WgradArgs A = A0;
   A.tiles_w = (A.W + WS::TW - 1) / WS::TW;
   A.tiles_h = (A.H + TH - 1) / TH;
   A.tiles_d = (A.D + TD - 1) / TD;
-  auto kern = wgrad3_s1_kernel<DIL, TH, TD, NWARP, TWT>;
+  auto kern = wgrad3_s1_kernel<DIL, TH, TD, NWARP, TWT, BIAS>;
   static int occ = 0;
   if (!occ) {
     NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
@@ -454,6 +529,12 @@ static int launch_wgrad3(const WgradArgs& A0, int C, cudaStream_t st) {
   if (gx > ntiles) gx = ntiles;
   kern<<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, C, (int)ntiles);
   return launched("wgrad3_s1");
+}
+
+template <int DIL, int TH, int TD, int NWARP, int TWT>
+static int launch_wgrad3(const WgradArgs& A, int C, cudaStream_t st) {
+  return A.dbias ? launch_wgrad3_b<DIL, TH, TD, NWARP, TWT, true>(A, C, st)
+                 : launch_wgrad3_b<DIL, TH, TD, NWARP, TWT, false>(A, C, st);
 }
 
 __global__ void __launch_bounds__(256)
@@ -479,6 +560,7 @@ int fill_channels(float* y, const float* bias, long long nvox, int C, int ld, cu
 // returns NAS3D_ERR_UNSUPPORTED (without setting an error) when the shape is not covered
 int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st) {
   if (A.W < 8 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.y)) return NAS3D_ERR_UNSUPPORTED;
+  if ((long long)A.Dx * A.Hx * A.Wx * A.ldx >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;   // 32-bit staging offsets
 #define NAS3D_CASE(CC, DD, HG, DG, MD)                                          \
   if (C == CC && dil == DD)                                                      \
     return flip ? launch_conv3<CC, DD, HG, DG, MD, true>(A, st)                  \
@@ -496,10 +578,23 @@ int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t s
 int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st) {
   if (A.W < 4 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.dy)) return NAS3D_ERR_UNSUPPORTED;
   if (C % 4 || C > 64) return NAS3D_ERR_UNSUPPORTED;
+  // 32-bit in-sample offsets in the staging loops
+  if ((long long)A.Dx * A.Hx * A.Wx * A.ldx >= (1ll << 31) || (long long)A.Dy * A.Hy * A.Wy * A.ldy >= (1ll << 31))
+    return NAS3D_ERR_UNSUPPORTED;
+  // tile (TH x TD) with the least zero-padded work: 12 x 4 (default), 6 x 8 (e.g. H = 64: 66
+  // instead of 72 padded rows; H = 16: 18 instead of 24), 6 x 4 for shallow volumes
+  auto padded = [&](int th, int td) {
+    return (long long)((A.H + th - 1) / th * th) * ((A.D + td - 1) / td * td);
+  };
+  const long long p12 = padded(12, 4), p68 = padded(6, 8), p64 = padded(6, 4);
+  const int cfg = (p12 <= p68 && p12 <= p64) ? 0 : (p68 <= p64 ? 1 : 2);
 #define NAS3D_WG(TWT)                                                              \
-  if (A.H >= 12) {                                                                  \
-    if (dil == 1) return launch_wgrad3<1, 12, 4, 8, TWT>(A, C, st);                 \
-    if (dil == 2) return launch_wgrad3<2, 12, 4, 8, TWT>(A, C, st);                 \
+  if (cfg == 0) {                                                                   \
+    if (dil == 1) return launch_wgrad3<1, 12, 4, 16, TWT>(A, C, st);                \
+    if (dil == 2) return launch_wgrad3<2, 12, 4, 16, TWT>(A, C, st);                \
+  } else if (cfg == 1) {                                                            \
+    if (dil == 1) return launch_wgrad3<1, 6, 8, 16, TWT>(A, C, st);                 \
+    if (dil == 2) return launch_wgrad3<2, 6, 8, 16, TWT>(A, C, st);                 \
   } else {                                                                          \
     if (dil == 1) return launch_wgrad3<1, 6, 4, 8, TWT>(A, C, st);                  \
     if (dil == 2) return launch_wgrad3<2, 6, 4, 8, TWT>(A, C, st);                  \

@@ -22,6 +22,7 @@ struct TiledArgs {
   int ys, Dy, Hy, Wy;
   int tiles_w, tiles_h, tiles_d;
   double* moments;     // optional [N][C][2] {sum, sum^2} of the written output (fused GN stats)
+  int tma_merged;      // set by the launcher: 4-D tensor map with the (W, C) dims merged (dense C = 4)
 };
 
 struct WgradArgs {

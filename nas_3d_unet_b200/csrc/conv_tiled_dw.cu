@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(D1_THREADS) dw3_s1_kernel(const TiledArgs A) {
     const int pd = r / D1_PH;
     const int gd = d0 - 1 + pd, gh = h0 - 1 + ph, gw = w0 - 1 + pw;
     const bool ok = gd >= 0 && gd < A.D && gh >= 0 && gh < A.H && gw >= 0 && gw < A.W;
-    const float* src = ok ? xb + (((long long)gd * A.H + gh) * A.W + gw) * A.ldx : A.x;
-    dcp16(&tile[i], src, ok);
+    // 32-bit in-sample offset (host guarantees samples < 2^31 floats)
+    const unsigned off = (unsigned)(((gd * A.H + gh) * A.W + gw) * A.ldx);
+    dcp16(&tile[i], ok ? xb + off : A.x, ok);
   }
   dcp_wait_all();
   __syncthreads();
@@ -144,8 +145,8 @@ __global__ void __launch_bounds__(DS_THREADS) dw3_s2_sfb_kernel(const S2Args A) 
     const int bw = pwi < DS_EVEN ? 2 * pwi : 2 * (pwi - DS_EVEN) + 1;
     const int gd = 2 * d0 - 1 + pd, gh = 2 * h0 - 1 + ph, gw = 2 * w0 - 1 + bw;
     const bool ok = gd >= 0 && gd < A.Db && gh >= 0 && gh < A.Hb && gw >= 0 && gw < A.Wb;
-    const float* src = ok ? xb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big : A.big;
-    dcp16(&tile[i], src, ok);
+    const unsigned off = (unsigned)(((gd * A.Hb + gh) * A.Wb + gw) * A.ld_big);
+    dcp16(&tile[i], ok ? xb + off : A.big, ok);
   }
   dcp_wait_all();
   __syncthreads();
@@ -217,8 +218,8 @@ __global__ void __launch_bounds__(DB_THREADS) dw3_s2_bfs_kernel(const S2Args A) 
     const int pd = r / DB_SH;
     const int gd = d0 / 2 + pd, gh = h0 / 2 + ph, gw = w0 / 2 + pw;
     const bool ok = gd < A.Ds && gh < A.Hs && gw < A.Ws;
-    const float* src = ok ? sb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small : A.small;
-    dcp16(&tile[i], src, ok);
+    const unsigned off = (unsigned)(((gd * A.Hs + gh) * A.Ws + gw) * A.ld_small);
+    dcp16(&tile[i], ok ? sb + off : A.small, ok);
   }
   dcp_wait_all();
   __syncthreads();
@@ -327,26 +328,27 @@ __global__ void __launch_bounds__(DwWgShape<S>::THREADS)
     const int w0 = tw * TW, h0 = th * TH, d0 = td * TD;
     __syncthreads();
     const float* xb = A.big + (long long)n * A.Db * A.Hb * A.Wb * A.ld_big + c0;
-    for (int i = threadIdx.x; i < WS::PD * PH * PW; i += WS::THREADS) {
-      int r = i;
-      const int pw = r % PW; r /= PW;
-      const int ph = r % PH;
-      const int pd = r / PH;
-      const int gd = S * d0 - 1 + pd, gh = S * h0 - 1 + ph, gw = S * w0 - 1 + pw;
-      const bool ok = gd >= 0 && gd < A.Db && gh >= 0 && gh < A.Hb && gw >= 0 && gw < A.Wb;
-      const float* src = ok ? xb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big : A.big;
-      dcp16(&xt[pd * WS::XPLANE + ph * PWP + pw], src, ok);
+    // row-wise staging: one 64-bit row pointer per (d,h) row, 32-bit per-lane offsets
+    for (int r = warp; r < WS::PD * PH; r += WS::NWARP) {
+      const int pd = r / PH, ph = r - pd * PH;
+      const int gd = S * d0 - 1 + pd, gh = S * h0 - 1 + ph;
+      const bool rok = gd >= 0 && gd < A.Db && gh >= 0 && gh < A.Hb;
+      const float* rp = xb + (long long)(gd * A.Hb + gh) * A.Wb * A.ld_big;
+      float4* drow = xt + pd * WS::XPLANE + ph * PWP;
+      for (int pw = lane; pw < PW; pw += 32) {
+        const int gw = S * w0 - 1 + pw;
+        const bool ok = rok && gw >= 0 && gw < A.Wb;
+        dcp16(drow + pw, ok ? rp + gw * A.ld_big : A.big, ok);
+      }
     }
     const float* yb = A.small + (long long)n * A.Ds * A.Hs * A.Ws * A.ld_small + c0;
     for (int i = threadIdx.x; i < TD * TH * TW; i += WS::THREADS) {
-      int r = i;
-      const int pw = r % TW; r /= TW;
-      const int ph = r % TH;
-      const int pd = r / TH;
+      const int pw = i % TW, r = i / TW;
+      const int ph = r % TH, pd = r / TH;
       const int gd = d0 + pd, gh = h0 + ph, gw = w0 + pw;
       const bool ok = gd < A.Ds && gh < A.Hs && gw < A.Ws;
-      const float* src = ok ? yb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small : A.small;
-      dcp16(&yt[(pd * TH + ph) * WS::YP + pw], src, ok);
+      const unsigned off = (unsigned)(((gd * A.Hs + gh) * A.Ws + gw) * A.ld_small);
+      dcp16(&yt[r * WS::YP + pw], ok ? yb + off : A.small, ok);
     }
     dcp_wait_all();
     __syncthreads();
@@ -396,6 +398,7 @@ static int set_smem(K kern, size_t bytes) {
 int tiled_dw_s1(bool flip, const TiledArgs& A0, int C, cudaStream_t st) {
   if (C % 4 || A0.ldx % 4 || A0.ldy % 4 || !aligned16(A0.x) || !aligned16(A0.y) || A0.W < 8)
     return NAS3D_ERR_UNSUPPORTED;
+  if ((long long)A0.D * A0.H * A0.W * A0.ldx >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;   // 32-bit staging offsets
   TiledArgs A = A0;
   A.tiles_w = (A.W + D1_TW - 1) / D1_TW;
   A.tiles_h = (A.H + D1_TH - 1) / D1_TH;
@@ -413,6 +416,7 @@ int tiled_dw_s1(bool flip, const TiledArgs& A0, int C, cudaStream_t st) {
 }
 
 static bool dw_s2_ok(const S2Args& A) {
+  if ((long long)A.Db * A.Hb * A.Wb * A.ld_big >= (1ll << 31)) return false;   // 32-bit staging offsets
   return A.Cb == A.Cs && A.Cb % 4 == 0 && A.ld_big % 4 == 0 && A.ld_small % 4 == 0 &&
          aligned16(A.big) && aligned16(A.small) && A.Db == 2 * A.Ds && A.Hb == 2 * A.Hs &&
          A.Wb == 2 * A.Ws && A.Ws >= 8;
@@ -470,6 +474,7 @@ int tiled_dw_wgrad(const S2Args& A, int stride, cudaStream_t st) {
   if (A.Cb != A.Cs || A.Cb % 4 || A.ld_big % 4 || A.ld_small % 4 || !aligned16(A.big) ||
       !aligned16(A.small) || A.Ws < 8)
     return NAS3D_ERR_UNSUPPORTED;
+  if ((long long)A.Db * A.Hb * A.Wb * A.ld_big >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;
   if (stride == 1 && A.Db == A.Ds && A.Hb == A.Hs && A.Wb == A.Ws) return launch_dw_wgrad<1>(A, st);
   if (stride == 2 && dw_s2_ok(A)) return launch_dw_wgrad<2>(A, st);
   return NAS3D_ERR_UNSUPPORTED;

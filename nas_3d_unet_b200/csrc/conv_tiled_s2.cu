@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
     const int bw = pwi < EVEN_N ? 2 * pwi : 2 * (pwi - EVEN_N) + 1;
     const int gd = 2 * d0 - 1 + pd, gh = 2 * h0 - 1 + ph, gw = 2 * w0 - 1 + bw;
     const bool ok = gd >= 0 && gd < A.Db && gh >= 0 && gh < A.Hb && gw >= 0 && gw < A.Wb;
-    const float* src = ok ? xb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big + cc * 4 : A.big;
-    cp16(&tile[cc * TS::PLANE + (pd * PH + ph) * PWS + pwi], src, ok);
+    // 32-bit in-sample offset (host guarantees samples < 2^31 floats)
+    const unsigned off = (unsigned)(((gd * A.Hb + gh) * A.Wb + gw) * A.ld_big + cc * 4);
+    cp16(&tile[cc * TS::PLANE + (pd * PH + ph) * PWS + pwi], ok ? xb + off : A.big, ok);
   }
   cp_wait_all();
   __syncthreads();
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(co
     const int pd = r / SH;
     const int gd = d0 / 2 + pd, gh = h0 / 2 + ph, gw = w0 / 2 + pw;
     const bool ok = gd < A.Ds && gh < A.Hs && gw < A.Ws;
-    const float* src = ok ? sb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small + cc * 4 : A.small;
-    cp16(&tile[cc * TS::PLANE + (pd * SH + ph) * SW + pw], src, ok);
+    const unsigned off = (unsigned)(((gd * A.Hs + gh) * A.Ws + gw) * A.ld_small + cc * 4);
+    cp16(&tile[cc * TS::PLANE + (pd * SH + ph) * SW + pw], ok ? sb + off : A.small, ok);
   }
   cp_wait_all();
   __syncthreads();
@@ -307,7 +308,8 @@ struct WgS2Shape {
   static constexpr size_t SMEM = sizeof(float4) * (XTILE + YTILE) + sizeof(float) * (27 * 16 + 4);
 };
 
-template <int TWT>
+// Row-wise staging / BIAS template: see wgrad3_s1_kernel (conv_tiled.cu).
+template <int TWT, bool BIAS>
 __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
     wgrad3_s2_kernel(const S2Args A, int ntiles) {
   using WS = WgS2Shape<TWT>;
@@ -347,26 +349,26 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
     const int w0 = tw * TW, h0 = th * TH, d0 = td * TD;     // small coordinates
     __syncthreads();
     const float* xb = A.big + (long long)n * A.Db * A.Hb * A.Wb * A.ld_big + cic * 4;
-    for (int i = threadIdx.x; i < WS::PD * PH * PW; i += WS::THREADS) {
-      int r = i;
-      const int pw = r % PW; r /= PW;
-      const int ph = r % PH;
-      const int pd = r / PH;
-      const int gd = 2 * d0 - 1 + pd, gh = 2 * h0 - 1 + ph, gw = 2 * w0 - 1 + pw;
-      const bool ok = gd >= 0 && gd < A.Db && gh >= 0 && gh < A.Hb && gw >= 0 && gw < A.Wb;
-      const float* src = ok ? xb + (((long long)gd * A.Hb + gh) * A.Wb + gw) * A.ld_big : A.big;
-      cp16(&xt[pd * WS::XPLANE + ph * PWP + pw], src, ok);
+    for (int r = warp; r < WS::PD * PH; r += WS::NWARP) {
+      const int pd = r / PH, ph = r - pd * PH;
+      const int gd = 2 * d0 - 1 + pd, gh = 2 * h0 - 1 + ph;
+      const bool rok = gd >= 0 && gd < A.Db && gh >= 0 && gh < A.Hb;
+      const float* rp = xb + (long long)(gd * A.Hb + gh) * A.Wb * A.ld_big;
+      float4* drow = xt + pd * WS::XPLANE + ph * PWP;
+      for (int pw = lane; pw < PW; pw += 32) {
+        const int gw = 2 * w0 - 1 + pw;
+        const bool ok = rok && gw >= 0 && gw < A.Wb;
+        cp16(drow + pw, ok ? rp + gw * A.ld_big : A.big, ok);
+      }
     }
     const float* yb = A.small + (long long)n * A.Ds * A.Hs * A.Ws * A.ld_small + coc * 4;
     for (int i = threadIdx.x; i < TD * TH * TW; i += WS::THREADS) {
-      int r = i;
-      const int pw = r % TW; r /= TW;
-      const int ph = r % TH;
-      const int pd = r / TH;
+      const int pw = i % TW, r = i / TW;
+      const int ph = r % TH, pd = r / TH;
       const int gd = d0 + pd, gh = h0 + ph, gw = w0 + pw;
       const bool ok = gd < A.Ds && gh < A.Hs && gw < A.Ws;
-      const float* src = ok ? yb + (((long long)gd * A.Hs + gh) * A.Ws + gw) * A.ld_small : A.small;
-      cp16(&yt[(pd * TH + ph) * WS::YP + pw], src, ok);
+      const unsigned off = (unsigned)(((gd * A.Hs + gh) * A.Ws + gw) * A.ld_small);
+      cp16(&yt[r * WS::YP + pw], ok ? yb + off : A.small, ok);
     }
     cp_wait_all();
     __syncthreads();
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
         const float4 xv3[3] = {xa, xb2, xc};
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) outer4(acc[kw], xv3[kw], g);
-        bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w;
+        if (BIAS) { bsum.x += g.x; bsum.y += g.y; bsum.z += g.z; bsum.w += g.w; }
         xa = xc;
       }
     }
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           atomicAdd(&red[((kdkh * 3 + kw) * 4 + a) * 4 + c], (c & 1) ? acc[kw][a][c >> 1].y : acc[kw][a][c >> 1].x);
-  } else if (active) {
+  } else if (BIAS && active) {
     atomicAdd(&red[27 * 16 + 0], bsum.x); atomicAdd(&red[27 * 16 + 1], bsum.y);
     atomicAdd(&red[27 * 16 + 2], bsum.z); atomicAdd(&red[27 * 16 + 3], bsum.w);
   }
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
     const int cs = coc * 4 + i % 4, cb = cic * 4 + (i / 4) % 4, t = i / 16;
     atomicAdd(A.dW + ((long long)cs * A.Cb + cb) * 27 + t, red[i]);
   }
-  if (A.dbias_small && cic == 0 && threadIdx.x < 4)
+  if (BIAS && A.dbias_small && cic == 0 && threadIdx.x < 4)
     atomicAdd(A.dbias_small + coc * 4 + threadIdx.x, red[27 * 16 + threadIdx.x]);
 }
 
@@ -453,6 +455,7 @@ static int launch_bfs(S2Args A, cudaStream_t st) {
 }
 
 static bool s2_common_ok(const S2Args& A) {
+  if ((long long)A.Db * A.Hb * A.Wb * A.ld_big >= (1ll << 31)) return false;   // 32-bit staging offsets
   return A.ld_big % 4 == 0 && A.ld_small % 4 == 0 && aligned16(A.big) && aligned16(A.small) &&
          A.Db == 2 * A.Ds && A.Hb == 2 * A.Hs && A.Wb == 2 * A.Ws && A.Ws >= 8;
 }
@@ -472,16 +475,16 @@ int tiled_s2_bfs(const S2Args& A, cudaStream_t st) {
   return NAS3D_ERR_UNSUPPORTED;
 }
 
-template <int TWT>
-static int launch_s2_wgrad(S2Args A, cudaStream_t st) {
+template <int TWT, bool BIAS>
+static int launch_s2_wgrad_b(S2Args A, cudaStream_t st) {
   using WS = WgS2Shape<TWT>;
   A.tiles_w = (A.Ws + WS::TW - 1) / WS::TW;
   A.tiles_h = (A.Hs + WS::TH - 1) / WS::TH;
   A.tiles_d = (A.Ds + WS::TD - 1) / WS::TD;
   static int occ = 0;
   if (!occ) {
-    NAS3D_CUDA(cudaFuncSetAttribute(wgrad3_s2_kernel<TWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
-    NAS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wgrad3_s2_kernel<TWT>, WS::THREADS, WS::SMEM));
+    NAS3D_CUDA(cudaFuncSetAttribute(wgrad3_s2_kernel<TWT, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
+    NAS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wgrad3_s2_kernel<TWT, BIAS>, WS::THREADS, WS::SMEM));
     if (occ < 1) occ = 1;
   }
   const long long ntiles = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
@@ -489,14 +492,20 @@ static int launch_s2_wgrad(S2Args A, cudaStream_t st) {
   long long gx = (long long)kNumSMs * occ / pairs;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
-  wgrad3_s2_kernel<TWT><<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, (int)ntiles);
+  wgrad3_s2_kernel<TWT, BIAS><<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, (int)ntiles);
   return launched("wgrad3_s2");
+}
+
+template <int TWT>
+static int launch_s2_wgrad(const S2Args& A, cudaStream_t st) {
+  return A.dbias_small ? launch_s2_wgrad_b<TWT, true>(A, st) : launch_s2_wgrad_b<TWT, false>(A, st);
 }
 
 int tiled_s2_wgrad(const S2Args& A, cudaStream_t st) {
   const bool ok = A.ld_big % 4 == 0 && A.ld_small % 4 == 0 && aligned16(A.big) && aligned16(A.small) &&
                   A.Db == 2 * A.Ds && A.Hb == 2 * A.Hs && A.Wb == 2 * A.Ws && A.Ws >= 2;
   if (!ok || A.Cb % 4 || A.Cs % 4 || A.Cb > 64 || A.Cs > 64) return NAS3D_ERR_UNSUPPORTED;
+  if ((long long)A.Db * A.Hb * A.Wb * A.ld_big >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;
   if (A.Ws <= 8) return launch_s2_wgrad<8>(A, st);
   if (A.Ws <= 16) return launch_s2_wgrad<16>(A, st);
   return launch_s2_wgrad<32>(A, st);

@@ -16,6 +16,7 @@
 // * one elected thread issues tcgen05.mma (cta_group::1, kind::tf32, M=128), completion is
 //   tracked with tcgen05.commit -> mbarrier, two smem stages so the gather of stage i+1 overlaps
 //   the MMAs of stage i; the epilogue reads TMEM with tcgen05.ld (32 lanes x 8 columns).
+#include <string.h>
 #include "common.cuh"
 
 namespace nas3d {
@@ -34,7 +35,38 @@ struct UmmaArgs {
   long long nvox;
   double* moments;         // optional fused GN statistics (host guarantees V % 128 == 0)
   int splits;              // split-K over the tap stages (gridDim.y); > 1: atomic epilogue
+  int cls;                 // 1: stride-2 transposed gather decomposed into the 8 output parity
+                           //    classes (gridDim.z = 8, nvox = voxels per class), see below
 };
+
+// Parity classes of a stride-2 / pad-1 / dil-1 transposed gather (ConvTranspose3d forward, Conv3d
+// dgrad): output voxel o = 2*q + p (per axis) receives input voxel (o + 1 - k) / 2 only when
+// o + 1 - k is even, i.e. p = 0: tap k = 1 (input q); p = 1: taps k = 0 (input q + 1), 2 (input q).
+// Walking all 27 taps for every voxel leaves 7/8 of the gathered rows (and MMAs) zero; per class
+// only (1+pd)(1+ph)(1+pw) taps exist - 27 over the 8 classes instead of 27 per voxel.
+// Class c = pd*4 + ph*2 + pw.  Stage offsets of the classes in the packed weights:
+__host__ __device__ __forceinline__ int cls_taps(int c) {
+  return (1 + ((c >> 2) & 1)) * (1 + ((c >> 1) & 1)) * (1 + (c & 1));
+}
+template <int TPS>
+__host__ __device__ __forceinline__ int cls_stages(int c) { return (cls_taps(c) + TPS - 1) / TPS; }
+template <int TPS>
+__host__ __device__ __forceinline__ int cls_stage_base(int c) {
+  int b = 0;
+  for (int i = 0; i < c; ++i) b += cls_stages<TPS>(i);
+  return b;
+}
+// slot-th tap of class c -> (kd, kh, kw) and the input offsets (+1 where k = 0)
+__host__ __device__ __forceinline__ void cls_tap(int c, int slot, int* kd, int* kh, int* kw,
+                                                 int* od, int* oh, int* ow) {
+  const int pd = (c >> 2) & 1, ph = (c >> 1) & 1, pw = c & 1;
+  const int aw = slot % (1 + pw); slot /= (1 + pw);
+  const int ah = slot % (1 + ph); slot /= (1 + ph);
+  const int ad = slot;
+  *kd = pd ? (ad ? 2 : 0) : 1; *od = (pd && !ad) ? 1 : 0;
+  *kh = ph ? (ah ? 2 : 0) : 1; *oh = (ph && !ah) ? 1 : 0;
+  *kw = pw ? (aw ? 2 : 0) : 1; *ow = (pw && !aw) ? 1 : 0;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -128,9 +160,11 @@ struct UmmaShape {
 
 // Wp[it][n/8][c][n%8][e] ; k = it*KS + c*4 + e -> (tap = k / CRED, cr = k % CRED)
 // rows n < NPROD: hi(W[prod = n][cr][tap]) ; rows n >= NPROD: lo(...)
+// bfs: 0 = reduce Cb (small-from-big), 1 = reduce Cs (big-from-small), 2 = big-from-small in
+// parity-class stage order (stride 2, see cls_tap)
 template <int CRED, int NPROD>
-__global__ void umma_pack_kernel(const float* __restrict__ w, int Cb, int bfs,
-                                 float* __restrict__ wp) {
+__device__ __forceinline__ void umma_pack_body(const float* __restrict__ w, int Cb, int bfs,
+                                               float* __restrict__ wp) {
   using US = UmmaShape<CRED, NPROD>;
   const int total = US::PACKED_FLOATS;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -142,7 +176,20 @@ __global__ void umma_pack_kernel(const float* __restrict__ w, int Cb, int bfs,
     const int it = r / (2 * NPROD / 8);
     const int n = nb * 8 + n8;
     const int kk = it * US::KS + c * 4 + e;
-    const int tap = kk / CRED, cr = kk % CRED;
+    int tap = kk / CRED;
+    const int cr = kk % CRED;
+    if (bfs == 2) {
+      // global stage `it` -> (class, local stage); slot = local stage * TPS + tap-in-stage
+      int cl = 0, base = 0;
+      while (cl < 7 && it >= base + cls_stages<US::TPS>(cl)) { base += cls_stages<US::TPS>(cl); ++cl; }
+      const int slot = (it - base) * US::TPS + (c * 4 + e) / CRED;
+      tap = 27;
+      if (it < base + cls_stages<US::TPS>(cl) && slot < cls_taps(cl)) {
+        int kd, kh, kw, o0, o1, o2;
+        cls_tap(cl, slot, &kd, &kh, &kw, &o0, &o1, &o2);
+        tap = (kd * 3 + kh) * 3 + kw;
+      }
+    }
     float v = 0.f;
     if (tap < 27) {
       const int prod = n % NPROD;
@@ -155,6 +202,29 @@ __global__ void umma_pack_kernel(const float* __restrict__ w, int Cb, int bfs,
     }
     wp[i] = v;
   }
+}
+
+template <int CRED, int NPROD>
+__global__ void umma_pack_kernel(const float* __restrict__ w, int Cb, int bfs,
+                                 float* __restrict__ wp) {
+  umma_pack_body<CRED, NPROD>(w, Cb, bfs, wp);
+}
+
+// all tcgen05 weight operands of a forward/backward in ONE launch (blockIdx.y = entry): they only
+// change in optimizer.step, and 38 separate 8-us pack launches per step were 0.3 ms of the graph
+constexpr int PACK_BATCH = 48;
+struct PackBatch {
+  const float* w[PACK_BATCH];
+  float* wp[PACK_BATCH];
+  unsigned char C[PACK_BATCH];
+  unsigned char bfs[PACK_BATCH];
+};
+__global__ void __launch_bounds__(256) umma_pack_batch_kernel(const __grid_constant__ PackBatch B) {
+  const int e = blockIdx.y;
+  const int Cc = B.C[e], bfs = B.bfs[e];
+  if (Cc == 16) umma_pack_body<16, 16>(B.w[e], 16, bfs, B.wp[e]);
+  else if (Cc == 32) umma_pack_body<32, 32>(B.w[e], 32, bfs, B.wp[e]);
+  else umma_pack_body<64, 64>(B.w[e], 64, bfs, B.wp[e]);
 }
 
 template <int CRED, int NPROD>
@@ -186,15 +256,26 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   const uint32_t tmem_base = *tmem_slot;
 
   // my output voxel (row m = tid of the 128-row tile)
-  const long long o = (long long)blockIdx.x * 128 + tid;
+  long long o = (long long)blockIdx.x * 128 + tid;
   const bool row_valid = o < A.nvox;
+  const int cl = A.cls ? (int)blockIdx.z : 0;
   int n = 0, od = 0, oh = 0, ow = 0;
   if (row_valid) {
     long long t = o;
-    ow = (int)(t % A.Wd); t /= A.Wd;
-    oh = (int)(t % A.Hd); t /= A.Hd;
-    od = (int)(t % A.Dd);
-    n = (int)(t / A.Dd);
+    if (A.cls) {
+      // row index inside the parity class -> output voxel 2*q + p
+      const int Wq = A.Wd >> 1, Hq = A.Hd >> 1, Dq = A.Dd >> 1;
+      ow = 2 * (int)(t % Wq) + (cl & 1); t /= Wq;
+      oh = 2 * (int)(t % Hq) + ((cl >> 1) & 1); t /= Hq;
+      od = 2 * (int)(t % Dq) + ((cl >> 2) & 1);
+      n = (int)(t / Dq);
+      o = (((long long)n * A.Dd + od) * A.Hd + oh) * A.Wd + ow;
+    } else {
+      ow = (int)(t % A.Wd); t /= A.Wd;
+      oh = (int)(t % A.Hd); t /= A.Hd;
+      od = (int)(t % A.Dd);
+      n = (int)(t / A.Dd);
+    }
   }
   const float* src_n = A.src + (long long)n * A.Dr * A.Hr * A.Wr * A.ldr;
   const uint32_t row_off = (uint32_t)((tid >> 3) * (KCH * 128) + (tid & 7) * 16);   // bytes
@@ -208,10 +289,16 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
 #pragma unroll
     for (int tp = 0; tp < US::TPS; ++tp) {
       const int tap = it * US::TPS + tp;
-      const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+      int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
       int id, ih, iw;
       bool ok = row_valid && tap < 27;
-      if (A.bfs) {
+      if (A.cls) {
+        // `it` is the class-local stage, tap its slot: every row of the tile has this tap
+        int o0, o1, o2;
+        ok = row_valid && tap < cls_taps(cl);
+        cls_tap(cl, ok ? tap : 0, &kd, &kh, &kw, &o0, &o1, &o2);
+        id = (od >> 1) + o0; ih = (oh >> 1) + o1; iw = (ow >> 1) + o2;
+      } else if (A.bfs) {
         const int nd = od + A.pad - kd * A.dil, nh = oh + A.pad - kh * A.dil,
                   nw = ow + A.pad - kw * A.dil;
         ok = ok && nd >= 0 && nh >= 0 && nw >= 0 && (nd % A.stride) == 0 &&
@@ -230,8 +317,10 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   };
   // split-K: this CTA reduces the K stages [it0, it1) (small problems have too few voxel tiles to
   // fill 148 SMs and would serialise 27 gather->MMA round trips per tile)
-  const int it0 = (int)((long long)blockIdx.y * NIT / A.splits);
-  const int it1 = (int)((long long)(blockIdx.y + 1) * NIT / A.splits);
+  const int nit = A.cls ? cls_stages<US::TPS>(cl) : NIT;
+  const int wbase = A.cls ? cls_stage_base<US::TPS>(cl) : 0;     // first packed stage of my class
+  const int it0 = (int)((long long)blockIdx.y * nit / A.splits);
+  const int it1 = (int)((long long)(blockIdx.y + 1) * nit / A.splits);
   gather(it0);
 
 #pragma unroll 1
@@ -246,7 +335,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
 
     // ---- B: packed weights of this stage (contiguous), asynchronous copy ----
     {
-      const float* g = A.wp + (long long)it * (US::B_BYTES / 4);
+      const float* g = A.wp + (long long)(wbase + it) * (US::B_BYTES / 4);
 #pragma unroll
       for (int i = tid; i < US::B_BYTES / 16; i += 128) cp_async16_u(b_sm + i * 16, g + i * 4);
       asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -356,7 +445,7 @@ static int launch_umma(const UmmaArgs& A, cudaStream_t st) {
     attr_done = true;
   }
   const unsigned blocks = (unsigned)((A.nvox + 127) / 128);
-  kern<<<dim3(blocks, (unsigned)A.splits), 128, US::SMEM, st>>>(A);
+  kern<<<dim3(blocks, (unsigned)A.splits, A.cls ? 8u : 1u), 128, US::SMEM, st>>>(A);
   return launched("umma_conv");
 }
 
@@ -368,6 +457,12 @@ static int launch_pack(const float* w, int Cb, int bfs, float* wp, cudaStream_t 
 }
 
 static bool umma_channels_ok(int c) { return c == 16 || c == 32 || c == 64; }
+
+// stride-2 transposed gather with even big extents: parity-class decomposition
+static bool umma_class_mode(const nas3d_conv_desc* d, int produce_big) {
+  return produce_big && d->k == 3 && d->stride == 2 && d->dil == 1 && d->pad == 1 &&
+         d->Db == 2 * d->Ds && d->Hb == 2 * d->Hs && d->Wb == 2 * d->Ws;
+}
 
 }  // namespace nas3d
 
@@ -385,16 +480,47 @@ long long nas3d_umma_packed_floats(const nas3d_conv_desc* d, int produce_big) {
   }
 }
 
+int nas3d_umma_pack_mode(const nas3d_conv_desc* d, int produce_big) {
+  if (!d || !produce_big) return 0;
+  return umma_class_mode(d, produce_big) ? 2 : 1;
+}
+
 int nas3d_umma_pack_weights(const nas3d_conv_desc* d, const float* w, int produce_big, float* packed,
                             void* stream) {
   NAS3D_REQUIRE(nas3d_umma_packed_floats(d, produce_big) > 0, "umma_pack: unsupported conv shape");
   NAS3D_REQUIRE(aligned16(packed), "umma_pack: packed buffer must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  const int mode = nas3d_umma_pack_mode(d, produce_big);
   switch (d->Cb) {
-    case 16: return launch_pack<16, 16>(w, d->Cb, produce_big, packed, st);
-    case 32: return launch_pack<32, 32>(w, d->Cb, produce_big, packed, st);
-    default: return launch_pack<64, 64>(w, d->Cb, produce_big, packed, st);
+    case 16: return launch_pack<16, 16>(w, d->Cb, mode, packed, st);
+    case 32: return launch_pack<32, 32>(w, d->Cb, mode, packed, st);
+    default: return launch_pack<64, 64>(w, d->Cb, mode, packed, st);
   }
+}
+
+int nas3d_umma_pack_weights_batch(int n, const int* channels, const int* modes,
+                                  const float* const* w, float* const* packed, void* stream) {
+  NAS3D_REQUIRE(n >= 0, "umma_pack_batch: n=%d", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < n; base += PACK_BATCH) {
+    const int m = n - base < PACK_BATCH ? n - base : PACK_BATCH;
+    PackBatch B;
+    memset(&B, 0, sizeof(B));
+    int cmax = 16;
+    for (int i = 0; i < m; ++i) {
+      const int c = channels[base + i], md = modes[base + i];
+      NAS3D_REQUIRE(umma_channels_ok(c) && md >= 0 && md <= 2, "umma_pack_batch: entry %d: C=%d mode=%d", base + i, c, md);
+      NAS3D_REQUIRE(aligned16(packed[base + i]), "umma_pack_batch: packed buffer must be 16B aligned");
+      B.w[i] = w[base + i]; B.wp[i] = packed[base + i];
+      B.C[i] = (unsigned char)c; B.bfs[i] = (unsigned char)md;
+      if (c > cmax) cmax = c;
+    }
+    const int gx = cmax == 16 ? 28 : cmax == 32 ? 108 : 216;   // ~2-4 grid-stride passes of the widest entry
+    umma_pack_batch_kernel<<<dim3(gx, m), 256, 0, st>>>(B);
+    int rc = launched("umma_pack_batch");
+    if (rc) return rc;
+  }
+  return NAS3D_OK;
 }
 
 int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
@@ -423,13 +549,15 @@ int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
   A.bfs = produce_big ? 1 : 0;
   A.accumulate = accumulate;
   A.nvox = (long long)d->N * A.Dd * A.Hd * A.Wd;
+  A.cls = umma_class_mode(d, produce_big) ? 1 : 0;
+  if (A.cls) A.nvox /= 8;                       // rows per parity class (gridDim.z = 8)
   const long long V = (long long)A.Dd * A.Hd * A.Wd;
   cudaStream_t st = (cudaStream_t)stream;
   // split-K when the voxel tiles alone cannot fill the machine (dense destination required)
   const long long tiles = (A.nvox + 127) / 128;
   const int Cprod = produce_big ? d->Cb : d->Cs;
   int splits = 1;
-  if (tiles < kNumSMs && A.ldd == Cprod) {
+  if (!A.cls && tiles < kNumSMs && A.ldd == Cprod) {
     splits = (int)(kNumSMs / tiles);
     if (splits > 9) splits = 9;
     if (splits < 1) splits = 1;
@@ -437,7 +565,7 @@ int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
   A.splits = splits;
   if (splits > 1 && !accumulate)
     NAS3D_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)A.nvox * Cprod, st));
-  const bool fuse = moments != nullptr && V % 128 == 0 && splits == 1;
+  const bool fuse = moments != nullptr && (A.cls ? (V / 8) % 128 == 0 : V % 128 == 0) && splits == 1;
   A.moments = fuse ? moments : nullptr;
   if (fuse)
     NAS3D_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * (size_t)d->N * (produce_big ? d->Cb : d->Cs), st));

@@ -686,7 +686,7 @@ def _umma_packed(ctx, d, m, produce_big):
     n = ctx.lib.nas3d_umma_packed_floats(C.byref(d), produce_big)
     if n <= 0 or not _umma_enabled(d):
         return None
-    key = (id(m.weight), produce_big)
+    key = (id(m.weight), produce_big, ctx.lib.nas3d_umma_pack_mode(C.byref(d), produce_big))
     wp = ctx.packed.get(key)
     if wp is None:
         wp = torch.empty(int(n), device=ctx.device, dtype=torch.float32)
@@ -694,6 +694,66 @@ def _umma_packed(ctx, d, m, produce_big):
                                               wp.data_ptr(), ctx.stream), "umma_pack_weights")
         ctx.packed[key] = wp
     return wp
+
+
+def _umma_prepack_list(module):
+    """(conv module, channels) of every conv under `module` that the tcgen05 path serves; cached on
+    the module (the structure of these networks is static)"""
+    lst = module.__dict__.get("_nas3d_umma_list")
+    if lst is None:
+        lst = []
+        for m in module.modules():
+            if not isinstance(m, (torch.nn.Conv3d, torch.nn.ConvTranspose3d)):
+                continue
+            if m.kernel_size != (3, 3, 3) or m.groups != 1 or m.in_channels != m.out_channels:
+                continue
+            d = ConvDesc()
+            d.Cb = d.Cs = m.in_channels
+            d.k, d.stride, d.dil, d.pad, d.depthwise = 3, m.stride[0], m.dilation[0], m.padding[0], 0
+            if d.Cb in (16, 32, 64) and len(set(m.stride)) == 1 and _umma_enabled(d):
+                lst.append(m)
+        module.__dict__["_nas3d_umma_list"] = lst
+    return lst
+
+
+def _prepack_umma(ctx, module):
+    """pack the weight operands of all tcgen05 convs of this module call in ONE launch (forward
+    direction, plus the dgrad direction when recording); conv() / _conv_bwd() find them in
+    ctx.packed.  The stride-2 transposed direction is packed in parity-class order, which the
+    kernel uses for even extents (always the case in these networks; otherwise _umma_packed
+    falls back to packing that operand on demand)."""
+    convs = _umma_prepack_list(module)
+    if not convs:
+        return
+    lib = ctx.lib
+    entries = []
+    for m in convs:
+        transposed = isinstance(m, torch.nn.ConvTranspose3d)
+        dirs = [1 if transposed else 0]
+        if ctx.record:
+            dirs.append(0 if transposed else 1)
+        for pb in dirs:
+            mode = 0 if not pb else (2 if (m.stride[0] == 2 and m.dilation[0] == 1 and m.padding[0] == 1) else 1)
+            entries.append((m, pb, mode))
+    d = ConvDesc()
+    d.k, d.depthwise = 3, 0
+    sizes = []
+    for m, pb, mode in entries:
+        d.Cb = d.Cs = m.in_channels
+        sizes.append(int(lib.nas3d_umma_packed_floats(C.byref(d), pb)))
+    arena = torch.empty(sum(sizes), device=ctx.device, dtype=torch.float32)
+    off = 0
+    ptrs = []
+    for (m, pb, mode), n in zip(entries, sizes):
+        t = arena[off:off + n]
+        off += n
+        ctx.packed[(id(m.weight), pb, mode)] = t
+        ptrs.append(t.data_ptr())
+    check(lib.nas3d_umma_pack_weights_batch(
+        len(entries), int_array([m.in_channels for m, _, _ in entries]),
+        int_array([mode for _, _, mode in entries]),
+        ptr_array([m.weight.data_ptr() for m, _, _ in entries]), ptr_array(ptrs), ctx.stream),
+        "umma_pack_weights_batch")
 
 
 def conv(ctx, x, m, spec, in_relu=False, in_scale=None, sigmoid=False, stats=False):
@@ -904,6 +964,7 @@ class _ModuleFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             acts = [as_act(t, bool(record and t.requires_grad)) for t in acts_t]
             extras = [Alpha(t) for t in extras_t]
+            _prepack_umma(ctx, module)
             out = module._run(ctx, *acts, *extras)
             if isinstance(out, Term):
                 out = materialize(ctx, out)

@@ -42,7 +42,7 @@ def _work(name, args):
     if name == "nas3d_umma_conv":
         b, f, tag = _conv_work(args[0])
         return b, f, tag + (" umma-T" if args[1] else " umma")
-    if name == "nas3d_umma_pack_weights":
+    if name in ("nas3d_umma_pack_weights", "nas3d_umma_pack_weights_batch"):
         return 0.0, 0.0, "pack"
     if name == "nas3d_affine_sum_fwd":
         n, N, V, Cc = args[0], args[9], args[10], args[11]
@@ -91,7 +91,8 @@ class ProfiledLib:
         fn = getattr(self._lib, name)
         if not name.startswith("nas3d_") or name in ("nas3d_last_error", "nas3d_version",
                                                        "nas3d_launch_count",
-                                                       "nas3d_umma_packed_floats"):
+                                                       "nas3d_umma_packed_floats",
+                                                       "nas3d_umma_pack_mode"):
             return fn
 
         def wrapped(*args):

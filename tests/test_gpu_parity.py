@@ -283,6 +283,40 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
         assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
 
 
+def test_tcgen05_stride2_dgrad_on_odd_extents_uses_tap_order():
+    """odd input extents (Db != 2*Ds): the stride-2 dgrad cannot use the parity-class
+    decomposition; the pre-packed class-order operand must be ignored and the tap-order one
+    packed on demand"""
+    import os
+    from nas_3d_unet_b200.prim_ops import ConvOps
+    torch.manual_seed(11)
+    c = 16
+    op = ConvOps(c, c, stride=2, dilation=1, transposed=False, ops_order='weight')
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, c, 7, 9, 11, generator=g) * 2.0
+    sd = O.leaf_state(op.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = O.conv_ops(sd, '', xr, 3, 2, 1, False, order='weight')
+    r = torch.randn(yr.shape, generator=g)
+    (yr * r).sum().backward()
+    op = op.cuda()
+    from nas_3d_unet_b200 import profiling
+    os.environ["NAS3D_UMMA_MIN_C"] = "16"
+    prof = profiling.enable()
+    try:
+        xg = x.cuda().requires_grad_(True)
+        y = op(xg)
+        (y * r.cuda()).sum().backward()
+        names = [rec[0] for rec in prof.records]
+    finally:
+        profiling.disable()
+        os.environ.pop("NAS3D_UMMA_MIN_C", None)
+    assert names.count("nas3d_umma_conv") == 2, names
+    assert "nas3d_umma_pack_weights" in names and "nas3d_umma_pack_weights_batch" in names, names
+    assert O.max_rel(y, yr) <= 2e-5
+    assert O.max_rel(xg.grad, xr.grad) <= 2e-5
+
+
 @pytest.mark.parametrize("cin,cout,transposed", [(4, 4, False), (8, 8, False), (4, 12, False),
                                                  (4, 4, True), (8, 8, True)])
 def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
