@@ -448,7 +448,8 @@ static void launch_pointwise_co(const PwArgs& A, unsigned gy, cudaStream_t st) {
   // small (deep-level) tensors: 1 voxel per thread, one tile per CTA - they are latency-bound
   if (pointwise_big(nvox)) {
     static const int vpt_sfb = pw_env("NAS3D_PW_VPT_SFB", 4), vpt_bfs = pw_env("NAS3D_PW_VPT_BFS", 2);
-    const int vpt = MOM ? 4 : (SRC_IS_BIG ? vpt_sfb : vpt_bfs);
+    static const int vpt_mom = pw_env("NAS3D_PW_VPT_MOM", 2);
+    const int vpt = MOM ? vpt_mom : (SRC_IS_BIG ? vpt_sfb : vpt_bfs);
     if (vpt == 1) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 1>(A, gy, nvox, st);
     else if (vpt == 2) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 2>(A, gy, nvox, st);
     else launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 4>(A, gy, nvox, st);

@@ -107,37 +107,66 @@ __global__ void __launch_bounds__(RB)
 #pragma unroll
       for (int e = 0; e < 4; ++e) r1[t][u][e] = r2[t][u][e] = 0.f;
 
-#pragma unroll 2
-  for (int it = 0; it < iters; ++it) {
-    long long j = j0 + (long long)it * RB;
-    if (j >= total) break;
-    const long long vox = j >> logP;
+  // Two voxels per thread per trip, all their dout / x_k loads issued before the first use
+  // (predicated, no early exit in the body): twice the bytes in flight per thread.
+  const float* xb[TG];
+  float4 a4[TG][U], b4[TG][U];
+  bool live[TG], relu[TG];
+#pragma unroll
+  for (int t = 0; t < TG; ++t) {
+    const int k = k0 + t;
+    live[t] = k < T.nterms;
+    relu[t] = live[t] && T.relu[k];
+    xb[t] = live[t] ? T.x[k] + (long long)n * V * T.ld[k] + cbase : nullptr;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const float4 d4 = ldg4(db + vox * ld_dout + u * 4);
-      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+      a4[t][u] = make_float4(1.f, 1.f, 1.f, 1.f);
+      b4[t][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (relu[t] && T.a[k]) a4[t][u] = ldg4(T.a[k] + (long long)n * C + cbase + u * 4);
+      if (relu[t] && T.b[k]) b4[t][u] = ldg4(T.b[k] + (long long)n * C + cbase + u * 4);
+    }
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; it += 2) {
+    const long long ja = j0 + (long long)it * RB, jb = ja + RB;
+    const bool va = ja < total, vb = (it + 1 < iters) && jb < total;
+    if (!va) break;
+    const long long voxa = ja >> logP, voxb = vb ? (jb >> logP) : voxa;
+    float4 da[U], dbv[U], xa[TG][U], xbv[TG][U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      da[u] = ldg4(db + voxa * ld_dout + u * 4);
+      dbv[u] = ldg4(db + voxb * ld_dout + u * 4);
 #pragma unroll
       for (int t = 0; t < TG; ++t) {
-        const int k = k0 + t;
-        if (k < T.nterms) {
-          const float4 x4 = ldg4(T.x[k] + ((long long)n * V + vox) * T.ld[k] + cbase + u * 4);
-          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-          float m[4] = {1.f, 1.f, 1.f, 1.f};
-          if (T.relu[k]) {
-            float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (T.a[k]) a4 = ldg4(T.a[k] + (long long)n * C + cbase + u * 4);
-            if (T.b[k]) b4 = ldg4(T.b[k] + (long long)n * C + cbase + u * 4);
-            m[0] = (a4.x * xv[0] + b4.x > 0.f) ? 1.f : 0.f;
-            m[1] = (a4.y * xv[1] + b4.y > 0.f) ? 1.f : 0.f;
-            m[2] = (a4.z * xv[2] + b4.z > 0.f) ? 1.f : 0.f;
-            m[3] = (a4.w * xv[3] + b4.w > 0.f) ? 1.f : 0.f;
-          }
+        xa[t][u] = xbv[t][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[t]) {
+          const int ldk = T.ld[k0 + t];
+          xa[t][u] = ldg4(xb[t] + voxa * ldk + u * 4);
+          xbv[t][u] = ldg4(xb[t] + voxb * ldk + u * 4);
+        }
+      }
+    }
+    const float wb = vb ? 1.f : 0.f;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float md = m[e] * d[e];
-            r1[t][u][e] += md;
-            r2[t][u][e] += md * xv[e];
-          }
+    for (int u = 0; u < U; ++u) {
+      const float d0[4] = {da[u].x, da[u].y, da[u].z, da[u].w};
+      const float d1[4] = {dbv[u].x * wb, dbv[u].y * wb, dbv[u].z * wb, dbv[u].w * wb};
+#pragma unroll
+      for (int t = 0; t < TG; ++t) {
+        if (!live[t]) continue;
+        const float x0[4] = {xa[t][u].x, xa[t][u].y, xa[t][u].z, xa[t][u].w};
+        const float x1[4] = {xbv[t][u].x, xbv[t][u].y, xbv[t][u].z, xbv[t][u].w};
+        const float av[4] = {a4[t][u].x, a4[t][u].y, a4[t][u].z, a4[t][u].w};
+        const float bv[4] = {b4[t][u].x, b4[t][u].y, b4[t][u].z, b4[t][u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float m0 = (!relu[t] || av[e] * x0[e] + bv[e] > 0.f) ? d0[e] : 0.f;
+          const float m1 = (!relu[t] || av[e] * x1[e] + bv[e] > 0.f) ? d1[e] : 0.f;
+          r1[t][u][e] += m0;
+          r2[t][u][e] += m0 * x0[e];
+          r1[t][u][e] += m1;
+          r2[t][u][e] += m1 * x1[e];
         }
       }
     }

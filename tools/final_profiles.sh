@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence run on ONE B200: tests, bench lines of every config, ncu launch list and
 # full captures of the dominant kernels.  Outputs land in gpurun_out/ (copied to profiles/ here).
-TAG=${1:-r1d}
+TAG=${1:-r1e}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
 timeout 900 python bench.py --steps 20 --warmup 5 --profile-out gpurun_out/${TAG}_kernels_per_shape.json > gpurun_out/${TAG}_bench_searched128_b8_n1.json 2> gpurun_out/${TAG}_bench.err
