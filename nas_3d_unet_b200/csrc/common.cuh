@@ -49,13 +49,15 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// Packed fp32 FMA (sm_100 FFMA2): one issue slot and one FMA-pipe pass for TWO fused
-// multiply-adds.  A 3-register scalar FFMA issues every other cycle per SM sub-partition on
-// Blackwell, so the FFMA-bound convolution kernels only reach the 128 FMA/clk/SM fp32 peak
-// through this form.  ptxas folds the {s,s} operand into the instruction's scalar-broadcast
-// modifier (FFMA2 Rd, Rs.F32, Rw.F32x2.HI_LO, Rd.F32x2.HI_LO) - no extra MOV.  Each half is an
-// IEEE fma.rn, so results are bit-identical to two fmaf() in the same order.
-// Build with -DNAS3D_NO_FFMA2 to fall back to scalar FFMA (A/B measurements).
+// Packed fp32 FMA (sm_100 FFMA2, PTX fma.rn.f32x2): TWO fused multiply-adds per issued
+// instruction.  Measured on B200 (tools/micro/fma_patterns.cu, profiles/r1e_fma_patterns_micro.jsonl):
+// with the operand patterns of these kernels both forms sustain the same 58-61 TFLOP/s
+// (~100 of 128 FMA/clk/SM), so the gain is in ISSUE SLOTS, not pipe throughput: the loads and
+// address arithmetic of the conv loops now share the scheduler with half as many FMA
+// instructions (+10 % on the fwd / dgrad kernels).  ptxas folds the {s,s} operand into the
+// instruction's scalar-broadcast modifier (FFMA2 Rd, Rs.F32, Rw.F32x2.HI_LO, Rd.F32x2.HI_LO),
+// no extra MOV.  Each half is an IEEE fma.rn, so results are bit-identical to two fmaf() in the
+// same order.  Build with -DNAS3D_NO_FFMA2 for the scalar form (A/B measurements).
 __device__ __forceinline__ void fma2(float2& d, float s, float wx, float wy) {
 #ifndef NAS3D_NO_FFMA2
   asm("{\n\t"
@@ -120,6 +122,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Warp "reduce-scatter" of N per-lane values (N a multiple of 32): on return lane l holds in
+// v[0 .. N/32) the warp totals of the original v[l*(N/32) + j].  Each of the 5 butterfly rounds
+// exchanges only the half a lane does not keep: N*(31/32) shuffles in total instead of 5*N for N
+// separate all-reduces.
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N]) {
+  static_assert(N % 32 == 0, "warp_reduce_scatter: N must be a multiple of 32");
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int o = 16 >> r;
+    const int n = N >> (r + 1);
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
 }
 
 // Fused GroupNorm statistics for conv epilogues: a warp whose 32 lanes hold values of the SAME 4

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(PW_T, NAS3D_PW_MINB) pointwise_kernel(const __
 
 // wgrad: thread register tile TS x TB over (small channels, big channels)
 constexpr int PWG_T = 256;
-constexpr int PWG_ITER = 32;
+constexpr int PWG_ITER = 128;   // voxels per thread before the 5-round warp reduction of its tile
 
 template <int TS, int TB>
 __global__ void __launch_bounds__(PWG_T)
@@ -321,18 +321,21 @@ __global__ void __launch_bounds__(PWG_T)
     for (int j = 0; j < TB / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
   }
   const bool do_bias = dbias_small != nullptr && blockIdx.z == 0;
+  const bool need_decomp = A.stride != 1 || A.scale != nullptr;    // host guarantees nvox < 2^31
 #pragma unroll 2
   for (int it = 0; it < iters; ++it) {
     const long long o = ((long long)blockIdx.x * iters + it) * PWG_T + threadIdx.x;
     if (o >= nvox) break;
     long long bidx = o;
-    int n;
-    {
-      long long t = o;
-      const int ow = (int)(t % A.Ws); t /= A.Ws;
-      const int oh = (int)(t % A.Hs); t /= A.Hs;
-      const int od = (int)(t % A.Ds);
-      n = (int)(t / A.Ds);
+    int n = 0;
+    if (need_decomp) {
+      // 32-bit voxel decomposition, only where the sample / big-lattice index is needed at all
+      // (the 64-bit div/mod chain cost more instructions than the FMAs of the voxel)
+      unsigned t = (unsigned)o;
+      const unsigned ow = t % (unsigned)A.Ws; t /= (unsigned)A.Ws;
+      const unsigned oh = t % (unsigned)A.Hs; t /= (unsigned)A.Hs;
+      const unsigned od = t % (unsigned)A.Ds;
+      n = (int)(t / (unsigned)A.Ds);
       if (A.stride != 1)
         bidx = (((long long)n * A.Db + od * A.stride) * A.Hb + oh * A.stride) * A.Wb + ow * A.stride;
     }
@@ -386,17 +389,23 @@ __global__ void __launch_bounds__(PWG_T)
       for (int j = 0; j < TB / 2; ++j) fma2(acc[i][j], sv[i], bv[2 * j], bv[2 * j + 1]);
     }
   }
-  __shared__ float red[PWG_T / 32][TS * TB + TS];
+  // warp totals of the TS*TB products and TS bias sums with one transposing butterfly
+  constexpr int NV = TS * TB + TS, NVP = (NV + 31) / 32 * 32, PER = NVP / 32;
+  __shared__ float red[PWG_T / 32][NVP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  {
+    float vals[NVP];
 #pragma unroll
-  for (int i = 0; i < TS; ++i) {
+    for (int i = 0; i < TS; ++i) {
 #pragma unroll
-    for (int j = 0; j < TB; ++j) {
-      const float v = warp_sum((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x);
-      if (lane == 0) red[wid][i * TB + j] = v;
+      for (int j = 0; j < TB; ++j) vals[i * TB + j] = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
+      vals[TS * TB + i] = bs[i];
     }
-    const float b = warp_sum(bs[i]);
-    if (lane == 0) red[wid][TS * TB + i] = b;
+#pragma unroll
+    for (int i = NV; i < NVP; ++i) vals[i] = 0.f;
+    warp_reduce_scatter<NVP>(vals);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) red[wid][lane * PER + j] = vals[j];
   }
   __syncthreads();
   for (int e = threadIdx.x; e < TS * TB + TS; e += PWG_T) {
@@ -567,6 +576,7 @@ int pointwise_wgrad(const nas3d_conv_desc* d, const float* small, const float* b
   A.N = d->N; A.Ds = d->Ds; A.Hs = d->Hs; A.Ws = d->Ws; A.Db = d->Db; A.Hb = d->Hb; A.Wb = d->Wb;
   A.stride = d->stride; A.relu = relu; A.scale = scale;
   const long long nvox = (long long)d->N * d->Ds * d->Hs * d->Ws;
+  if (nvox >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;   // 32-bit voxel indices
   const int Cs = d->Cs, Cb = d->Cb;
   // register tile over (small, big) channels: cover the whole matrix when it is small so each
   // tensor is read once; voxels per thread shrink for small (deep-level) tensors so that at least
