@@ -322,10 +322,13 @@ __global__ void __launch_bounds__(PWG_T)
   }
   const bool do_bias = dbias_small != nullptr && blockIdx.z == 0;
   const bool need_decomp = A.stride != 1 || A.scale != nullptr;    // host guarantees nvox < 2^31
-#pragma unroll 2
-  for (int it = 0; it < iters; ++it) {
-    const long long o = ((long long)blockIdx.x * iters + it) * PWG_T + threadIdx.x;
-    if (o >= nvox) break;
+  // trip count known up front (no early exit in the body), so the loads of the next voxels can
+  // be hoisted above the FMAs of the current one
+  const long long o0 = (long long)blockIdx.x * iters * PWG_T + threadIdx.x;
+  const int my_iters = o0 < nvox ? (int)min((long long)iters, (nvox - o0 + PWG_T - 1) / PWG_T) : 0;
+#pragma unroll 4
+  for (int it = 0; it < my_iters; ++it) {
+    const long long o = o0 + (long long)it * PWG_T;
     long long bidx = o;
     int n = 0;
     if (need_decomp) {
