@@ -516,6 +516,9 @@ def roofline_pass(step, profiling, args):
         "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac,
         "peak_source": peaks["src"], "traffic": ncu_traffic(top["kernel"], top["shape"]),
         "share_of_step": top["ms"] / total_ms if total_ms else None,
+        # all shapes of the same kernel: the figure the ncu launch list (profiles/*_ncu_launch_summary.csv)
+        # reports for this kernel name
+        "kernel_share_of_step": by_kernel[top["kernel"]]["ms"] / total_ms if total_ms else None,
         "avg_launch_ms": top["ms"] / top["launches"],
         "achieved_tflops": ach_tf, "fp32_ffma_peak_tflops": fp32_tflops,
         "frac_of_fp32_ffma": ach_tf / fp32_tflops,

@@ -116,6 +116,25 @@ int nas3d_conv1x1_cat_wgrad(const nas3d_conv_desc* d, int nparts, const float* c
                             const int* part_ld, const float* small, const float* big_scale,
                             int big_relu, float* dW, float* d_bias_small, void* stream);
 
+/* Fused backward of a dense 1x1x1 STRIDE-1 convolution (the cell preprocess convs cell.py:47-50,
+ * separable pointwise convs prim_ops.py:97-98, the head nas.py:50-52): in one pass over memory
+ *   dbig[v,cb] (+)= big_scale[n,cb] * (big[v,cb] > 0 if big_relu) * sum_cs ds[v,cs] * W[cs][cb]
+ *   dW[cs][cb]  += sum_v ds[v,cs] * f(big[v,cb])       (f = relu and/or scale, as in the forward)
+ *   d_bias_small[cs] += sum_v ds[v,cs]                  (if non-NULL)
+ * with ds = dsmall, or ds = dsmall * prob * (1 - prob) when small_prob (the sigmoid output of
+ * this conv, same layout as dsmall) is given - the backward of nn.Sigmoid (nas.py:52) folded in.
+ * It replaces the pair nas3d_conv1x1_cat_dgrad / nas3d_conv_big_from_small + nas3d_conv1x1_cat_wgrad
+ * / nas3d_conv_wgrad (+ nas3d_sigmoid_bwd), which read dsmall and big twice.  big is nparts
+ * (1..4) dense parts of Cb/nparts channels (nparts = 1: an ordinary tensor with pitch part_ld[0]);
+ * dbig_parts NULL (or dbig_parts[0] NULL) = weight/bias gradients only.  Covered: Cs <= 8,
+ * Cb <= 64 with Cb/4 dividing 192; nas3d_conv1x1_bwd_fused_supported() tells (1/0). */
+int nas3d_conv1x1_bwd_fused_supported(const nas3d_conv_desc* d, int nparts);
+int nas3d_conv1x1_bwd_fused(const nas3d_conv_desc* d, int nparts, const float* const* big_parts,
+                            const int* part_ld, float* const* dbig_parts, const int* dpart_ld,
+                            const int* accumulate, const float* dsmall, const float* small_prob,
+                            const float* w, const float* big_scale, int big_relu, float* dW,
+                            float* d_bias_small, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Tensor-core path (tcgen05.mma kind::tf32, fp32 accumulators in TMEM, 3xTF32 error
  * compensation => fp32-grade results) for dense 3x3x3 convolutions with Cb == Cs in {16,32,64},

@@ -46,6 +46,9 @@ _SIGNATURES = {
                                 c_vp],
     "nas3d_conv1x1_cat_wgrad": [C.POINTER(ConvDesc), c_int, _PP, _PI, c_vp, c_vp, c_int, c_vp, c_vp,
                                 c_vp],
+    "nas3d_conv1x1_bwd_fused_supported": [C.POINTER(ConvDesc), c_int],
+    "nas3d_conv1x1_bwd_fused": [C.POINTER(ConvDesc), c_int, _PP, _PI, _PP, _PI, _PI, c_vp, c_vp, c_vp,
+                                c_vp, c_int, c_vp, c_vp, c_vp],
     "nas3d_umma_packed_floats": [C.POINTER(ConvDesc), c_int],
     "nas3d_umma_pack_weights": [C.POINTER(ConvDesc), c_vp, c_int, c_vp, c_vp],
     "nas3d_umma_pack_mode": [C.POINTER(ConvDesc), c_int],

@@ -841,6 +841,8 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
             return
         st = ctx.stream
         dy_t = y.g
+        if spec.stride == 1 and _pw_bwd_fused(ctx, d, parts, y, m, in_relu, in_scale, sigmoid):
+            return
         if sigmoid:
             dl = torch.empty_like(dy_t)
             check(lib.nas3d_sigmoid_bwd(y.ptr, dy_t.data_ptr(), dl.data_ptr(), y.N * y.V * y.C, st),
@@ -873,12 +875,57 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
     return y
 
 
+def fused_pw_bwd_enabled():
+    """1x1x1 stride-1 convs: dgrad + wgrad (+ sigmoid backward) in one pass (NAS3D_PW_FUSED_BWD=0:
+    the separate kernels)"""
+    return os.environ.get("NAS3D_PW_FUSED_BWD", "1") != "0"
+
+
+def _pw_bwd_fused(ctx, d, parts, y, m, in_relu, in_scale, sigmoid):
+    """backward of a dense 1x1x1 stride-1 conv y = conv(f(cat(parts))) through
+    nas3d_conv1x1_bwd_fused; returns False when the shape is not covered (caller falls back)"""
+    lib = ctx.lib
+    if not fused_pw_bwd_enabled() or not lib.nas3d_conv1x1_bwd_fused_supported(C.byref(d), len(parts)):
+        return False
+    dy_t = y.g
+    ld_dy = _ndhwc_pitch(dy_t)
+    if ld_dy != d.ld_small or dy_t.data_ptr() % 16:
+        return False
+    live = [p for p in parts if p.requires_grad]
+    if live and len(live) != len(parts):
+        return False
+    if any(p.ld % 4 or p.ptr % 16 for p in parts):
+        return False
+    gs = lds = accs = None
+    if live:
+        gs, accs = [], []
+        for p in parts:
+            g, acc = p.grad_slot()
+            gs.append(g)
+            accs.append(acc)
+        lds = [_ndhwc_pitch(g) for g in gs]
+        if any(l is None or l % 4 or g.data_ptr() % 16 for l, g in zip(lds, gs)):
+            raise Nas3dDeviceError("gradient buffer of a 1x1 conv input is not a dense NDHWC tensor")
+    db = ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None
+    check(lib.nas3d_conv1x1_bwd_fused(
+        C.byref(d), len(parts), ptr_array([p.ptr for p in parts]), int_array([p.ld for p in parts]),
+        ptr_array([g.data_ptr() for g in gs]) if gs else None, int_array(lds) if gs else None,
+        int_array(accs) if gs else None, dy_t.data_ptr(), y.ptr if sigmoid else None,
+        m.weight.data_ptr(), _tp(in_scale), 1 if in_relu else 0, ctx.gptr(m.weight), db,
+        ctx.stream), "conv1x1_bwd_fused")
+    return True
+
+
 def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
     if y.g is None:
         return
     lib = ctx.lib
     st = ctx.stream
     dy_t = y.g
+    if (spec.k == 1 and spec.stride == 1 and not spec.transposed and not spec.depthwise
+            and x.requires_grad and _pw_bwd_fused(ctx, _desc(spec, x, y), [x], y, m, in_relu,
+                                                  in_scale, sigmoid)):
+        return
     if sigmoid:
         # y holds probabilities; dlogit = dprob * p * (1-p)   (nn.Sigmoid, nas.py:52)
         dl = torch.empty_like(dy_t)

@@ -36,6 +36,13 @@ def _work(name, args):
     """(algorithmic bytes, flops, tag) of one call"""
     if name in ("nas3d_conv_small_from_big", "nas3d_conv_big_from_small", "nas3d_conv_wgrad"):
         return _conv_work(args[0])
+    if name == "nas3d_conv1x1_bwd_fused":
+        # reads dsmall + big once, writes dbig: the fused pair does the flops of dgrad AND wgrad
+        d = args[0]._obj if hasattr(args[0], "_obj") else args[0]
+        b, f, tag = _conv_work(d)
+        vb = d.N * d.Db * d.Hb * d.Wb
+        has_dx = bool(args[4])
+        return b + (4.0 * vb * d.Cb if has_dx else 0.0), f * (2 if has_dx else 1), tag + " bwd-fused"
     if name.startswith("nas3d_conv1x1_cat_"):
         b, f, tag = _conv_work(args[0])
         return b, f, tag + " cat"
@@ -92,7 +99,8 @@ class ProfiledLib:
         if not name.startswith("nas3d_") or name in ("nas3d_last_error", "nas3d_version",
                                                        "nas3d_launch_count",
                                                        "nas3d_umma_packed_floats",
-                                                       "nas3d_umma_pack_mode"):
+                                                       "nas3d_umma_pack_mode",
+                                                       "nas3d_conv1x1_bwd_fused_supported"):
             return fn
 
         def wrapped(*args):

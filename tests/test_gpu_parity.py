@@ -430,3 +430,97 @@ def test_dice_accepts_int8_masks():
         out.backward()
         assert abs(out.item() - ref.item()) <= 1e-6
         assert rel_err(pg.grad.cpu().numpy(), pr.grad.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("cb,cs,nparts,relu,scale,sigmoid,acc,want_dx", [
+    (12, 4, 1, True, False, False, False, True),     # cell preprocess0 of the top up cell
+    (12, 3, 3, False, True, True, False, True),      # the head: virtual concat, Dropout3d scale, sigmoid
+    (24, 4, 3, True, False, False, True, True),      # preprocess over a concat, accumulating
+    (12, 8, 1, True, False, False, False, True),
+    (4, 4, 1, False, False, False, True, True),      # separable pointwise conv (thread per voxel)
+    (48, 8, 3, True, True, False, False, True),
+    (12, 8, 3, False, False, False, False, False),   # weight / bias gradients only
+])
+def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sigmoid, acc, want_dx):
+    """nas3d_conv1x1_bwd_fused (dgrad + wgrad + bias grad + sigmoid backward in one pass) through
+    the C-ABI against the same op written with torch in fp64, on a ragged voxel count with pitched
+    parts; tolerance 1e-5 (fp32 sums of ~1e3 terms)"""
+    import ctypes as C
+    from nas_3d_unet_b200 import _lib
+    from nas_3d_unet_b200._lib import ConvDesc, check, int_array, ptr_array
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(cb * 7 + cs)
+    N, D, H, W = 2, 5, 9, 11
+    nv = N * D * H * W
+    sw = cb // nparts
+    pitch = sw + 4      # parts are channel slices of wider buffers
+    parts = [torch.randn(nv, pitch, generator=g).to(dev) for _ in range(nparts)]
+    x = torch.cat([p[:, :sw] for p in parts], 1).double()
+    lds = cs if cs % 4 else cs + 4
+    dy_buf = torch.randn(nv, lds, generator=g).to(dev)
+    prob_buf = torch.rand(nv, lds, generator=g).to(dev)
+    Wt = torch.randn(cs, cb, generator=g).to(dev)
+    sc = (torch.rand(N, cb, generator=g) * 2).to(dev) if scale else None
+    dparts = [torch.randn(nv, pitch, generator=g).to(dev) for _ in range(nparts)]
+    dparts0 = [t.clone() for t in dparts]
+    dW = torch.zeros(cs, cb, device=dev)
+    db = torch.zeros(cs, device=dev)
+
+    d = ConvDesc()
+    d.N, d.Db, d.Hb, d.Wb, d.Cb, d.ld_big = N, D, H, W, cb, pitch
+    d.Ds, d.Hs, d.Ws, d.Cs, d.ld_small = D, H, W, cs, lds
+    d.k, d.stride, d.dil, d.pad, d.depthwise = 1, 1, 1, 0, 0
+    assert lib.nas3d_conv1x1_bwd_fused_supported(C.byref(d), nparts) == 1
+    check(lib.nas3d_conv1x1_bwd_fused(
+        C.byref(d), nparts, ptr_array([p.data_ptr() for p in parts]), int_array([pitch] * nparts),
+        ptr_array([t.data_ptr() for t in dparts]) if want_dx else None,
+        int_array([pitch] * nparts) if want_dx else None,
+        int_array([1 if acc else 0] * nparts) if want_dx else None,
+        dy_buf.data_ptr(), prob_buf.data_ptr() if sigmoid else None, Wt.data_ptr(),
+        sc.data_ptr() if scale else None, 1 if relu else 0, dW.data_ptr(), db.data_ptr(),
+        torch.cuda.current_stream().cuda_stream), "conv1x1_bwd_fused")
+    torch.cuda.synchronize()
+
+    ds = dy_buf[:, :cs].double()
+    if sigmoid:
+        p = prob_buf[:, :cs].double()
+        ds = ds * p * (1 - p)
+    scv = sc.double().repeat_interleave(D * H * W, 0) if scale else torch.ones(nv, cb, device=dev, dtype=torch.float64)
+    xf = (x.clamp_min(0) if relu else x) * scv
+    dW_ref = ds.t() @ xf
+    db_ref = ds.sum(0)
+    dx_ref = (ds @ Wt.double()) * scv
+    if relu:
+        dx_ref = dx_ref * (x > 0)
+    assert O.max_rel(dW, dW_ref) <= 1e-5
+    assert O.max_rel(db, db_ref) <= 1e-5
+    for j in range(nparts):
+        ref = dx_ref[:, j * sw:(j + 1) * sw]
+        if not want_dx:
+            assert torch.equal(dparts[j], dparts0[j])
+            continue
+        if acc:
+            ref = ref + dparts0[j][:, :sw].double()
+        assert O.max_rel(dparts[j][:, :sw], ref) <= 1e-5
+        assert torch.equal(dparts[j][:, sw:], dparts0[j][:, sw:])     # slice neighbours untouched
+
+
+def test_fused_pointwise_backward_equals_separate_kernels_in_the_net():
+    """searched-net gradients with the fused 1x1 backward on and off (NAS3D_PW_FUSED_BWD)"""
+    import os
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    x, y = O.synthetic_batch(1, 32, seed=3)
+    grads = {}
+    for mode in ("1", "0"):
+        os.environ["NAS3D_PW_FUSED_BWD"] = mode
+        try:
+            model = make_searched().cuda()
+            model.train()
+            torch.manual_seed(11)
+            loss = WeightedDiceLoss()(model(x.cuda()), y.cuda())
+            loss.backward()
+            grads[mode] = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        finally:
+            os.environ["NAS3D_PW_FUSED_BWD"] = "1"
+    assert O.max_rel(grads["1"], grads["0"]) <= 1e-5

@@ -11,7 +11,9 @@ WANT = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pipe_pct"),
-    ("sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+    ("sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+     "tcgen05_tf32_ops_pct_of_peak"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"), ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
     ("smsp__inst_executed.sum", "instructions"),
@@ -24,9 +26,6 @@ def main():
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     cols = [(h, n) for h, n in WANT if h in idx]
-    tens = [h for h in hdr if "pipe_tensor" in h and h.endswith("pct_of_peak_sustained_active")]
-    if tens and not any(h == tens[0] for h, _ in cols):
-        cols.append((tens[0], "tensor_pipe_pct"))
     w = csv.writer(sys.stdout)
     w.writerow([n for _, n in cols])
     for r in rows[2:]:
