@@ -244,6 +244,34 @@ int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_
                                const float* dout, int ld_dout, int N, long long V, int C,
                                void* stream);
 
+/* The two passes above with the GroupNorm coefficient kernels of their terms FOLDED IN (one launch
+ * instead of two on the critical path of every cell node; the coefficient math is a few hundred
+ * flops per sample, done by every CTA in its prologue):
+ *   nas3d_affine_sum_fwd_gn: for a term k with gn_S[k] != NULL, a[k] / b[k] / gn_mean_rstd[k] are
+ *     OUTPUTS computed as by nas3d_gn_coef from the moments gn_S[k] ([N,C,2] fp64), gn_gamma[k],
+ *     gn_beta[k] (G groups, eps) and then used; other terms behave as in nas3d_affine_sum_fwd.
+ *   nas3d_affine_sum_bwd_apply_gn: for a term k with gn_R[k] != NULL, p[k] / q[k] / r[k] ([N,C]
+ *     fp32 scratch) are computed as by nas3d_gn_bwd_coef from gn_R[k] (the output of
+ *     nas3d_affine_sum_bwd_reduce), gn_mean_rstd[k], gn_gamma[k], a[k], b[k], w[k], and
+ *     gn_dgamma[k] / gn_dbeta[k] / gn_dw[k] (d alpha, may be NULL) / gn_dbias_prev[k] (with
+ *     gn_S[k]; may be NULL) are accumulated exactly once. */
+int nas3d_affine_sum_fwd_gn(int nterms, const float* const* x, const int* ld_x,
+                            float* const* a, float* const* b, const float* const* w,
+                            const int* relu, const double* const* gn_S,
+                            const float* const* gn_gamma, const float* const* gn_beta,
+                            float* const* gn_mean_rstd, int G, float eps, float* out, int ld_out,
+                            int N, long long V, int C, void* stream);
+int nas3d_affine_sum_bwd_apply_gn(int nterms, const float* const* x, const int* ld_x,
+                                  const float* const* a, const float* const* b, const int* relu,
+                                  float* const* p, float* const* q, float* const* r,
+                                  const float* const* w, float* const* dx, const int* ld_dx,
+                                  const int* accumulate, const float* dout, int ld_dout,
+                                  const double* const* gn_R, const float* const* gn_mean_rstd,
+                                  const float* const* gn_gamma, float* const* gn_dgamma,
+                                  float* const* gn_dbeta, float* const* gn_dw,
+                                  const double* const* gn_S, float* const* gn_dbias_prev, int G,
+                                  int N, long long V, int C, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * 2x2x2 stride-2 pooling (prim_ops.py:160-168).  kind 0 = avg, 1 = max.
  * Backward of max re-derives the arg-max from x (first maximum in d,h,w scan order, as

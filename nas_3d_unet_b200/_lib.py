@@ -67,6 +67,11 @@ _SIGNATURES = {
     "nas3d_se_excite": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp],
     "nas3d_affine_sum_fwd": [c_int, _PP, _PI, _PP, _PP, _PP, _PI, c_vp, c_int, c_int, c_ll, c_int,
                              c_vp],
+    "nas3d_affine_sum_fwd_gn": [c_int, _PP, _PI, _PP, _PP, _PP, _PI, _PP, _PP, _PP, _PP, c_int,
+                                C.c_float, c_vp, c_int, c_int, c_ll, c_int, c_vp],
+    "nas3d_affine_sum_bwd_apply_gn": [c_int, _PP, _PI, _PP, _PP, _PI, _PP, _PP, _PP, _PP, _PP, _PI,
+                                      _PI, c_vp, c_int, _PP, _PP, _PP, _PP, _PP, _PP, _PP, _PP,
+                                      c_int, c_int, c_ll, c_int, c_vp],
     "nas3d_affine_sum_bwd_reduce": [c_int, _PP, _PI, _PP, _PP, _PI, c_vp, c_int, _PP, c_int, c_ll,
                                     c_int, c_vp],
     "nas3d_gn_bwd_coef": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_ll, c_vp, c_vp,

@@ -7,6 +7,7 @@
 // HBM-bound: one float4 (4 channels of one voxel) per thread per iteration, grid-stride,
 // grid = 148 SMs x 8 CTAs.  Per-(n,c) coefficients are tiny and stay in L1.
 #include "common.cuh"
+#include "gn_coef.cuh"
 
 namespace nas3d {
 
@@ -20,17 +21,25 @@ struct FwdTerms {
   int nterms;
 };
 
+// coefficient load: the read-only path, or a plain (coherent) load when the coefficients were
+// written by this very kernel's prologue
+template <bool COH>
+__device__ __forceinline__ float4 coef4(const float* p) {
+  return COH ? *reinterpret_cast<const float4*>(p) : ldg4(p);
+}
+
 // grid = (chunks, N): blockIdx.y is the sample, so no 64-bit division in the hot loop; every
 // thread keeps two independent float4 elements (x K terms) in flight.
+template <bool COH>
 __device__ __forceinline__ float4 affine_term(const FwdTerms& T, int k, const float* base_k,
                                               unsigned vox, int c, long long nc) {
   float4 v = ldg4(base_k + (long long)vox * T.ld[k] + c);
   if (T.a[k]) {
-    const float4 a = ldg4(T.a[k] + nc);
+    const float4 a = coef4<COH>(T.a[k] + nc);
     v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w;
   }
   if (T.b[k]) {
-    const float4 b = ldg4(T.b[k] + nc);
+    const float4 b = coef4<COH>(T.b[k] + nc);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if (T.relu[k]) {
@@ -39,9 +48,10 @@ __device__ __forceinline__ float4 affine_term(const FwdTerms& T, int k, const fl
   return v;
 }
 
-__global__ void __launch_bounds__(256)
-    affine_sum_fwd_kernel(const __grid_constant__ FwdTerms T, float* __restrict__ out, int ld_out,
-                          long long V, int C, int C4, unsigned per_sample) {
+template <bool COH>
+__device__ __forceinline__ void affine_sum_fwd_loop(const FwdTerms& T, float* __restrict__ out,
+                                                    int ld_out, long long V, int C, int C4,
+                                                    unsigned per_sample) {
   const int n = blockIdx.y;
   const long long vbase = (long long)n * V;
   float* outn = out + vbase * ld_out;
@@ -56,8 +66,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll 2
     for (int k = 0; k < T.nterms; ++k) {
       const float* bk = T.x[k] + vbase * T.ld[k];
-      const float4 v0 = affine_term(T, k, bk, vox0, c0, nc0);
-      const float4 v1 = affine_term(T, k, bk, vox1, c1, nc1);
+      const float4 v0 = affine_term<COH>(T, k, bk, vox0, c0, nc0);
+      const float4 v1 = affine_term<COH>(T, k, bk, vox1, c1, nc1);
       const float w = T.w[k] ? __ldg(T.w[k]) : 1.f;
       acc0.x += w * v0.x; acc0.y += w * v0.y; acc0.z += w * v0.z; acc0.w += w * v0.w;
       acc1.x += w * v1.x; acc1.y += w * v1.y; acc1.z += w * v1.z; acc1.w += w * v1.w;
@@ -65,6 +75,27 @@ __global__ void __launch_bounds__(256)
     st4(outn + (long long)vox0 * ld_out + c0, acc0);
     if (has2) st4(outn + (long long)vox1 * ld_out + c1, acc1);
   }
+}
+
+__global__ void __launch_bounds__(256)
+    affine_sum_fwd_kernel(const __grid_constant__ FwdTerms T, float* __restrict__ out, int ld_out,
+                          long long V, int C, int C4, unsigned per_sample) {
+  affine_sum_fwd_loop<false>(T, out, ld_out, V, C, C4, per_sample);
+}
+
+// Same pass with the GroupNorm coefficient kernels of its terms folded in: every CTA first derives
+// a, b (and mean / rstd, kept for the backward) of its sample from the fp64 moments - a few hundred
+// flops - instead of waiting for a separate 5 us launch per node on the critical path.  All CTAs of
+// a sample store identical values; the loop then reads them with coherent loads.
+__global__ void __launch_bounds__(256)
+    affine_sum_fwd_gn_kernel(const __grid_constant__ FwdTerms T, const __grid_constant__ GnFwdBatch B,
+                             int G, double inv_m, float eps, float* __restrict__ out, int ld_out,
+                             long long V, int C, int C4, unsigned per_sample) {
+  __shared__ GnScratch sc;
+  for (int k = 0; k < T.nterms; ++k)
+    if (B.S[k]) gn_coef_body(B, k, blockIdx.y, C, G, inv_m, eps, sc);
+  __syncthreads();
+  affine_sum_fwd_loop<true>(T, out, ld_out, V, C, C4, per_sample);
 }
 
 struct BwdTerms {
@@ -84,6 +115,7 @@ struct BwdTerms {
 };
 
 // dx_k (+)= p_k*m_k*dout + q_k*x_k + r_k for one float4 element of term k
+template <bool COH>
 __device__ __forceinline__ void bwd_apply_one(const BwdTerms& T, int k, float4 g, const float4& x,
                                               long long nc, float* dst) {
   if (T.relu[k]) {
@@ -96,18 +128,18 @@ __device__ __forceinline__ void bwd_apply_one(const BwdTerms& T, int k, float4 g
     g.w = (a.w * x.w + b.w > 0.f) ? g.w : 0.f;
   }
   if (T.p[k]) {
-    const float4 p = ldg4(T.p[k] + nc);
+    const float4 p = coef4<COH>(T.p[k] + nc);
     g.x *= p.x; g.y *= p.y; g.z *= p.z; g.w *= p.w;
   } else if (T.w[k]) {
     const float w = __ldg(T.w[k]);
     g.x *= w; g.y *= w; g.z *= w; g.w *= w;
   }
   if (T.q[k]) {
-    const float4 q = ldg4(T.q[k] + nc);
+    const float4 q = coef4<COH>(T.q[k] + nc);
     g.x += q.x * x.x; g.y += q.y * x.y; g.z += q.z * x.z; g.w += q.w * x.w;
   }
   if (T.r[k]) {
-    const float4 r = ldg4(T.r[k] + nc);
+    const float4 r = coef4<COH>(T.r[k] + nc);
     g.x += r.x; g.y += r.y; g.z += r.z; g.w += r.w;
   }
   if (T.acc[k]) {
@@ -122,9 +154,11 @@ __device__ __forceinline__ void bwd_apply_one(const BwdTerms& T, int k, float4 g
 // Two independent float4 elements per thread per iteration (as in the forward kernel): the dout
 // and x_k loads of both are issued before the first dependent use, doubling the bytes in flight
 // per thread (r1d ncu: 4.6 TB/s with one element in flight per thread, latency-bound).
-__global__ void __launch_bounds__(256)
-    affine_sum_bwd_apply_kernel(const __grid_constant__ BwdTerms T, const float* __restrict__ dout,
-                                int ld_dout, long long V, int C, int C4, unsigned per_sample) {
+template <bool COH>
+__device__ __forceinline__ void affine_sum_bwd_apply_loop(const BwdTerms& T,
+                                                          const float* __restrict__ dout,
+                                                          int ld_dout, long long V, int C, int C4,
+                                                          unsigned per_sample) {
   const int n = blockIdx.y;
   const long long vbase = (long long)n * V;
   const float* dn = dout + vbase * ld_dout;
@@ -144,10 +178,32 @@ __global__ void __launch_bounds__(256)
         x0 = ldg4(T.x[k] + (vbase + vox0) * T.ld[k] + c0);
         x1 = ldg4(T.x[k] + (vbase + vox1) * T.ld[k] + c1);
       }
-      bwd_apply_one(T, k, d0, x0, nc0, T.dx[k] + (vbase + vox0) * T.ld_dx[k] + c0);
-      if (has2) bwd_apply_one(T, k, d1, x1, nc1, T.dx[k] + (vbase + vox1) * T.ld_dx[k] + c1);
+      bwd_apply_one<COH>(T, k, d0, x0, nc0, T.dx[k] + (vbase + vox0) * T.ld_dx[k] + c0);
+      if (has2) bwd_apply_one<COH>(T, k, d1, x1, nc1, T.dx[k] + (vbase + vox1) * T.ld_dx[k] + c1);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+    affine_sum_bwd_apply_kernel(const __grid_constant__ BwdTerms T, const float* __restrict__ dout,
+                                int ld_dout, long long V, int C, int C4, unsigned per_sample) {
+  affine_sum_bwd_apply_loop<false>(T, dout, ld_dout, V, C, C4, per_sample);
+}
+
+// With the GroupNorm backward coefficient kernel of its terms folded in (see the forward): every
+// CTA derives p, q, r of its sample from the reductions R; the CTA with blockIdx.x == 0 also adds
+// the parameter gradients that fall out of the same sums (d gamma, d beta, the bias of the conv
+// that fed the GroupNorm, d alpha).
+__global__ void __launch_bounds__(256)
+    affine_sum_bwd_apply_gn_kernel(const __grid_constant__ BwdTerms T,
+                                   const __grid_constant__ GnBwdBatch B, int G, double inv_m,
+                                   const float* __restrict__ dout, int ld_dout, long long V, int C,
+                                   int C4, unsigned per_sample) {
+  __shared__ GnScratch sc;
+  for (int k = 0; k < T.nterms; ++k)
+    if (B.R[k]) gn_bwd_coef_body(B, k, blockIdx.y, C, G, inv_m, (double)V, blockIdx.x == 0, sc);
+  __syncthreads();
+  affine_sum_bwd_apply_loop<true>(T, dout, ld_dout, V, C, C4, per_sample);
 }
 
 __global__ void __launch_bounds__(256)
@@ -242,6 +298,88 @@ int nas3d_affine_sum_fwd(int nterms, const float* const* x, const int* ld_x,
   affine_sum_fwd_kernel<<<grid2d(per_sample, N, 512), 256, 0, (cudaStream_t)stream>>>(
       T, out, ld_out, V, C, C4, (unsigned)per_sample);
   return launched("affine_sum_fwd");
+}
+
+int nas3d_affine_sum_fwd_gn(int nterms, const float* const* x, const int* ld_x,
+                            float* const* a, float* const* b, const float* const* w,
+                            const int* relu, const double* const* gn_S,
+                            const float* const* gn_gamma, const float* const* gn_beta,
+                            float* const* gn_mean_rstd, int G, float eps, float* out, int ld_out,
+                            int N, long long V, int C, void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "affine_sum_fwd_gn: nterms=%d", nterms);
+  NAS3D_REQUIRE(C % 4 == 0 && ld_out % 4 == 0 && aligned16(out),
+                "affine_sum_fwd_gn: C=%d ld_out=%d must be multiples of 4, out 16B aligned", C, ld_out);
+  NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "affine_sum_fwd_gn: bad groups %d for C=%d", G, C);
+  NAS3D_REQUIRE(gn_S && gn_gamma && gn_beta && gn_mean_rstd && a && b, "affine_sum_fwd_gn: NULL array");
+  FwdTerms T;
+  GnFwdBatch B;
+  T.nterms = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    NAS3D_REQUIRE(ld_x[k] % 4 == 0 && aligned16(x[k]), "affine_sum_fwd_gn: term %d misaligned", k);
+    T.x[k] = x[k]; T.ld[k] = ld_x[k];
+    T.a[k] = a[k]; T.b[k] = b[k]; T.w[k] = w ? w[k] : nullptr;
+    T.relu[k] = relu ? relu[k] : 0;
+    B.S[k] = gn_S[k]; B.gamma[k] = gn_gamma[k]; B.beta[k] = gn_beta[k];
+    B.a[k] = a[k]; B.b[k] = b[k]; B.mr[k] = gn_mean_rstd[k];
+    NAS3D_REQUIRE(!B.S[k] || (B.gamma[k] && B.beta[k] && B.a[k] && B.b[k] && B.mr[k]),
+                  "affine_sum_fwd_gn: GroupNorm term %d needs gamma, beta, a, b, mean_rstd", k);
+  }
+  const int C4 = C / 4;
+  const long long per_sample = V * C4;
+  NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_fwd_gn: sample too large for 32-bit indexing");
+  const double inv_m = 1.0 / ((double)(C / G) * (double)V);
+  affine_sum_fwd_gn_kernel<<<grid2d(per_sample, N, 512), 256, 0, (cudaStream_t)stream>>>(
+      T, B, G, inv_m, eps, out, ld_out, V, C, C4, (unsigned)per_sample);
+  return launched("affine_sum_fwd_gn");
+}
+
+int nas3d_affine_sum_bwd_apply_gn(int nterms, const float* const* x, const int* ld_x,
+                                  const float* const* a, const float* const* b, const int* relu,
+                                  float* const* p, float* const* q, float* const* r,
+                                  const float* const* w, float* const* dx, const int* ld_dx,
+                                  const int* accumulate, const float* dout, int ld_dout,
+                                  const double* const* gn_R, const float* const* gn_mean_rstd,
+                                  const float* const* gn_gamma, float* const* gn_dgamma,
+                                  float* const* gn_dbeta, float* const* gn_dw,
+                                  const double* const* gn_S, float* const* gn_dbias_prev, int G,
+                                  int N, long long V, int C, void* stream) {
+  NAS3D_REQUIRE(nterms >= 1 && nterms <= NAS3D_MAX_TERMS, "affine_sum_bwd_apply_gn: nterms=%d", nterms);
+  NAS3D_REQUIRE(C % 4 == 0 && ld_dout % 4 == 0 && aligned16(dout),
+                "affine_sum_bwd_apply_gn: C=%d ld_dout=%d", C, ld_dout);
+  NAS3D_REQUIRE(G >= 1 && G <= 64 && C % G == 0, "affine_sum_bwd_apply_gn: bad groups %d for C=%d", G, C);
+  NAS3D_REQUIRE(gn_R && gn_mean_rstd && gn_gamma && gn_dgamma && gn_dbeta && p && q && r,
+                "affine_sum_bwd_apply_gn: NULL array");
+  BwdTerms T;
+  GnBwdBatch B;
+  T.nterms = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    NAS3D_REQUIRE(ld_dx[k] % 4 == 0 && aligned16(dx[k]), "affine_sum_bwd_apply_gn: dx %d misaligned", k);
+    T.x[k] = x ? x[k] : nullptr; T.ld[k] = ld_x ? ld_x[k] : 0;
+    T.a[k] = a ? a[k] : nullptr; T.b[k] = b ? b[k] : nullptr;
+    T.p[k] = p[k]; T.q[k] = q[k]; T.r[k] = r[k];
+    T.w[k] = w ? w[k] : nullptr;
+    T.dx[k] = dx[k]; T.ld_dx[k] = ld_dx[k];
+    T.relu[k] = relu ? relu[k] : 0; T.acc[k] = accumulate ? accumulate[k] : 0;
+    NAS3D_REQUIRE(!(T.relu[k] || T.q[k]) || T.x[k], "affine_sum_bwd_apply_gn: term %d needs x", k);
+    B.R[k] = gn_R[k]; B.mr[k] = gn_mean_rstd[k]; B.gamma[k] = gn_gamma[k];
+    B.a[k] = T.a[k]; B.b[k] = T.b[k]; B.w[k] = T.w[k];
+    B.p[k] = p[k]; B.q[k] = q[k]; B.r[k] = r[k];
+    B.dgamma[k] = gn_dgamma[k]; B.dbeta[k] = gn_dbeta[k]; B.dw[k] = gn_dw ? gn_dw[k] : nullptr;
+    B.S[k] = gn_S ? gn_S[k] : nullptr; B.dbias[k] = gn_dbias_prev ? gn_dbias_prev[k] : nullptr;
+    if (B.R[k]) {
+      NAS3D_REQUIRE(B.mr[k] && B.gamma[k] && B.a[k] && B.b[k] && B.p[k] && B.q[k] && B.r[k] &&
+                        B.dgamma[k] && B.dbeta[k],
+                    "affine_sum_bwd_apply_gn: GroupNorm term %d lacks an array", k);
+      NAS3D_REQUIRE(B.dbias[k] == nullptr || B.S[k] != nullptr, "affine_sum_bwd_apply_gn: dbias needs S");
+    }
+  }
+  const int C4 = C / 4;
+  const long long per_sample = V * C4;
+  NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_bwd_apply_gn: sample too large");
+  const double inv_m = 1.0 / ((double)(C / G) * (double)V);
+  affine_sum_bwd_apply_gn_kernel<<<grid2d(per_sample, N, 512), 256, 0, (cudaStream_t)stream>>>(
+      T, B, G, inv_m, dout, ld_dout, V, C, C4, (unsigned)per_sample);
+  return launched("affine_sum_bwd_apply_gn");
 }
 
 int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_x,

@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(PW_T, NAS3D_PW_MINB) pointwise_kernel(const __
   const bool vec_in = (A.Cin % 4 == 0) && (A.ld_src % 4 == 0);
   const bool vec_out = (A.ld_dst % 4 == 0) && (co0 + CO <= A.Cout);
   // fast epilogue: whole float4 channel groups, all per-channel operands fetched as float4
-  const bool fast = (A.Cout % 4 == 0) && (A.nseg > 1 || vec_out) &&
+  // a ragged Cout (the 12->3 head) stored at a multiple-of-4 pitch is written as whole float4s
+  // too: the pad lanes receive act(0) and are never read as data
+  const bool pad_out = SRC_IS_BIG && (A.ld_dst % 4 == 0) && (co0 + CO <= A.ld_dst);
+  const bool fast = ((A.Cout % 4 == 0 && (A.nseg > 1 || vec_out)) || pad_out) &&
                     (A.mask == nullptr || A.ld_mask % 4 == 0);
   const bool need_n = A.stride != 1 || A.scale != nullptr;
   int mom_n = -1;
@@ -217,7 +220,15 @@ __global__ void __launch_bounds__(PW_T, NAS3D_PW_MINB) pointwise_kernel(const __
         // segment of this channel group (equal widths, multiples of 4): no integer division
         sg = (A.nseg > 1) ? (c >= A.seg_w) + (c >= 2 * A.seg_w) + (c >= 3 * A.seg_w) : 0;
         off = c - sg * A.seg_w;
-        if (A.bias) b4 = ldg4(A.bias + c);
+        if (A.bias) {
+          if (c + 4 <= A.Cout) {
+            b4 = ldg4(A.bias + c);
+          } else {
+            b4.x = __ldg(A.bias + c);
+            if (c + 1 < A.Cout) b4.y = __ldg(A.bias + c + 1);
+            if (c + 2 < A.Cout) b4.z = __ldg(A.bias + c + 2);
+          }
+        }
       }
       // relu-mask operands of the thread's voxels: issued together, consumed below
       float4 m4[VPT];

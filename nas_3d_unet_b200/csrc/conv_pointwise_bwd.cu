@@ -77,7 +77,11 @@ __global__ void __launch_bounds__(PB_T, CS == 4 ? 3 : 2) pw_bwd_fused_kernel(con
   constexpr int D4 = CS / 4;
   const int Cb = A.Cb, Cs = A.Cs;
   const int Q = Cb >> 2;
-  const int g = threadIdx.x % Q;
+  // quad of this thread.  Dense big tensor: consecutive threads walk consecutive quads (a warp =
+  // 512 contiguous bytes).  Virtual concat of 4-channel parts: a warp stays inside ONE part and
+  // walks 32 consecutive voxels of it, which is what is contiguous there.
+  const bool part_major = (A.seg_w == 4) && (A.nseg == Q) && (Q > 1);
+  const int g = part_major ? threadIdx.x / (PB_T / Q) : threadIdx.x % Q;
   const int c0 = g * 4;
   const int sg = c0 / A.seg_w, off = c0 - sg * A.seg_w;
   const int xl = pb_pick4(A.ldx, sg);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(PB_T, CS == 4 ? 3 : 2) pw_bwd_fused_kernel(con
   const unsigned tile0 = blockIdx.x * (unsigned)tiles_per_cta;
   const unsigned tile1 = min(tile0 + (unsigned)tiles_per_cta, ntiles);
   const unsigned vend = min(tile1 * vpt, A.nvox);      // this CTA's voxels: [tile0*vpt, vend)
-  unsigned v = tile0 * vpt + threadIdx.x / Q;          // consume side
+  unsigned v = tile0 * vpt + (part_major ? threadIdx.x % vpt : threadIdx.x / Q);   // consume side
   unsigned vi = v;                                     // issue side (PB_S-1 tiles ahead)
   // running pointers of the issue side
   const float* px = pb_pick4(A.x, sg) + off + (long long)vi * xl;
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(PB_T, CS == 4 ? 3 : 2) pw_bwd_fused_kernel(con
           dyv[4 * i + 2] *= p4.z * (1.f - p4.z); dyv[4 * i + 3] *= p4.w * (1.f - p4.w);
         }
       }
-      if (!VEC) {   // channels past Cs were never copied
+      if (Cs < CS) {   // channels past Cs were never copied / are pad lanes of the pitch
 #pragma unroll
         for (int i = 0; i < CS; ++i) dyv[i] = i < Cs ? dyv[i] : 0.f;
       }
@@ -323,7 +327,7 @@ int nas3d_conv1x1_bwd_fused(const nas3d_conv_desc* d, int nparts, const float* c
   A.Vs = (unsigned)((long long)d->Ds * d->Hs * d->Ws);
   A.relu = big_relu;
   const bool want_dx = dbig_parts != nullptr && dbig_parts[0] != nullptr;
-  if (d->ld_small % 4 == 0 && d->Cs % 4 == 0)
+  if (d->ld_small % 4 == 0)
     NAS3D_REQUIRE(aligned16(dsmall) && (!small_prob || aligned16(small_prob)), "conv1x1_bwd_fused: dsmall must be 16-byte aligned");
   NAS3D_REQUIRE(!big_scale || aligned16(big_scale), "conv1x1_bwd_fused: scale must be 16-byte aligned");
   for (int i = 0; i < nparts; ++i) {
@@ -339,7 +343,7 @@ int nas3d_conv1x1_bwd_fused(const nas3d_conv_desc* d, int nparts, const float* c
   }
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  const bool vec = d->ld_small % 4 == 0 && (d->Cs == 4 || d->Cs == 8);
+  const bool vec = d->ld_small % 4 == 0 && d->ld_small >= (d->Cs <= 4 ? 4 : 8);   // whole float4s of dsmall
   if (small_prob) {
     NAS3D_REQUIRE(d->Cs <= 4 && want_dx, "conv1x1_bwd_fused: the sigmoid prologue serves the head (Cs <= 4, with dgrad)");
     rc = vec ? pb_launch<4, true, true, true>(A, st) : pb_launch<4, true, true, false>(A, st);

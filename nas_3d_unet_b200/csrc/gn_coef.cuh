@@ -1,0 +1,134 @@
+// GroupNorm coefficient math shared by the stand-alone coefficient kernels (reduce.cu) and the
+// affine kernels that compute their own coefficients in a prologue (affine.cu).
+#pragma once
+#include "common.cuh"
+
+namespace nas3d {
+
+struct GnFwdBatch {
+  const double* S[NAS3D_MAX_TERMS];
+  const float* gamma[NAS3D_MAX_TERMS];
+  const float* beta[NAS3D_MAX_TERMS];
+  float* a[NAS3D_MAX_TERMS];
+  float* b[NAS3D_MAX_TERMS];
+  float* mr[NAS3D_MAX_TERMS];
+};
+struct GnBwdBatch {
+  const double* R[NAS3D_MAX_TERMS];
+  const float* mr[NAS3D_MAX_TERMS];
+  const float* gamma[NAS3D_MAX_TERMS];
+  const float* a[NAS3D_MAX_TERMS];
+  const float* b[NAS3D_MAX_TERMS];
+  const float* w[NAS3D_MAX_TERMS];
+  float* p[NAS3D_MAX_TERMS];
+  float* q[NAS3D_MAX_TERMS];
+  float* r[NAS3D_MAX_TERMS];
+  float* dgamma[NAS3D_MAX_TERMS];
+  float* dbeta[NAS3D_MAX_TERMS];
+  float* dw[NAS3D_MAX_TERMS];
+  const double* S[NAS3D_MAX_TERMS];
+  float* dbias[NAS3D_MAX_TERMS];
+};
+
+// Scratch of the bodies below (G <= 64, block of <= 1024 threads).
+struct GnScratch {
+  double dA[64], dB[64];
+  double red[32];
+};
+
+// block-wide sum; every thread of the block must call it
+__device__ __forceinline__ double gn_block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) t += red[i];
+  return t;
+}
+
+// y = a*x + b with a = rstd*gamma, b = beta - mean*a for sample n of term k (nn.GroupNorm,
+// biased variance; prim_ops.py:56-58).  Called by ALL threads of a block; writes a, b, mean_rstd
+// of (k, n).  Several blocks may execute it for the same (k, n): they store identical values.
+__device__ __forceinline__ void gn_coef_body(const GnFwdBatch& B, int k, int n, int C, int G,
+                                             double inv_m, float eps, GnScratch& sc) {
+  const int cg = C / G;
+  float* sh_mean = reinterpret_cast<float*>(sc.dA);
+  float* sh_rstd = reinterpret_cast<float*>(sc.dB);
+  const double* Sn = B.S[k] + (long long)n * C * 2;
+  __syncthreads();   // scratch may still be read by the previous call
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { s += Sn[c * 2]; q += Sn[c * 2 + 1]; }
+    double mean = s * inv_m;
+    double var = q * inv_m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sh_mean[g] = (float)mean;
+    sh_rstd[g] = rstd;
+    B.mr[k][((long long)n * G + g) * 2 + 0] = (float)mean;
+    B.mr[k][((long long)n * G + g) * 2 + 1] = rstd;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cg;
+    float av = sh_rstd[g] * B.gamma[k][c];
+    B.a[k][(long long)n * C + c] = av;
+    B.b[k][(long long)n * C + c] = B.beta[k][c] - sh_mean[g] * av;
+  }
+}
+
+// GroupNorm backward coefficients of (k, n) from the reductions R:  dx = p*m*dout + q*x + r.
+// p, q, r are stored by every calling block (identical values); the parameter-gradient atomics
+// (dgamma, dbeta, the bias of the producing conv, d alpha) only when `side` is set - exactly one
+// block per (k, n) must pass side = true.
+__device__ __forceinline__ void gn_bwd_coef_body(const GnBwdBatch& B, int k, int n, int C, int G,
+                                                 double inv_m, double V, bool side, GnScratch& sc) {
+  const int cg = C / G;
+  const float* mean_rstd = B.mr[k];
+  const float* gamma = B.gamma[k];
+  const double wv = B.w[k] ? (double)B.w[k][0] : 1.0;
+  double* shA = sc.dA;
+  double* shB = sc.dB;
+  const double* Rn = B.R[k] + (long long)n * C * 2;
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+    double A = 0.0, Bq = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
+      A += (double)gamma[c] * r1;
+      Bq += (double)gamma[c] * rho * (r2 - mu * r1);
+    }
+    shA[g] = A;
+    shB[g] = Bq;
+  }
+  __syncthreads();
+  double dwp = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cg;
+    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+    double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
+    double qq = -rho * rho * shB[g] * inv_m;
+    const double pp = wv * rho * (double)gamma[c];
+    const double rr = wv * (-qq * mu - rho * shA[g] * inv_m);
+    B.p[k][(long long)n * C + c] = (float)pp;
+    B.q[k][(long long)n * C + c] = (float)(wv * qq);
+    B.r[k][(long long)n * C + c] = (float)rr;
+    if (side) {
+      atomicAdd(&B.dgamma[k][c], (float)(wv * rho * (r2 - mu * r1)));
+      atomicAdd(&B.dbeta[k][c], (float)(wv * r1));
+      if (B.dbias[k])
+        atomicAdd(&B.dbias[k][c], (float)(pp * r1 + wv * qq * B.S[k][((long long)n * C + c) * 2] + rr * V));
+      dwp += (double)B.a[k][(long long)n * C + c] * r2 + (double)B.b[k][(long long)n * C + c] * r1;
+    }
+  }
+  if (B.dw[k] && side) {   // `side` is uniform over the block
+    double tot = gn_block_sum(dwp, sc.red);
+    if (threadIdx.x == 0) atomicAdd(B.dw[k], (float)tot);
+  }
+}
+
+}  // namespace nas3d

@@ -5,6 +5,7 @@
 // 128-bit loads; fp32 partials over <=32 elements per thread, fp64 from there on
 // (GroupNorm statistics of inputs up to ~110 in magnitude cancel badly in fp32).
 #include "common.cuh"
+#include "gn_coef.cuh"
 
 namespace nas3d {
 
@@ -364,105 +365,19 @@ __global__ void __launch_bounds__(TB)
 }
 
 // ---- batched variants: all GroupNorm terms of one node in a single launch (grid = N x nterms);
-// the supernet has up to 22 terms per node and these tiny kernels are pure launch latency ----
-struct GnFwdBatch {
-  const double* S[NAS3D_MAX_TERMS];
-  const float* gamma[NAS3D_MAX_TERMS];
-  const float* beta[NAS3D_MAX_TERMS];
-  float* a[NAS3D_MAX_TERMS];
-  float* b[NAS3D_MAX_TERMS];
-  float* mr[NAS3D_MAX_TERMS];
-};
-struct GnBwdBatch {
-  const double* R[NAS3D_MAX_TERMS];
-  const float* mr[NAS3D_MAX_TERMS];
-  const float* gamma[NAS3D_MAX_TERMS];
-  const float* a[NAS3D_MAX_TERMS];
-  const float* b[NAS3D_MAX_TERMS];
-  const float* w[NAS3D_MAX_TERMS];
-  float* p[NAS3D_MAX_TERMS];
-  float* q[NAS3D_MAX_TERMS];
-  float* r[NAS3D_MAX_TERMS];
-  float* dgamma[NAS3D_MAX_TERMS];
-  float* dbeta[NAS3D_MAX_TERMS];
-  float* dw[NAS3D_MAX_TERMS];
-  const double* S[NAS3D_MAX_TERMS];
-  float* dbias[NAS3D_MAX_TERMS];
-};
-
+// the supernet has up to 22 terms per node and these tiny kernels are pure launch latency.  The
+// affine kernels can also run the same bodies in their own prologue (affine.cu, *_gn entry points).
 __global__ void __launch_bounds__(TB)
     gn_coef_batch_kernel(const __grid_constant__ GnFwdBatch B, int C, int G, double inv_m, float eps) {
-  const int n = blockIdx.x, k = blockIdx.y;
-  const int cg = C / G;
-  __shared__ float sh_mean[64], sh_rstd[64];
-  const double* Sn = B.S[k] + (long long)n * C * 2;
-  for (int g = threadIdx.x; g < G; g += TB) {
-    double s = 0.0, q = 0.0;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) { s += Sn[c * 2]; q += Sn[c * 2 + 1]; }
-    double mean = s * inv_m;
-    double var = q * inv_m - mean * mean;
-    if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    sh_mean[g] = (float)mean;
-    sh_rstd[g] = rstd;
-    B.mr[k][((long long)n * G + g) * 2 + 0] = (float)mean;
-    B.mr[k][((long long)n * G + g) * 2 + 1] = rstd;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += TB) {
-    int g = c / cg;
-    float av = sh_rstd[g] * B.gamma[k][c];
-    B.a[k][(long long)n * C + c] = av;
-    B.b[k][(long long)n * C + c] = B.beta[k][c] - sh_mean[g] * av;
-  }
+  __shared__ GnScratch sc;
+  gn_coef_body(B, blockIdx.y, blockIdx.x, C, G, inv_m, eps, sc);
 }
 
 __global__ void __launch_bounds__(TB)
     gn_bwd_coef_batch_kernel(const __grid_constant__ GnBwdBatch B, int C, int G, double inv_m,
                              double V) {
-  const int n = blockIdx.x, k = blockIdx.y;
-  const int cg = C / G;
-  const float* mean_rstd = B.mr[k];
-  const float* gamma = B.gamma[k];
-  const double wv = B.w[k] ? (double)B.w[k][0] : 1.0;
-  __shared__ double shA[64], shB[64];
-  __shared__ double sh[TB / 32];
-  const double* Rn = B.R[k] + (long long)n * C * 2;
-  for (int g = threadIdx.x; g < G; g += TB) {
-    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
-    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
-    double A = 0.0, Bq = 0.0;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) {
-      double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
-      A += (double)gamma[c] * r1;
-      Bq += (double)gamma[c] * rho * (r2 - mu * r1);
-    }
-    shA[g] = A;
-    shB[g] = Bq;
-  }
-  __syncthreads();
-  double dwp = 0.0;
-  for (int c = threadIdx.x; c < C; c += TB) {
-    int g = c / cg;
-    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
-    double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
-    double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
-    double qq = -rho * rho * shB[g] * inv_m;
-    const double pp = wv * rho * (double)gamma[c];
-    const double rr = wv * (-qq * mu - rho * shA[g] * inv_m);
-    B.p[k][(long long)n * C + c] = (float)pp;
-    B.q[k][(long long)n * C + c] = (float)(wv * qq);
-    B.r[k][(long long)n * C + c] = (float)rr;
-    atomicAdd(&B.dgamma[k][c], (float)(wv * rho * (r2 - mu * r1)));
-    atomicAdd(&B.dbeta[k][c], (float)(wv * r1));
-    if (B.dbias[k])
-      atomicAdd(&B.dbias[k][c], (float)(pp * r1 + wv * qq * B.S[k][((long long)n * C + c) * 2] + rr * V));
-    dwp += (double)B.a[k][(long long)n * C + c] * r2 + (double)B.b[k][(long long)n * C + c] * r1;
-  }
-  if (B.dw[k]) {
-    double tot = block_sum(dwp, sh);
-    if (threadIdx.x == 0) atomicAdd(B.dw[k], (float)tot);
-  }
+  __shared__ GnScratch sc;
+  gn_bwd_coef_body(B, blockIdx.y, blockIdx.x, C, G, inv_m, V, true, sc);
 }
 
 // super-elements per thread: RITER for big tensors (fewest atomics), fewer when the tensor is small

@@ -214,6 +214,17 @@ def new_act(N, Cc, D, H, W, device):
     return Act(alloc(N, Cc, D, H, W, device), Cc)
 
 
+def new_act_padded(N, Cc, D, H, W, device):
+    """Cc channels stored at the next multiple-of-4 voxel pitch (the 3-channel head output,
+    nas.py:50-52): every access to it is then one aligned 128-bit vector.  The pad lanes hold
+    unspecified values and are never read as data."""
+    ld = (Cc + 3) // 4 * 4
+    if ld == Cc:
+        return new_act(N, Cc, D, H, W, device)
+    buf = torch.empty((N, D, H, W, ld), device=device, dtype=torch.float32)
+    return Act(buf.permute(0, 4, 1, 2, 3)[:, :Cc], ld)
+
+
 def _ndhwc_pitch(t):
     """voxel pitch if t is laid out NDHWC (possibly channel-sliced), else None"""
     N, Cc, D, H, W = t.shape
@@ -393,18 +404,54 @@ def _tp(t):
     return t.data_ptr() if t is not None else None
 
 
+def gn_fold_enabled():
+    """GroupNorm coefficient kernels folded into the affine kernels' prologues (NAS3D_GN_FOLD=0: one
+    separate coefficient launch per node and direction)"""
+    return os.environ.get("NAS3D_GN_FOLD", "1") != "0"
+
+
+def _take_gn_jobs(ctx, terms, out):
+    """pending GroupNorm coefficient jobs of `terms` that the affine kernel can compute itself
+    (same G and eps): {id(term): job}; they leave ctx.pending_gn"""
+    if not (gn_fold_enabled() and ctx.pending_gn):
+        return {}
+    pend = {id(j) for j in ctx.pending_gn}
+    cand = [(t, t.aux["job"]) for t in terms
+            if t.kind == "gn" and t.aux.get("job") is not None and id(t.aux["job"]) in pend]
+    if not cand or len({(j[4], j[6]) for _, j in cand}) != 1:
+        return {}
+    if any((j[2], j[3], j[5]) != (out.N, out.C, out.V) for _, j in cand):
+        return {}
+    taken = {id(j) for _, j in cand}
+    ctx.pending_gn = [j for j in ctx.pending_gn if id(j) not in taken]
+    return {id(t): j for t, j in cand}
+
+
 def affine_sum(ctx, terms, out):
     """out = sum_k w_k act_k(a_k x_k + b_k)   (cell.py:30,32,81 / prim_ops.py:75-80,152)"""
     n = len(terms)
     lib = ctx.lib
+    fold = _take_gn_jobs(ctx, terms, out)
     flush_gn(ctx)
-    rc = lib.nas3d_affine_sum_fwd(
-        n, ptr_array([t.x.ptr for t in terms]), int_array([t.x.ld for t in terms]),
-        ptr_array([_tp(t.a) for t in terms]), ptr_array([_tp(t.b) for t in terms]),
-        ptr_array([t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None for t in terms]),
-        int_array([1 if t.relu else 0 for t in terms]),
-        out.ptr, out.ld, out.N, out.V, out.C, ctx.stream)
-    check(rc, "affine_sum_fwd")
+    xs, lds = ptr_array([t.x.ptr for t in terms]), int_array([t.x.ld for t in terms])
+    aa, bb = ptr_array([_tp(t.a) for t in terms]), ptr_array([_tp(t.b) for t in terms])
+    ww = ptr_array([t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None for t in terms])
+    rl = int_array([1 if t.relu else 0 for t in terms])
+    if fold:
+        jobs = [fold.get(id(t)) for t in terms]
+        j0 = next(j for j in jobs if j is not None)
+        rc = lib.nas3d_affine_sum_fwd_gn(
+            n, xs, lds, aa, bb, ww, rl,
+            ptr_array([j[0].data_ptr() if j else None for j in jobs]),
+            ptr_array([j[1].weight.data_ptr() if j else None for j in jobs]),
+            ptr_array([j[1].bias.data_ptr() if j else None for j in jobs]),
+            ptr_array([j[8].data_ptr() if j else None for j in jobs]),
+            j0[4], j0[6], out.ptr, out.ld, out.N, out.V, out.C, ctx.stream)
+        check(rc, "affine_sum_fwd_gn")
+    else:
+        rc = lib.nas3d_affine_sum_fwd(n, xs, lds, aa, bb, ww, rl, out.ptr, out.ld, out.N, out.V,
+                                      out.C, ctx.stream)
+        check(rc, "affine_sum_fwd")
     ctx.push(lambda: _affine_sum_bwd(ctx, terms, out))
     return out
 
@@ -450,7 +497,10 @@ def _affine_sum_bwd(ctx, terms, out):
         by_g = {}
         for i, t in enumerate(gn_terms):
             by_g.setdefault(t.aux["G"], []).append(i)
-        for G, idxs in by_g.items():
+        # one GroupNorm geometry and every GroupNorm term receives a dx: the apply kernel below
+        # derives p, q, r (and the parameter gradients) itself
+        fold_gn = (gn_fold_enabled() and len(by_g) == 1 and all(t.x.requires_grad for t in gn_terms))
+        for G, idxs in ({} if fold_gn else by_g).items():
             for c0 in range(0, len(idxs), 32):
                 ii = idxs[c0:c0 + 32]
                 tt = [gn_terms[i] for i in ii]
@@ -514,7 +564,7 @@ def _affine_sum_bwd(ctx, terms, out):
             return t.a.data_ptr()     # y = a*x with constant a:  dx = a*dout
         return None
 
-    rc = lib.nas3d_affine_sum_bwd_apply(
+    common = (
         len(live), ptr_array([t.x.ptr for t in live]), int_array([t.x.ld for t in live]),
         ptr_array([_tp(t.a) for t in live]), ptr_array([_tp(t.b) for t in live]),
         int_array([1 if t.relu else 0 for t in live]),
@@ -523,8 +573,22 @@ def _affine_sum_bwd(ctx, terms, out):
         ptr_array([Rr[id(t)].data_ptr() if id(t) in Rr else None for t in live]),
         ptr_array([t.alpha[0].ptr(t.alpha[1], t.alpha[2]) if t.alpha else None for t in live]),
         ptr_array([g.data_ptr() for g in dxs]), int_array([_ndhwc_pitch(g) for g in dxs]),
-        int_array(accs), dout.data_ptr(), ld_dout, N, V, Cc, st)
-    check(rc, "affine_sum_bwd_apply")
+        int_array(accs), dout.data_ptr(), ld_dout)
+    if gn_terms and fold_gn:
+        gi = {id(t): i for i, t in enumerate(gn_terms)}
+
+        def gp(fn):
+            return ptr_array([fn(t, gi[id(t)]) if id(t) in gi else None for t in live])
+        rc = lib.nas3d_affine_sum_bwd_apply_gn(
+            *common,
+            gp(lambda t, i: R[id(t)].data_ptr()), gp(lambda t, i: t.aux["mean_rstd"].data_ptr()),
+            gp(lambda t, i: t.aux["gamma"].data_ptr()), gp(lambda t, i: ctx.gptr(t.aux["gamma"])),
+            gp(lambda t, i: ctx.gptr(t.aux["beta"])), gp(lambda t, i: dwps[i]),
+            gp(lambda t, i: t.aux["S"].data_ptr()), gp(lambda t, i: bps[i]),
+            gn_terms[0].aux["G"], N, V, Cc, st)
+        check(rc, "affine_sum_bwd_apply_gn")
+    else:
+        check(lib.nas3d_affine_sum_bwd_apply(*common, N, V, Cc, st), "affine_sum_bwd_apply")
 
 
 def materialize(ctx, term):
@@ -568,8 +632,9 @@ def gn_term(ctx, x, norm, relu):
     ab = torch.empty((2, x.N, x.C), device=ctx.device, dtype=torch.float32)
     mr = torch.empty((x.N, G, 2), device=ctx.device, dtype=torch.float32)
     # the coefficient kernel is deferred: affine_sum() flushes all pending ones of a node at once
-    ctx.pending_gn.append((S, norm, x.N, x.C, G, x.V, float(norm.eps), ab, mr, ctx.lane))
-    aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G, "S": S}
+    job = (S, norm, x.N, x.C, G, x.V, float(norm.eps), ab, mr, ctx.lane)
+    ctx.pending_gn.append(job)
+    aux = {"mean_rstd": mr, "gamma": norm.weight, "beta": norm.bias, "G": G, "S": S, "job": job}
     return Term(x, ab[0], ab[1], relu, "gn", aux)
 
 
@@ -822,8 +887,9 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
     """1x1x1 conv whose input is a virtual concat (preprocess convs of the next cell, the head)"""
     lib = ctx.lib
     ctx.use(m.weight, m.bias)
-    y = new_act(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
-                ctx.device)
+    mk = new_act_padded if (spec.stride == 1 and fused_pw_bwd_enabled()) else new_act
+    y = mk(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
+           ctx.device)
     S = None
     if stats:
         S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)
@@ -844,6 +910,8 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
         if spec.stride == 1 and _pw_bwd_fused(ctx, d, parts, y, m, in_relu, in_scale, sigmoid):
             return
         if sigmoid:
+            if y.ld != y.C or _ndhwc_pitch(dy_t) != y.C:
+                raise Nas3dDeviceError("sigmoid backward of a pitched head output needs the fused 1x1 backward")
             dl = torch.empty_like(dy_t)
             check(lib.nas3d_sigmoid_bwd(y.ptr, dy_t.data_ptr(), dl.data_ptr(), y.N * y.V * y.C, st),
                   "sigmoid_bwd")

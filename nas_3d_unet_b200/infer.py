@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import _stream, get_lib
+from .engine import _ndhwc_pitch, _stream, get_lib
 
 
 # ---- host-side integer logic (patches.py:9-75), kept bit-exact incl. float -> int truncation ----
@@ -133,6 +133,7 @@ class SlidingWindowPredictor:
         mine = list(range(rank, B, world))
         preds_mine = self.predict_patches(brain, corners[mine]) if mine else None
         Pd, Ph, Pw = self.patch_shape
+        ld_pred = 3
         if world > 1:
             per = (B + world - 1) // world
             buf = torch.zeros((per, Pd, Ph, Pw, 3), device=volume.device, dtype=torch.float32)
@@ -146,9 +147,11 @@ class SlidingWindowPredictor:
                 if idx:
                     preds[idx] = allb[r][:len(idx)]
         else:
+            ld_pred = _ndhwc_pitch(preds_mine)              # the head output is stored at pitch 4
             preds = preds_mine.permute(0, 2, 3, 4, 1)       # (B,Pd,Ph,Pw,3) view of the NDHWC data
-            if not preds.is_contiguous():
+            if ld_pred is None:
                 preds = preds.contiguous()
+                ld_pred = 3
         cdev = torch.as_tensor(np.ascontiguousarray(corners, dtype=np.int32), device=volume.device)
         labels = torch.empty((D, H, W), device=volume.device, dtype=torch.uint8)
         stitched = (torch.empty((3,) + tuple(int(b) for b in bshape), device=volume.device,
@@ -157,7 +160,7 @@ class SlidingWindowPredictor:
         if skull_mask is not None:
             skull = torch.as_tensor(skull_mask).to(volume.device).to(torch.uint8).contiguous()
         _lib.check(lib.nas3d_stitch_labels(
-            preds.data_ptr(), 3, cdev.data_ptr(), B, Pd, Ph, Pw, int(bshape[0]), int(bshape[1]),
+            preds.data_ptr(), ld_pred, cdev.data_ptr(), B, Pd, Ph, Pw, int(bshape[0]), int(bshape[1]),
             int(bshape[2]), D, H, W, int(off[0]), int(off[1]), int(off[2]), self.threshold,
             1 if self.inclusive else 0, skull.data_ptr() if skull is not None else None,
             labels.data_ptr(), stitched.data_ptr() if stitched is not None else None, _stream()),

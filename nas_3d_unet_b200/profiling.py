@@ -54,6 +54,12 @@ def _work(name, args):
     if name == "nas3d_affine_sum_fwd":
         n, N, V, Cc = args[0], args[9], args[10], args[11]
         return 4.0 * (n + 1) * N * V * Cc, 0.0, "K=%d C=%d V=%d" % (n, Cc, V)
+    if name == "nas3d_affine_sum_fwd_gn":
+        n, N, V, Cc = args[0], args[15], args[16], args[17]
+        return 4.0 * (n + 1) * N * V * Cc, 0.0, "K=%d C=%d V=%d" % (n, Cc, V)
+    if name == "nas3d_affine_sum_bwd_apply_gn":
+        n, N, V, Cc = args[0], args[24], args[25], args[26]
+        return 4.0 * (2 * n + 1) * N * V * Cc, 0.0, "K=%d C=%d V=%d" % (n, Cc, V)
     if name == "nas3d_affine_sum_bwd_reduce":
         n, N, V, Cc = args[0], args[9], args[10], args[11]
         return 4.0 * (n + 1) * N * V * Cc, 0.0, "K=%d C=%d V=%d" % (n, Cc, V)

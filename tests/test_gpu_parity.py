@@ -435,6 +435,7 @@ def test_dice_accepts_int8_masks():
 @pytest.mark.parametrize("cb,cs,nparts,relu,scale,sigmoid,acc,want_dx", [
     (12, 4, 1, True, False, False, False, True),     # cell preprocess0 of the top up cell
     (12, 3, 3, False, True, True, False, True),      # the head: virtual concat, Dropout3d scale, sigmoid
+    (12, -3, 3, False, True, True, False, True),     # the head with its output stored at pitch 4
     (24, 4, 3, True, False, False, True, True),      # preprocess over a concat, accumulating
     (12, 8, 1, True, False, False, False, True),
     (4, 4, 1, False, False, False, True, True),      # separable pointwise conv (thread per voxel)
@@ -450,7 +451,7 @@ def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sig
     from nas_3d_unet_b200._lib import ConvDesc, check, int_array, ptr_array
     lib = _lib.load()
     dev = torch.device("cuda")
-    g = torch.Generator().manual_seed(cb * 7 + cs)
+    g = torch.Generator().manual_seed(cb * 7 + abs(cs))
     N, D, H, W = 2, 5, 9, 11
     nv = N * D * H * W
     sw = cb // nparts
@@ -458,8 +459,14 @@ def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sig
     parts = [torch.randn(nv, pitch, generator=g).to(dev) for _ in range(nparts)]
     x = torch.cat([p[:, :sw] for p in parts], 1).double()
     lds = cs if cs % 4 else cs + 4
+    if cs < 0:          # ragged channel count at the next multiple-of-4 pitch (pad lanes hold garbage)
+        cs = -cs
+        lds = (cs + 3) // 4 * 4
     dy_buf = torch.randn(nv, lds, generator=g).to(dev)
     prob_buf = torch.rand(nv, lds, generator=g).to(dev)
+    if lds > cs and lds - cs < 4:
+        dy_buf[:, cs:] = float('nan')       # pad lanes of a pitched ragged tensor are never data
+        prob_buf[:, cs:] = float('nan')
     Wt = torch.randn(cs, cb, generator=g).to(dev)
     sc = (torch.rand(N, cb, generator=g) * 2).to(dev) if scale else None
     dparts = [torch.randn(nv, pitch, generator=g).to(dev) for _ in range(nparts)]
@@ -524,3 +531,27 @@ def test_fused_pointwise_backward_equals_separate_kernels_in_the_net():
         finally:
             os.environ["NAS3D_PW_FUSED_BWD"] = "1"
     assert O.max_rel(grads["1"], grads["0"]) <= 1e-5
+
+
+@pytest.mark.parametrize("net", ["searched", "supernet"])
+def test_folded_groupnorm_coefficients_equal_separate_kernels(net):
+    """NAS3D_GN_FOLD: the affine kernels deriving the GroupNorm coefficients (forward a, b;
+    backward p, q, r and the parameter gradients) in their prologue against the separate
+    coefficient kernels: same outputs and gradients (both paths run the same device functions)"""
+    import os
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    x, y = O.synthetic_batch(2, 32, seed=5)
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["NAS3D_GN_FOLD"] = mode
+        try:
+            model = (make_searched() if net == "searched" else make_supernet(dropout0=True)).cuda()
+            pred = model(x.cuda())
+            loss = WeightedDiceLoss()(pred, y.cuda())
+            loss.backward()
+            res[mode] = (pred.detach().clone(),
+                         torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
+        finally:
+            os.environ["NAS3D_GN_FOLD"] = "1"
+    assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
+    assert O.max_rel(res["1"][1], res["0"][1]) <= 1e-5
