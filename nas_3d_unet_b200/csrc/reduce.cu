@@ -382,12 +382,35 @@ __global__ void __launch_bounds__(TB)
 
 // super-elements per thread: RITER for big tensors (fewest atomics), fewer when the tensor is small
 // so that at least ~4 CTAs per SM share the work (deep U-Net levels are latency-, not HBM-bound)
-static int reduce_iters(long long total_per_sample, int N, int zdim) {
+// `resident` (CTAs of this kernel that fit on the GPU at once, 0 = unknown): a grid of 4.6 waves
+// runs as long as one of 5, so for big tensors the per-thread trip count is stretched by up to
+// 25 % to make the grid a whole number of waves (bwd_reduce at 8 x 128^3: 2048 CTAs of 32 trips
+// = 4.61 waves -> 1776 CTAs of 37 trips = 4 waves).
+static int reduce_iters(long long total_per_sample, int N, int zdim, int resident = 0) {
   const long long want_ctas = (long long)kNumSMs * 4;
   long long it = total_per_sample * N * zdim / (want_ctas * RB);
   if (it < 1) it = 1;
   if (it > RITER) it = RITER;
+  if (resident > 0 && it == RITER) {
+    const long long nz = (long long)N * zdim;
+    const long long ctas = ((total_per_sample + RB * it - 1) / (RB * it)) * nz;
+    const long long waves = ctas / resident;
+    if (waves >= 2 && ctas % resident != 0) {
+      const long long gx_max = waves * resident / nz;      // grid.x that fits `waves` whole waves
+      if (gx_max >= 1) {
+        const long long it2 = (total_per_sample + RB * gx_max - 1) / (RB * gx_max);
+        if (it2 > it && it2 * 4 <= it * 5) it = it2;
+      }
+    }
+  }
   return (int)it;
+}
+
+template <typename K>
+static int resident_ctas(K kernel, int block) {
+  int o = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, block, 0) != cudaSuccess || o < 1) return 0;
+  return o * kNumSMs;
 }
 
 static int check_channels(int C, int ld, int* U, int* P, int* logP) {
@@ -509,7 +532,8 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
   // TG=2 keeps the fp64 staging array (TG*C*2 doubles) inside 48 KB static smem for C<=768/..;
   // wide tensors are tiny in this network so TG=1 there.
   if (U == 1 && C <= 256) {
-    const int zd = (nterms + 1) / 2, iters = reduce_iters(total, N, zd);
+    static const int resident = resident_ctas(bwd_reduce_kernel<1, 2>, RB);
+    const int zd = (nterms + 1) / 2, iters = reduce_iters(total, N, zd, resident);
     dim3 grid((unsigned)((total + RB * iters - 1) / (RB * iters)), N, zd);
     bwd_reduce_kernel<1, 2><<<grid, RB, 0, st>>>(T, dout, ld_dout, V, C, P, logP, iters);
   } else if (U == 1) {

@@ -405,9 +405,12 @@ def _tp(t):
 
 
 def gn_fold_enabled():
-    """GroupNorm coefficient kernels folded into the affine kernels' prologues (NAS3D_GN_FOLD=0: one
-    separate coefficient launch per node and direction)"""
-    return os.environ.get("NAS3D_GN_FOLD", "1") != "0"
+    """NAS3D_GN_FOLD=1: the GroupNorm coefficient kernels are folded into the affine kernels'
+    prologues (94 fewer launches per searched-net step).  Off by default: measured on B200 it is
+    SLOWER (406 vs 414 patches/s, profiles/r1f_ab_gn_fold_*.json) - the separate 5 us coefficient
+    kernels overlap with other stream lanes, while a prologue of dependent fp64 loads / rsqrt /
+    two block barriers delays the first load of every CTA of the one-wave streaming kernels."""
+    return os.environ.get("NAS3D_GN_FOLD", "0") == "1"
 
 
 def _take_gn_jobs(ctx, terms, out):

@@ -552,6 +552,6 @@ def test_folded_groupnorm_coefficients_equal_separate_kernels(net):
             res[mode] = (pred.detach().clone(),
                          torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
         finally:
-            os.environ["NAS3D_GN_FOLD"] = "1"
+            os.environ.pop("NAS3D_GN_FOLD", None)
     assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
     assert O.max_rel(res["1"][1], res["0"][1]) <= 1e-5
