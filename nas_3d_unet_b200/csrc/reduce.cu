@@ -4,6 +4,7 @@
 // Memory-bound family (HBM roofline): each activation tensor is read exactly once, with
 // 128-bit loads; fp32 partials over <=32 elements per thread, fp64 from there on
 // (GroupNorm statistics of inputs up to ~110 in magnitude cancel badly in fp32).
+#include <stdlib.h>
 #include "common.cuh"
 #include "gn_coef.cuh"
 
@@ -383,23 +384,29 @@ __global__ void __launch_bounds__(TB)
 // super-elements per thread: RITER for big tensors (fewest atomics), fewer when the tensor is small
 // so that at least ~4 CTAs per SM share the work (deep U-Net levels are latency-, not HBM-bound)
 // `resident` (CTAs of this kernel that fit on the GPU at once, 0 = unknown): a grid of 4.6 waves
-// runs as long as one of 5, so for big tensors the per-thread trip count is stretched by up to
-// 25 % to make the grid a whole number of waves (bwd_reduce at 8 x 128^3: 2048 CTAs of 32 trips
-// = 4.61 waves -> 1776 CTAs of 37 trips = 4 waves).
+// runs as long as one of 5, so the per-thread trip count is stretched to make the grid a whole
+// number of waves whenever that is predicted to be faster (bwd_reduce at 8 x 128^3: 2048 CTAs of
+// 32 trips = 4.61 waves -> 1776 CTAs of 37 trips = 4 waves, 4.3 -> 4.6 TB/s; at 8 x 64^3 x 8 ch:
+// 608 CTAs of 27 trips = 1.37 waves -> 440 CTAs of 38 trips = 1 wave).
 static int reduce_iters(long long total_per_sample, int N, int zdim, int resident = 0) {
   const long long want_ctas = (long long)kNumSMs * 4;
   long long it = total_per_sample * N * zdim / (want_ctas * RB);
   if (it < 1) it = 1;
   if (it > RITER) it = RITER;
-  if (resident > 0 && it == RITER) {
+  static const bool whole_waves = [] {
+    const char* e = getenv("NAS3D_REDUCE_WAVES");    // A/B switch, default on
+    return !(e && e[0] == '0');
+  }();
+  if (whole_waves && resident > 0) {
     const long long nz = (long long)N * zdim;
     const long long ctas = ((total_per_sample + RB * it - 1) / (RB * it)) * nz;
-    const long long waves = ctas / resident;
-    if (waves >= 2 && ctas % resident != 0) {
-      const long long gx_max = waves * resident / nz;      // grid.x that fits `waves` whole waves
+    const long long w = ctas / resident;                   // whole waves
+    if (w >= 1 && ctas % resident != 0) {
+      const long long gx_max = w * resident / nz;          // grid.x that fits w whole waves
       if (gx_max >= 1) {
+        // w waves of it2 trips against w+1 waves of `it` trips
         const long long it2 = (total_per_sample + RB * gx_max - 1) / (RB * gx_max);
-        if (it2 > it && it2 * 4 <= it * 5) it = it2;
+        if (it2 > it && it2 * w < it * (w + 1) && it2 <= 2 * RITER) it = it2;
       }
     }
   }
