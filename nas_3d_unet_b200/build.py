@@ -39,6 +39,9 @@ VARIANTS = {
     "noffma2": ["-DNAS3D_NO_FFMA2"],      # scalar FFMA instead of packed FFMA2 (common.cuh)
     "pwminb4": ["-DNAS3D_PW_MINB=4"],     # pointwise kernels: register cap for 4 / 6 CTAs per SM
     "pwminb6": ["-DNAS3D_PW_MINB=6"],
+    # fused 1x1 backward: ring depth / CTAs per SM
+    "pbs6m3": ["-DNAS3D_PB_S=6", "-DNAS3D_PB_MINB=3"],
+    "pbs8m3": ["-DNAS3D_PB_S=8", "-DNAS3D_PB_MINB=3"],
 }
 
 

@@ -45,7 +45,16 @@ __device__ __forceinline__ T pb_pick4(const T (&a)[4], int i) {
 }
 
 constexpr int PB_T = 192;        // divisible by every supported Q (1,2,3,4,6,8,12,16)
-constexpr int PB_S = 6;          // cp.async ring depth (tiles in flight per thread: PB_S - 1)
+#ifndef NAS3D_PB_S
+#define NAS3D_PB_S 4
+#endif
+#ifndef NAS3D_PB_MINB
+#define NAS3D_PB_MINB 4
+#endif
+// cp.async ring depth (tiles in flight per thread: PB_S - 1) and CTAs per SM of the Cs <= 4
+// instantiations.  Measured (profiles/r1f_ab_pb_variants.txt): 4 stages x 4 CTAs 416.7 patches/s,
+// 6 x 3 415.1, 8 x 3 414.5 - the shallower ring leaves more of the SM's L1 to the dsmall reads.
+constexpr int PB_S = NAS3D_PB_S;
 constexpr int PB_MAX_CB = 64;
 
 __device__ __forceinline__ unsigned pb_smem(const void* p) {
@@ -70,7 +79,7 @@ __device__ __forceinline__ void pb_cp4(void* dst, const void* src) {
 // running pointer (+= constant), the per-(n,cb) scale is reloaded only at sample boundaries, and
 // the scalar dsmall path (the head: Cs = 3, pitch 3) is its own instantiation.
 template <int CS, bool DX, bool PROB, bool VEC>
-__global__ void __launch_bounds__(PB_T, CS == 4 ? 3 : 2) pw_bwd_fused_kernel(const __grid_constant__ PwBwdArgs A, int tiles_per_cta) {
+__global__ void __launch_bounds__(PB_T, CS == 4 ? NAS3D_PB_MINB : 2) pw_bwd_fused_kernel(const __grid_constant__ PwBwdArgs A, int tiles_per_cta) {
   extern __shared__ __align__(16) float4 ring[];   // [component][stage][thread]
   __shared__ float sW[CS * PB_MAX_CB];
   __shared__ float sB[CS];

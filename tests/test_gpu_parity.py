@@ -432,6 +432,8 @@ def test_dice_accepts_int8_masks():
         assert rel_err(pg.grad.cpu().numpy(), pr.grad.numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("dims", [(2, 5, 9, 11), (3, 2, 2, 3), (1, 1, 1, 1)],
+                         ids=["ragged", "samples-smaller-than-a-tile", "one-voxel"])
 @pytest.mark.parametrize("cb,cs,nparts,relu,scale,sigmoid,acc,want_dx", [
     (12, 4, 1, True, False, False, False, True),     # cell preprocess0 of the top up cell
     (12, 3, 3, False, True, True, False, True),      # the head: virtual concat, Dropout3d scale, sigmoid
@@ -442,7 +444,7 @@ def test_dice_accepts_int8_masks():
     (48, 8, 3, True, True, False, False, True),
     (12, 8, 3, False, False, False, False, False),   # weight / bias gradients only
 ])
-def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sigmoid, acc, want_dx):
+def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sigmoid, acc, want_dx, dims):
     """nas3d_conv1x1_bwd_fused (dgrad + wgrad + bias grad + sigmoid backward in one pass) through
     the C-ABI against the same op written with torch in fp64, on a ragged voxel count with pitched
     parts; tolerance 1e-5 (fp32 sums of ~1e3 terms)"""
@@ -452,7 +454,7 @@ def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sig
     lib = _lib.load()
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(cb * 7 + abs(cs))
-    N, D, H, W = 2, 5, 9, 11
+    N, D, H, W = dims
     nv = N * D * H * W
     sw = cb // nparts
     pitch = sw + 4      # parts are channel slices of wider buffers
