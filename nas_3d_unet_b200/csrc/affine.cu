@@ -6,6 +6,7 @@
 //
 // HBM-bound: one float4 (4 channels of one voxel) per thread per iteration, grid-stride,
 // grid = 148 SMs x 8 CTAs.  Per-(n,c) coefficients are tiny and stay in L1.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gn_coef.cuh"
 
@@ -96,6 +97,113 @@ __global__ void __launch_bounds__(256)
     if (B.S[k]) gn_coef_body(B, k, blockIdx.y, C, G, inv_m, eps, sc);
   __syncthreads();
   affine_sum_fwd_loop<true>(T, out, ld_out, V, C, C4, per_sample);
+}
+
+// Ring-staged forward for the big few-term sums (K <= 3): same element mapping and arithmetic, but
+// a thread's next AR_S-1 elements of every term are in flight as cp.async copies into its own
+// slots of a shared-memory ring (see reduce.cu / conv_pointwise_bwd.cu: the register-staged
+// streaming kernels are latency-bound at 5.0-5.2 TB/s).  gridDim.x * 256 is a multiple of C4, so
+// a thread's channel group is fixed and every address is a running pointer.
+constexpr int AR_S = 5;
+
+__device__ __forceinline__ void ar_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+    affine_sum_fwd_ring_kernel(const __grid_constant__ FwdTerms T, float* __restrict__ out,
+                               int ld_out, long long V, int C, int C4, unsigned per_sample) {
+  extern __shared__ __align__(16) float4 aring[];     // [term][stage][thread]
+  const int n = blockIdx.y;
+  const unsigned stride = gridDim.x * 256u;
+  const unsigned i0 = blockIdx.x * 256u + threadIdx.x;
+  const unsigned vox0 = i0 / (unsigned)C4;
+  const int c = (int)(i0 - vox0 * C4) * 4;
+  const unsigned vs = stride / (unsigned)C4;
+  const int trips = i0 < per_sample ? (int)((per_sample - i0 + stride - 1) / stride) : 0;
+  const long long nc = (long long)n * C + c;
+
+  const float* px[K];
+  long long sx[K];
+  float4 a[K], b[K];
+  float w[K];
+  bool relu[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    px[k] = T.x[k] + ((long long)n * V + vox0) * T.ld[k] + c;
+    sx[k] = (long long)vs * T.ld[k];
+    a[k] = T.a[k] ? ldg4(T.a[k] + nc) : make_float4(1.f, 1.f, 1.f, 1.f);
+    b[k] = T.b[k] ? ldg4(T.b[k] + nc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w[k] = T.w[k] ? __ldg(T.w[k]) : 1.f;
+    relu[k] = T.relu[k] != 0;
+  }
+  float* po = out + ((long long)n * V + vox0) * ld_out + c;
+  const long long so = (long long)vs * ld_out;
+
+  float4* const r0 = aring + threadIdx.x;
+  float4* const r_end = r0 + AR_S * 256;
+  float4* is = r0;
+  int issued = 0;
+  auto issue = [&]() {
+    if (issued < trips) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) ar_cp16(is + k * AR_S * 256, px[k]);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ++issued;
+#pragma unroll
+    for (int k = 0; k < K; ++k) px[k] += sx[k];
+    is += 256;
+    if (is == r_end) is = r0;
+  };
+#pragma unroll
+  for (int s = 0; s < AR_S - 1; ++s) issue();
+  const float4* cs = r0;
+#pragma unroll 1
+  for (int it = 0; it < trips; ++it) {
+    issue();
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(AR_S - 1) : "memory");
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float4 v = cs[k * AR_S * 256];
+      v.x *= a[k].x; v.y *= a[k].y; v.z *= a[k].z; v.w *= a[k].w;
+      v.x += b[k].x; v.y += b[k].y; v.z += b[k].z; v.w += b[k].w;
+      if (relu[k]) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      acc.x += w[k] * v.x; acc.y += w[k] * v.y; acc.z += w[k] * v.z; acc.w += w[k] * v.w;
+    }
+    st4(po, acc);
+    po += so;
+    cs += 256;
+    if (cs == r_end) cs = r0;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int K>
+static int launch_fwd_ring(const FwdTerms& T, float* out, int ld_out, int N, long long V, int C,
+                           int C4, long long per_sample, cudaStream_t st) {
+  auto kern = affine_sum_fwd_ring_kernel<K>;
+  const int smem = K * AR_S * 256 * (int)sizeof(float4);
+  static int resident = -1;
+  if (resident < 0) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, smem) != cudaSuccess || o < 1) o = 2;
+    resident = o * kNumSMs;
+  }
+  // one resident wave; gridDim.x * 256 must be a multiple of C4 (C4 is 3 or a power of two <= 256)
+  long long bx = resident / N;
+  const long long need = (per_sample + 255) / 256;
+  if (bx > need) bx = need;
+  if (C4 % 3 == 0) bx -= bx % 3;
+  if (bx < 1 || (bx * 256) % C4 != 0) return NAS3D_ERR_UNSUPPORTED;
+  kern<<<dim3((unsigned)bx, (unsigned)N), 256, smem, st>>>(T, out, ld_out, V, C, C4, (unsigned)per_sample);
+  return NAS3D_OK;
 }
 
 struct BwdTerms {
@@ -295,6 +403,16 @@ int nas3d_affine_sum_fwd(int nterms, const float* const* x, const int* ld_x,
   const int C4 = C / 4;
   const long long per_sample = V * C4;
   NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_fwd: sample too large for 32-bit indexing");
+  // NAS3D_AFFINE_RING=1: ring-staged kernel for big sums of <= 3 terms (A/B switch, read per call)
+  const char* ring_env = getenv("NAS3D_AFFINE_RING");
+  if (ring_env && ring_env[0] == '1' && nterms <= 3 && per_sample * N >= (1ll << 22) &&
+      (C4 == 3 || (C4 & (C4 - 1)) == 0) && C4 <= 256) {
+    int rc = nterms == 1 ? launch_fwd_ring<1>(T, out, ld_out, N, V, C, C4, per_sample, (cudaStream_t)stream)
+           : nterms == 2 ? launch_fwd_ring<2>(T, out, ld_out, N, V, C, C4, per_sample, (cudaStream_t)stream)
+                         : launch_fwd_ring<3>(T, out, ld_out, N, V, C, C4, per_sample, (cudaStream_t)stream);
+    if (rc == NAS3D_OK) return launched("affine_sum_fwd_ring");
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   affine_sum_fwd_kernel<<<grid2d(per_sample, N, 512), 256, 0, (cudaStream_t)stream>>>(
       T, out, ld_out, V, C, C4, (unsigned)per_sample);
   return launched("affine_sum_fwd");

@@ -204,6 +204,139 @@ __global__ void __launch_bounds__(RB)
 }
 
 // ---------------------------------------------------------------------------------------
+// Ring-staged variant of bwd_reduce for the big narrow tensors (C = 4*P <= 64, P a power of two):
+// same mapping, sums and epilogue, but the dout / x_k float4s of a thread's next RR_S-1 trips are
+// in flight as cp.async copies into the thread's own slots of a shared-memory ring (as in
+// conv_pointwise_bwd.cu) instead of being held in registers: this read-only kernel ran at
+// 4.3-4.6 TB/s with two trips in flight per thread (ncu: long_scoreboard), while the U = 3
+// instantiation, which has 2x the bytes in flight per thread, reaches 6.3 TB/s.
+// ---------------------------------------------------------------------------------------
+constexpr int RR_S = 5;
+
+__device__ __forceinline__ void rr_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int TG>
+__global__ void __launch_bounds__(RB)
+    bwd_reduce_ring_kernel(const __grid_constant__ ReduceTerms T, const float* __restrict__ dout,
+                           int ld_dout, long long V, int C, int P, int logP, int iters) {
+  extern __shared__ __align__(16) float4 rring[];      // [component][stage][thread]
+  __shared__ double sm[TG * 64 * 2];                   // C <= 64
+  const int n = blockIdx.y;
+  const int k0 = blockIdx.z * TG;
+  const long long total = V << logP;
+  const long long j0 = (long long)blockIdx.x * (RB * iters) + threadIdx.x;
+  const int p = threadIdx.x & (P - 1);
+  const int cbase = p * 4;
+  const int my_iters = j0 < total ? (int)min((long long)iters, (total - j0 + RB - 1) / RB) : 0;
+  const long long vox0 = j0 >> logP;                   // trip i reads voxel vox0 + i * (RB >> logP)
+  const long long vstep = RB >> logP;
+
+  bool live[TG], relu[TG];
+  float4 a4[TG], b4[TG];
+  const float* px[TG];
+  long long sx[TG];
+#pragma unroll
+  for (int t = 0; t < TG; ++t) {
+    const int k = k0 + t;
+    live[t] = k < T.nterms;
+    relu[t] = live[t] && T.relu[k];
+    a4[t] = make_float4(1.f, 1.f, 1.f, 1.f);
+    b4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    px[t] = nullptr; sx[t] = 0;
+    if (live[t]) {
+      px[t] = T.x[k] + ((long long)n * V + vox0) * T.ld[k] + cbase;
+      sx[t] = vstep * T.ld[k];
+      if (relu[t] && T.a[k]) a4[t] = ldg4(T.a[k] + (long long)n * C + cbase);
+      if (relu[t] && T.b[k]) b4[t] = ldg4(T.b[k] + (long long)n * C + cbase);
+    }
+  }
+  const float* pd = dout + ((long long)n * V + vox0) * ld_dout + cbase;
+  const long long sd = vstep * ld_dout;
+
+  float4* const r0 = rring + threadIdx.x;
+  float4* const r_end = r0 + RR_S * RB;
+  float4* is = r0;
+  int issued = 0;
+  auto issue = [&]() {
+    if (issued < my_iters) {
+      rr_cp16(is, pd);
+#pragma unroll
+      for (int t = 0; t < TG; ++t)
+        if (live[t]) rr_cp16(is + (1 + t) * RR_S * RB, px[t]);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ++issued;
+    pd += sd;
+#pragma unroll
+    for (int t = 0; t < TG; ++t) px[t] += sx[t];
+    is += RB;
+    if (is == r_end) is = r0;
+  };
+#pragma unroll
+  for (int s = 0; s < RR_S - 1; ++s) issue();
+
+  float r1[TG][4], r2[TG][4];
+#pragma unroll
+  for (int t = 0; t < TG; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r1[t][e] = r2[t][e] = 0.f;
+
+  const float4* cs = r0;
+#pragma unroll 1
+  for (int it = 0; it < my_iters; ++it) {
+    issue();
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(RR_S - 1) : "memory");
+    const float4 d4 = cs[0];
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int t = 0; t < TG; ++t) {
+      if (!live[t]) continue;
+      const float4 x4 = cs[(1 + t) * RR_S * RB];
+      const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float av[4] = {a4[t].x, a4[t].y, a4[t].z, a4[t].w};
+      const float bv[4] = {b4[t].x, b4[t].y, b4[t].z, b4[t].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float m = (!relu[t] || av[e] * x[e] + bv[e] > 0.f) ? d[e] : 0.f;
+        r1[t][e] += m;
+        r2[t][e] += m * x[e];
+      }
+    }
+    cs += RB;
+    if (cs == r_end) cs = r0;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < TG * C * 2; i += RB) sm[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < TG; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double a = r1[t][e], b = r2[t][e];
+      for (int o = 16; o >= P; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane < P || P > 32) {
+        const int c = cbase + e;
+        atomicAdd(&sm[(t * C + c) * 2 + 0], a);
+        atomicAdd(&sm[(t * C + c) * 2 + 1], b);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TG * C * 2; i += RB) {
+    const int t = i / (C * 2);
+    const int k = k0 + t;
+    if (k < T.nterms) atomicAdd(&T.R[k][(long long)n * C * 2 + (i - t * C * 2)], sm[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // tiny per-sample coefficient kernels: grid = N, block = 128
 // ---------------------------------------------------------------------------------------
 constexpr int TB = 128;
@@ -538,6 +671,26 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
   long long total = V * P;
   // TG=2 keeps the fp64 staging array (TG*C*2 doubles) inside 48 KB static smem for C<=768/..;
   // wide tensors are tiny in this network so TG=1 there.
+  // default on (NAS3D_REDUCE_RING=0: the register-staged kernel); read per call so tests can toggle.
+  // Measured on B200: affine_sum_bwd_reduce 2.14 -> 1.79 ms per searched-net step, 416.6 -> 420.7
+  // patches/s (profiles/r1f_ab_reduce_ring.json)
+  const char* ring_env = getenv("NAS3D_REDUCE_RING");
+  const bool use_ring = !(ring_env && ring_env[0] == '0');
+  if (use_ring && U == 1 && C <= 64 && total * N >= (1ll << 22)) {
+    auto kern = bwd_reduce_ring_kernel<2>;
+    const int smem = 3 * RR_S * RB * (int)sizeof(float4);
+    static int resident = -1;
+    if (resident < 0) {
+      NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int o = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, RB, smem) != cudaSuccess || o < 1) o = 0;
+      resident = o * kNumSMs;
+    }
+    const int zd = (nterms + 1) / 2, iters = reduce_iters(total, N, zd, resident);
+    dim3 grid((unsigned)((total + RB * iters - 1) / (RB * iters)), N, zd);
+    kern<<<grid, RB, smem, st>>>(T, dout, ld_dout, V, C, P, logP, iters);
+    return launched("affine_sum_bwd_reduce_ring");
+  }
   if (U == 1 && C <= 256) {
     static const int resident = resident_ctas(bwd_reduce_kernel<1, 2>, RB);
     const int zd = (nterms + 1) / 2, iters = reduce_iters(total, N, zd, resident);

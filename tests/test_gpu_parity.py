@@ -557,3 +557,88 @@ def test_folded_groupnorm_coefficients_equal_separate_kernels(net):
             os.environ.pop("NAS3D_GN_FOLD", None)
     assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
     assert O.max_rel(res["1"][1], res["0"][1]) <= 1e-5
+
+
+@pytest.mark.parametrize("c,ld", [(4, 4), (4, 8), (8, 8), (16, 16)])
+def test_ring_staged_backward_reduce_matches_torch(c, ld):
+    """NAS3D_REDUCE_RING=1: the cp.async-ring variant of nas3d_affine_sum_bwd_reduce (big narrow
+    tensors only) against the sums written with torch in fp64 and against the default kernel"""
+    import ctypes as C
+    import os
+    from nas_3d_unet_b200 import _lib
+    from nas_3d_unet_b200._lib import check, int_array, ptr_array
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(c + ld)
+    N, V = 2, 128 * 128 * 130 + 3            # >= 2^22 super-elements, ragged tail
+    x0 = torch.randn(N * V, ld, generator=g).to(dev)
+    x1 = torch.randn(N * V, ld, generator=g).to(dev)
+    dout = torch.randn(N * V, c, generator=g).to(dev)
+    a = (torch.rand(N, c, generator=g) + 0.5).to(dev)
+    b = (torch.randn(N, c, generator=g) * 0.3).to(dev)
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["NAS3D_REDUCE_RING"] = mode
+        try:
+            R = torch.full((2, N, c, 2), float("nan"), device=dev, dtype=torch.float64)
+            check(lib.nas3d_affine_sum_bwd_reduce(
+                2, ptr_array([x0.data_ptr(), x1.data_ptr()]), int_array([ld, ld]),
+                ptr_array([a.data_ptr(), None]), ptr_array([b.data_ptr(), None]), int_array([1, 0]),
+                dout.data_ptr(), c, ptr_array([R[0].data_ptr(), R[1].data_ptr()]), N, V, c,
+                torch.cuda.current_stream().cuda_stream), "affine_sum_bwd_reduce")
+            torch.cuda.synchronize()
+            out[mode] = R
+        finally:
+            os.environ.pop("NAS3D_REDUCE_RING", None)
+    d = dout.double().view(N, V, c)
+    xs = [x0[:, :c].double().view(N, V, c), x1[:, :c].double().view(N, V, c)]
+    m0 = (a.double()[:, None, :] * xs[0] + b.double()[:, None, :] > 0).double() * d
+    ref = torch.stack([torch.stack([m0.sum(1), (m0 * xs[0]).sum(1)], -1),
+                       torch.stack([d.sum(1), (d * xs[1]).sum(1)], -1)])
+    for mode in ("1", "0"):
+        assert O.max_rel(out[mode], ref) <= 2e-6, mode
+
+
+@pytest.mark.parametrize("k,c", [(1, 12), (2, 4), (3, 8), (2, 16)])
+def test_ring_staged_affine_sum_matches_default_kernel(k, c):
+    """NAS3D_AFFINE_RING=1: the cp.async-ring variant of nas3d_affine_sum_fwd (big sums of <= 3
+    terms) against the default kernel and against the same sum written with torch"""
+    import os
+    from nas_3d_unet_b200 import _lib
+    from nas_3d_unet_b200._lib import check, int_array, ptr_array
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(10 * k + c)
+    N, V = 2, 128 * 128 * 130 + 3
+    ld = c + 4
+    xs = [torch.randn(N * V, ld, generator=g).to(dev) for _ in range(k)]
+    a = [(torch.rand(N, c, generator=g) + 0.5).to(dev) if i != 1 else None for i in range(k)]
+    b = [(torch.randn(N, c, generator=g) * 0.3).to(dev) if i != 1 else None for i in range(k)]
+    w = [torch.rand(1, generator=g).to(dev) if i != 2 else None for i in range(k)]
+    relu = [1 if i != 1 else 0 for i in range(k)]
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["NAS3D_AFFINE_RING"] = mode
+        try:
+            o = torch.full((N * V, c), float("nan"), device=dev)
+            check(lib.nas3d_affine_sum_fwd(
+                k, ptr_array([x.data_ptr() for x in xs]), int_array([ld] * k),
+                ptr_array([t.data_ptr() if t is not None else None for t in a]),
+                ptr_array([t.data_ptr() if t is not None else None for t in b]),
+                ptr_array([t.data_ptr() if t is not None else None for t in w]),
+                int_array(relu), o.data_ptr(), c, N, V, c,
+                torch.cuda.current_stream().cuda_stream), "affine_sum_fwd")
+            torch.cuda.synchronize()
+            out[mode] = o
+        finally:
+            os.environ.pop("NAS3D_AFFINE_RING", None)
+    ref = torch.zeros(N, V, c, device=dev)
+    for i in range(k):
+        v = xs[i][:, :c].view(N, V, c)
+        if a[i] is not None:
+            v = v * a[i][:, None, :] + b[i][:, None, :]
+        if relu[i]:
+            v = v.clamp_min(0)
+        ref = ref + (w[i] if w[i] is not None else 1.0) * v
+    assert O.max_rel(out["1"], out["0"]) <= 1e-6
+    assert O.max_rel(out["1"], ref.view(N * V, c)) <= 1e-5
