@@ -314,6 +314,145 @@ __global__ void __launch_bounds__(256)
   affine_sum_bwd_apply_loop<true>(T, dout, ld_dout, V, C, C4, per_sample);
 }
 
+// Ring-staged backward apply for big sums of <= 2 terms (same staging as affine_sum_fwd_ring_kernel;
+// NOT YET MEASURED ON A B200 - off unless NAS3D_APPLY_RING=1).  Ring
+// components: dout | x_k of the terms that need x (relu mask or q) | old dx_k of the accumulating
+// terms.  The host only takes this path when no two terms share a dx buffer.
+template <int K>
+__global__ void __launch_bounds__(256)
+    affine_sum_bwd_apply_ring_kernel(const __grid_constant__ BwdTerms T, const float* __restrict__ dout,
+                                     int ld_dout, long long V, int C, int C4, unsigned per_sample) {
+  extern __shared__ __align__(16) float4 aring[];     // [component][stage][thread]
+  const int n = blockIdx.y;
+  const unsigned stride = gridDim.x * 256u;           // multiple of C4 (host)
+  const unsigned i0 = blockIdx.x * 256u + threadIdx.x;
+  const unsigned vox0 = i0 / (unsigned)C4;
+  const int c = (int)(i0 - vox0 * C4) * 4;
+  const unsigned vs = stride / (unsigned)C4;
+  const int trips = i0 < per_sample ? (int)((per_sample - i0 + stride - 1) / stride) : 0;
+  const long long nc = (long long)n * C + c;
+
+  const float* pd = dout + ((long long)n * V + vox0) * ld_dout + c;
+  const long long sd = (long long)vs * ld_dout;
+  const float* px[K];
+  float* pdx[K];
+  long long sx[K], sdx[K];
+  bool need_x[K], relu[K], acc[K], has_q[K], has_r[K];
+  int cx[K], cold[K];                                 // ring component of x_k / old dx_k
+  float4 a[K], b[K], pc[K], q[K], r[K];
+  int ncomp = 1;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    relu[k] = T.relu[k] != 0;
+    has_q[k] = T.q[k] != nullptr;
+    has_r[k] = T.r[k] != nullptr;
+    need_x[k] = relu[k] || has_q[k];
+    acc[k] = T.acc[k] != 0;
+    px[k] = need_x[k] ? T.x[k] + ((long long)n * V + vox0) * T.ld[k] + c : nullptr;
+    sx[k] = (long long)vs * T.ld[k];
+    pdx[k] = T.dx[k] + ((long long)n * V + vox0) * T.ld_dx[k] + c;
+    sdx[k] = (long long)vs * T.ld_dx[k];
+    a[k] = (relu[k] && T.a[k]) ? ldg4(T.a[k] + nc) : make_float4(1.f, 1.f, 1.f, 1.f);
+    b[k] = (relu[k] && T.b[k]) ? ldg4(T.b[k] + nc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (T.p[k]) {
+      pc[k] = ldg4(T.p[k] + nc);
+    } else {
+      const float w = T.w[k] ? __ldg(T.w[k]) : 1.f;
+      pc[k] = make_float4(w, w, w, w);
+    }
+    q[k] = has_q[k] ? ldg4(T.q[k] + nc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r[k] = has_r[k] ? ldg4(T.r[k] + nc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cx[k] = need_x[k] ? ncomp++ : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) cold[k] = acc[k] ? ncomp++ : 0;
+
+  float4* const r0 = aring + threadIdx.x;
+  float4* const r_end = r0 + AR_S * 256;
+  float4* is = r0;
+  int issued = 0;
+  const float* pold[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) pold[k] = pdx[k];
+  auto issue = [&]() {
+    if (issued < trips) {
+      ar_cp16(is, pd);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (need_x[k]) ar_cp16(is + cx[k] * AR_S * 256, px[k]);
+        if (acc[k]) ar_cp16(is + cold[k] * AR_S * 256, pold[k]);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ++issued;
+    pd += sd;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (need_x[k]) px[k] += sx[k];
+      pold[k] += sdx[k];
+    }
+    is += 256;
+    if (is == r_end) is = r0;
+  };
+#pragma unroll
+  for (int s = 0; s < AR_S - 1; ++s) issue();
+  const float4* cs = r0;
+#pragma unroll 1
+  for (int it = 0; it < trips; ++it) {
+    issue();
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(AR_S - 1) : "memory");
+    const float4 d = cs[0];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float4 g = d;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (need_x[k]) x = cs[cx[k] * AR_S * 256];
+      if (relu[k]) {
+        g.x = (a[k].x * x.x + b[k].x > 0.f) ? g.x : 0.f;
+        g.y = (a[k].y * x.y + b[k].y > 0.f) ? g.y : 0.f;
+        g.z = (a[k].z * x.z + b[k].z > 0.f) ? g.z : 0.f;
+        g.w = (a[k].w * x.w + b[k].w > 0.f) ? g.w : 0.f;
+      }
+      g.x *= pc[k].x; g.y *= pc[k].y; g.z *= pc[k].z; g.w *= pc[k].w;
+      if (has_q[k]) { g.x += q[k].x * x.x; g.y += q[k].y * x.y; g.z += q[k].z * x.z; g.w += q[k].w * x.w; }
+      if (has_r[k]) { g.x += r[k].x; g.y += r[k].y; g.z += r[k].z; g.w += r[k].w; }
+      if (acc[k]) {
+        const float4 o = cs[cold[k] * AR_S * 256];
+        g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+      }
+      st4(pdx[k], g);
+      pdx[k] += sdx[k];
+    }
+    cs += 256;
+    if (cs == r_end) cs = r0;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int K>
+static int launch_bwd_apply_ring(const BwdTerms& T, const float* dout, int ld_dout, int N, long long V,
+                                 int C, int C4, long long per_sample, cudaStream_t st) {
+  auto kern = affine_sum_bwd_apply_ring_kernel<K>;
+  int ncomp = 1;
+  for (int k = 0; k < K; ++k) ncomp += ((T.relu[k] || T.q[k]) ? 1 : 0) + (T.acc[k] ? 1 : 0);
+  const int smem = ncomp * AR_S * 256 * (int)sizeof(float4);
+  static int occ[2 * K + 2] = {0};     // by component count
+  if (occ[ncomp] == 0) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (2 * K + 1) * AR_S * 256 * (int)sizeof(float4)));
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, smem) != cudaSuccess || o < 1) o = 1;
+    occ[ncomp] = o;
+  }
+  long long bx = (long long)occ[ncomp] * kNumSMs / N;
+  const long long need = (per_sample + 255) / 256;
+  if (bx > need) bx = need;
+  if (C4 % 3 == 0) bx -= bx % 3;
+  if (bx < 1 || (bx * 256) % C4 != 0) return NAS3D_ERR_UNSUPPORTED;
+  kern<<<dim3((unsigned)bx, (unsigned)N), 256, smem, st>>>(T, dout, ld_dout, V, C, C4, (unsigned)per_sample);
+  return NAS3D_OK;
+}
+
 __global__ void __launch_bounds__(256)
     add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n4,
                        long long n) {
@@ -527,6 +666,16 @@ int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_
   const int C4 = C / 4;
   const long long per_sample = V * C4;
   NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_bwd_apply: sample too large");
+  // NAS3D_APPLY_RING=1: ring-staged kernel (not yet measured on a B200: opt-in, read per call)
+  const char* ring_env = getenv("NAS3D_APPLY_RING");
+  if (ring_env && ring_env[0] == '1' && nterms <= 2 && per_sample * N >= (1ll << 22) &&
+      (C4 == 3 || (C4 & (C4 - 1)) == 0) && C4 <= 256 && (nterms < 2 || T.dx[0] != T.dx[1])) {
+    int rc = nterms == 1
+                 ? launch_bwd_apply_ring<1>(T, dout, ld_dout, N, V, C, C4, per_sample, (cudaStream_t)stream)
+                 : launch_bwd_apply_ring<2>(T, dout, ld_dout, N, V, C, C4, per_sample, (cudaStream_t)stream);
+    if (rc == NAS3D_OK) return launched("affine_sum_bwd_apply_ring");
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   affine_sum_bwd_apply_kernel<<<grid2d(per_sample, N, 512), 256, 0, (cudaStream_t)stream>>>(
       T, dout, ld_dout, V, C, C4, (unsigned)per_sample);
   return launched("affine_sum_bwd_apply");

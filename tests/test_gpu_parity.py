@@ -642,3 +642,49 @@ def test_ring_staged_affine_sum_matches_default_kernel(k, c):
         ref = ref + (w[i] if w[i] is not None else 1.0) * v
     assert O.max_rel(out["1"], out["0"]) <= 1e-6
     assert O.max_rel(out["1"], ref.view(N * V, c)) <= 1e-5
+
+
+@pytest.mark.skipif(__import__("os").environ.get("NAS3D_TEST_UNVALIDATED") != "1",
+                    reason="opt-in kernel variant written after the round's GPU budget was spent; "
+                           "run with NAS3D_TEST_UNVALIDATED=1 before enabling NAS3D_APPLY_RING")
+@pytest.mark.parametrize("k,c,acc", [(1, 12, 0), (2, 4, 0), (2, 8, 1), (2, 16, 1)])
+def test_ring_staged_affine_bwd_apply_matches_default_kernel(k, c, acc):
+    """NAS3D_APPLY_RING=1 (opt-in): ring-staged nas3d_affine_sum_bwd_apply against the default kernel"""
+    import os
+    from nas_3d_unet_b200 import _lib
+    from nas_3d_unet_b200._lib import check, int_array, ptr_array
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(100 * k + c + acc)
+    N, V = 2, 128 * 128 * 130 + 3
+    ld = c + 4
+    xs = [torch.randn(N * V, ld, generator=g).to(dev) for _ in range(k)]
+    dout = torch.randn(N * V, c, generator=g).to(dev)
+    coef = lambda: torch.randn(N, c, generator=g).to(dev)
+    a, b, p, q, r = ([coef() for _ in range(k)] for _ in range(5))
+    w = torch.rand(1, generator=g).to(dev)
+    relu = [1, 0][:k]
+    dx0 = [torch.randn(N * V, ld, generator=g).to(dev) for _ in range(k)]
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["NAS3D_APPLY_RING"] = mode
+        try:
+            dx = [t.clone() for t in dx0]
+            check(lib.nas3d_affine_sum_bwd_apply(
+                k, ptr_array([x.data_ptr() for x in xs]), int_array([ld] * k),
+                ptr_array([t.data_ptr() for t in a]), ptr_array([t.data_ptr() for t in b]),
+                int_array(relu),
+                ptr_array([p[0].data_ptr()] + [None] * (k - 1)),      # term 1: weight instead of p
+                ptr_array([q[0].data_ptr()] + [None] * (k - 1)),
+                ptr_array([t.data_ptr() for t in r]),
+                ptr_array([None] + [w.data_ptr()] * (k - 1)),
+                ptr_array([t.data_ptr() for t in dx]), int_array([ld] * k), int_array([acc] * k),
+                dout.data_ptr(), c, N, V, c, torch.cuda.current_stream().cuda_stream),
+                "affine_sum_bwd_apply")
+            torch.cuda.synchronize()
+            out[mode] = dx
+        finally:
+            os.environ.pop("NAS3D_APPLY_RING", None)
+    for i in range(k):
+        assert torch.equal(out["1"][i][:, c:], dx0[i][:, c:])          # slice neighbours untouched
+        assert O.max_rel(out["1"][i][:, :c], out["0"][i][:, :c]) <= 1e-6
