@@ -531,6 +531,10 @@ static bool fill_segments(PwArgs* A, const PwCat* cat, int Cb) {
 int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
                   const float* scale, int relu, int sigmoid, float* small, int accumulate,
                   double* moments, cudaStream_t st, const PwCat* cat) {
+  if (!accumulate) {   // opt-in ring-staged kernel for the big stride-1 shapes (NAS3D_PW_FWD_RING=1)
+    const int rc = pointwise_sfb_ring(d, big, w, bias, scale, relu, sigmoid, small, moments, st, cat);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   // fused statistics need tiles that do not straddle samples
   if (moments) {
     const long long Vs = (long long)d->Ds * d->Hs * d->Ws;

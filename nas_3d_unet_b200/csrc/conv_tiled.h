@@ -70,6 +70,10 @@ struct PwCat {
 int pointwise_sfb(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
                   const float* scale, int relu, int sigmoid, float* small, int accumulate,
                   double* moments, cudaStream_t st, const PwCat* cat = nullptr);
+// opt-in ring-staged forward (conv_pointwise_fwd_ring.cu); NAS3D_ERR_UNSUPPORTED = not taken
+int pointwise_sfb_ring(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
+                       const float* scale, int relu, int sigmoid, float* small, double* moments,
+                       cudaStream_t st, const PwCat* cat);
 int pointwise_bfs(const nas3d_conv_desc* d, const float* small, const float* w, const float* bias,
                   const float* mask_big, int ld_mask, const float* scale, float* big,
                   int accumulate, cudaStream_t st, const PwCat* cat = nullptr);

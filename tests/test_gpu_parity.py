@@ -688,3 +688,62 @@ def test_ring_staged_affine_bwd_apply_matches_default_kernel(k, c, acc):
     for i in range(k):
         assert torch.equal(out["1"][i][:, c:], dx0[i][:, c:])          # slice neighbours untouched
         assert O.max_rel(out["1"][i][:, :c], out["0"][i][:, :c]) <= 1e-6
+
+
+@pytest.mark.skipif(__import__("os").environ.get("NAS3D_TEST_UNVALIDATED") != "1",
+                    reason="opt-in kernel variant written after the round's GPU budget was spent; "
+                           "run with NAS3D_TEST_UNVALIDATED=1 before enabling NAS3D_PW_FWD_RING")
+@pytest.mark.parametrize("cin,cout,nparts,relu,scale,sigmoid,stats", [
+    (4, 12, 1, False, False, False, True),     # stem0
+    (12, 4, 1, True, False, False, True),      # cell preprocess over a dense tensor
+    (12, 3, 3, False, True, True, False),      # the head over a virtual concat
+    (24, 4, 3, True, False, False, True),      # preprocess over a concat of 8-channel nodes
+    (12, 8, 1, True, False, False, True),
+])
+def test_ring_staged_pointwise_forward_matches_default_kernel(cin, cout, nparts, relu, scale, sigmoid, stats):
+    """NAS3D_PW_FWD_RING=1 (opt-in): ring-staged 1x1 forward against the default kernel, outputs and
+    fused GroupNorm moments"""
+    import ctypes as C
+    import os
+    from nas_3d_unet_b200 import _lib
+    from nas_3d_unet_b200._lib import ConvDesc, check, int_array, ptr_array
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(cin * 31 + cout)
+    N, D, H, W = 2, 64, 128, 128
+    nv = N * D * H * W
+    sw = cin // nparts
+    parts = [torch.randn(nv, sw, generator=g).to(dev) for _ in range(nparts)]
+    Wt = torch.randn(cout, cin, generator=g).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    sc = (torch.rand(N, cin, generator=g) * 2).to(dev) if scale else None
+    ldy = (cout + 3) // 4 * 4
+    d = ConvDesc()
+    d.N, d.Db, d.Hb, d.Wb, d.Cb, d.ld_big = N, D, H, W, cin, sw if nparts == 1 else cin
+    d.Ds, d.Hs, d.Ws, d.Cs, d.ld_small = D, H, W, cout, ldy
+    d.k, d.stride, d.dil, d.pad, d.depthwise = 1, 1, 1, 0, 0
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["NAS3D_PW_FWD_RING"] = mode
+        try:
+            y = torch.zeros(nv, ldy, device=dev)
+            S = torch.zeros(N, cout, 2, device=dev, dtype=torch.float64) if stats else None
+            if nparts == 1:
+                check(lib.nas3d_conv_small_from_big(
+                    C.byref(d), parts[0].data_ptr(), Wt.data_ptr(), bias.data_ptr(),
+                    sc.data_ptr() if scale else None, 1 if relu else 0, 1 if sigmoid else 0,
+                    y.data_ptr(), 0, S.data_ptr() if stats else None, st), "conv_small_from_big")
+            else:
+                check(lib.nas3d_conv1x1_cat_fwd(
+                    C.byref(d), nparts, ptr_array([p.data_ptr() for p in parts]), int_array([sw] * nparts),
+                    Wt.data_ptr(), bias.data_ptr(), sc.data_ptr() if scale else None,
+                    1 if relu else 0, 1 if sigmoid else 0, y.data_ptr(),
+                    S.data_ptr() if stats else None, st), "conv1x1_cat_fwd")
+            torch.cuda.synchronize()
+            res[mode] = (y[:, :cout].clone(), S)
+        finally:
+            os.environ.pop("NAS3D_PW_FWD_RING", None)
+    assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
+    if stats:
+        assert O.max_rel(res["1"][1], res["0"][1]) <= 1e-6
