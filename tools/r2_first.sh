@@ -19,3 +19,8 @@ print("bench [$cfg]", round(j["value"], 2), round(j["ms_per_step"], 3), round(j[
 PY
   i=$((i+1))
 done
+# L2 blocking over samples: does a smaller batch already run faster per patch?
+for b in 1 2 4; do
+  out=$(timeout 300 python bench.py --batch $b --steps 10 --warmup 3 --no-cpu-baseline --no-roofline 2>/dev/null | tail -1)
+  echo "batch $b => $(python -c "import json,sys; j=json.loads(sys.argv[1]); print(round(j['value'],2), 'patches/s', round(j['ms_per_step'],3), 'ms/step')" "$out")"
+done
