@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <atomic>
 #include "../../include/nas3d_b200.h"
@@ -166,6 +167,15 @@ __device__ __forceinline__ void cta_moments_flush(const double* sm, double* mome
                                                   int nthreads) {
   for (int i = threadIdx.x; i < 2 * C; i += nthreads)
     atomicAdd(&moments[(long long)n * C * 2 + i], sm[i]);
+}
+
+// smallest tensor (float4 elements per launch) the ring-staged streaming kernels take: 2^22 is what
+// was measured (batch 8 at 128^3 / 64^3); NAS3D_RING_MIN_LOG2 lowers it, e.g. to 21 for the
+// per-sample launches of NAS3D_SAMPLE_BLOCK=1
+static inline long long ring_min_elems() {
+  const char* e = getenv("NAS3D_RING_MIN_LOG2");
+  const int l = e ? atoi(e) : 22;
+  return 1ll << (l < 10 ? 10 : (l > 40 ? 40 : l));
 }
 
 // odd part / power-of-two part of the float4-group count of a channel dimension

@@ -676,7 +676,7 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
   // patches/s (profiles/r1f_ab_reduce_ring.json)
   const char* ring_env = getenv("NAS3D_REDUCE_RING");
   const bool use_ring = !(ring_env && ring_env[0] == '0');
-  if (use_ring && U == 1 && C <= 64 && total * N >= (1ll << 22)) {
+  if (use_ring && U == 1 && C <= 64 && total * N >= ring_min_elems()) {
     auto kern = bwd_reduce_ring_kernel<2>;
     const int smem = 3 * RR_S * RB * (int)sizeof(float4);
     static int resident = -1;

@@ -129,11 +129,12 @@ def _require_cuda(t, what):
 # ----------------------------------------------------------------------------------------
 class Act:
     __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad", "S", "bias_param",
-                 "bias_done")
+                 "bias_done", "fresh")
 
     def __init__(self, t, ld, requires_grad=True):
         self.t = t
         self.g = None
+        self.fresh = False   # g is a pre-bound, still unwritten buffer: the first producer overwrites
         self.S = None      # per-(n,c) fp64 {sum, sum^2} if a producer kernel already computed them
         self.bias_param = None   # bias of the conv that produced this tensor (GN-bwd yields its grad)
         self.bias_done = False
@@ -153,6 +154,9 @@ class Act:
         """(grad Act-like tensor, accumulate flag) for a producer of d(this)."""
         if self.g is None:
             self.g = alloc(self.N, self.C, self.D, self.H, self.W, self.t.device)
+            return self.g, 0
+        if self.fresh:
+            self.fresh = False
             return self.g, 0
         return self.g, 1
 
@@ -260,8 +264,17 @@ def as_act(t, requires_grad):
 def owned_grad(g, like, force_copy=False):
     """normalise an incoming gradient tensor to like's NDHWC layout"""
     ld = _ndhwc_pitch(g)
-    if ld is not None and not force_copy and g.data_ptr() % 16 == 0 and (ld % 4 == 0 or like.C % 4):
+    # an output stored at a padded pitch (the 3-channel head, new_act_padded) takes its gradient at
+    # the same pitch: the fused 1x1 backward reads both as aligned vectors
+    padded = like.ld != like.C
+    if (ld is not None and not force_copy and g.data_ptr() % 16 == 0 and (ld % 4 == 0 or like.C % 4)
+            and (not padded or ld == like.ld)):
         return g, ld
+    if padded:
+        buf = torch.empty((like.N, like.D, like.H, like.W, like.ld), device=g.device, dtype=torch.float32)
+        out = buf.permute(0, 4, 1, 2, 3)[:, :like.C]
+        out.copy_(g)
+        return out, like.ld
     out = alloc(like.N, like.C, like.D, like.H, like.W, g.device)
     out.copy_(g)
     return out, like.C
@@ -307,6 +320,9 @@ class ExecCtx:
         self.lanes = n_lanes()
         self.lane = 0
         self.dirty_lanes = set()
+        self.sample_index = None     # (n, N) while a per-sample section runs (run_per_sample)
+        self.dropout_cache = {}      # whole-batch Dropout3d scales drawn inside per-sample sections
+        self.next_conv_out = None    # one-shot: output Act of the next virtual-concat 1x1 conv
 
     def use(self, *params):
         for p in params:
@@ -615,6 +631,80 @@ def bind_concat(ctx, out, nodes, c_node):
 
 
 # ----------------------------------------------------------------------------------------
+# L2 blocking over samples.  NOT YET RUN ON A B200: opt-in with
+# NAS3D_SAMPLE_BLOCK=1, parity test behind NAS3D_TEST_UNVALIDATED=1.
+#
+# A 4-channel 128^3 activation of one sample is 33.5 MB and the L2 holds 126 MB, but with the whole
+# batch in every launch each tensor (268 MB at batch 8) streams through HBM between its producer and
+# its consumer.  run_per_sample() executes a section of the network (the last up cell + the head:
+# all 128^3 work of the U except the stem) sample by sample, so that within a sample a consumer
+# finds its inputs in L2.  GroupNorm statistics and the Dice loss are per-sample, so the arithmetic
+# is unchanged; parameter gradients accumulate over the samples in the flat bucket as before.
+# ----------------------------------------------------------------------------------------
+def sample_block_enabled():
+    return os.environ.get("NAS3D_SAMPLE_BLOCK", "0") == "1"
+
+
+def sample_view(act, n):
+    """sample n of a batched Act as an Act over the same memory"""
+    v = Act(act.t[n:n + 1], act.ld, act.requires_grad)
+    if act.S is not None:
+        v.S = act.S[n:n + 1]
+    return v
+
+
+def _split_samples(x, splits):
+    if isinstance(x, CatAct):
+        per_part = [_split_samples(p, splits) for p in x.parts]
+        return [CatAct([pp[n] for pp in per_part]) for n in range(x.N)]
+    views = [sample_view(x, n) for n in range(x.N)]
+    splits.append((x, views))
+    return views
+
+
+def run_per_sample(ctx, inputs, body, out):
+    """body(n, *per-sample inputs) runs once per sample; it must write sample n of `out` (a batched
+    Act; run_per_sample hands its sample views to body as the last argument).  Gradients: in the
+    backward the per-sample consumers run BEFORE the batched consumers of the same inputs (they
+    were recorded later), so the batched gradient buffers are allocated up front and every sample
+    view's gradient aliases its slice, the first write overwriting (Act.fresh)."""
+    N = inputs[0].N
+    splits = []
+
+    def zero_unwritten():      # runs after the section's backward: a slice nobody wrote is zero
+        for x, views in splits:
+            for v in views:
+                if v.fresh and v.g is not None:
+                    v.g.zero_()
+                    v.fresh = False
+    ctx.push(zero_unwritten)
+    per = [_split_samples(x, splits) for x in inputs]
+    out_views = [sample_view(out, n) for n in range(N)]
+    try:
+        for n in range(N):
+            ctx.sample_index = (n, N)
+            body(n, *[p[n] for p in per], out_views[n])
+    finally:
+        ctx.sample_index = None
+
+    def bind():                # runs first in the backward
+        if out.g is not None:
+            for n, v in enumerate(out_views):
+                v.g = out.g[n:n + 1]
+        for x, views in splits:
+            if not x.requires_grad:
+                continue
+            fresh = x.g is None
+            if fresh:
+                x.g = alloc(x.N, x.C, x.D, x.H, x.W, x.t.device)
+            for n, v in enumerate(views):
+                v.g = x.g[n:n + 1]
+                v.fresh = fresh
+    ctx.push(bind)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # GroupNorm / SE coefficient producers
 # ----------------------------------------------------------------------------------------
 def moments(ctx, x):
@@ -891,8 +981,13 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
     lib = ctx.lib
     ctx.use(m.weight, m.bias)
     mk = new_act_padded if (spec.stride == 1 and fused_pw_bwd_enabled()) else new_act
-    y = mk(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W),
-           ctx.device)
+    y, ctx.next_conv_out = ctx.next_conv_out, None
+    want = (x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W))
+    if y is None:
+        y = mk(*want, ctx.device)
+    elif (y.N, y.C, y.D, y.H, y.W) != want:
+        raise ValueError("preallocated conv output %s does not match %s"
+                         % ((y.N, y.C, y.D, y.H, y.W), want))
     S = None
     if stats:
         S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)

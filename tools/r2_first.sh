@@ -4,10 +4,11 @@
 #   gpurun --timeout 600 -- 'bash tools/r2_first.sh'
 mkdir -p gpurun_out
 NAS3D_TEST_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q \
-    -k "ring_staged_affine_bwd_apply or ring_staged_pointwise_forward" 2>&1 | tail -15
+    -k "ring_staged_affine_bwd_apply or ring_staged_pointwise_forward or sample_blocked" 2>&1 | tail -15
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 i=0
-for cfg in "X=1" "NAS3D_APPLY_RING=1" "NAS3D_PW_FWD_RING=1" "NAS3D_APPLY_RING=1 NAS3D_PW_FWD_RING=1"; do
+for cfg in "X=1" "NAS3D_APPLY_RING=1" "NAS3D_PW_FWD_RING=1" "NAS3D_APPLY_RING=1 NAS3D_PW_FWD_RING=1" \
+           "NAS3D_SAMPLE_BLOCK=1" "NAS3D_SAMPLE_BLOCK=1 NAS3D_RING_MIN_LOG2=21"; do
   env $cfg timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
       --profile-out gpurun_out/r2_first_prof$i.json > gpurun_out/r2_first_$i.json 2> gpurun_out/r2_first_$i.err
   python - <<PY
