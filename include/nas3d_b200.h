@@ -42,6 +42,18 @@ const char* nas3d_last_error(void);
 /* number of kernels this library has launched in this process (bench.py: gpu_launches) */
 unsigned long long nas3d_launch_count(void);
 
+/* Kernel-selection options (csrc/options.cu).  The reference has one code path per op; here
+ * several kernels may serve the same op (tiled vs generic gather, cp.async-ring vs register
+ * staging, TMA vs cp.async halo tiles) and every variant computes the same result - the parity
+ * tests flip these and compare.  The table is process-wide, read once from the environment
+ * (NAS3D_<UPPERCASE NAME>) when the library is loaded and changed afterwards only here; no launch
+ * path reads the environment.  Names: tiled, tma, tma_merged, affine_ring, apply_ring,
+ * reduce_ring, pw_fwd_ring, reduce_waves, ring_min_log2, pw_vpt_sfb, pw_vpt_bfs, pw_vpt_mom,
+ * wgrad_split.  set: 0 or NAS3D_ERR_ARG (unknown name / value out of range); get: the value
+ * (>= 0) or NAS3D_ERR_ARG. */
+int nas3d_set_option(const char* name, int value);
+int nas3d_get_option(const char* name);
+
 /* ---------------------------------------------------------------------------------------
  * Layout: NCDHW (what search.py:212 hands over) -> NDHWC with pitch ld_dst.
  * V = D*H*W.  C arbitrary.

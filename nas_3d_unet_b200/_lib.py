@@ -34,6 +34,8 @@ _SIGNATURES = {
     "nas3d_version": [],
     "nas3d_last_error": [],
     "nas3d_launch_count": [],
+    "nas3d_set_option": [C.c_char_p, c_int],
+    "nas3d_get_option": [C.c_char_p],
     "nas3d_ncdhw_to_ndhwc": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp],
     "nas3d_conv_small_from_big": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp,
                                   c_int, c_vp, c_vp],
@@ -129,6 +131,26 @@ def check(rc, what):
     if rc != 0:
         msg = load().nas3d_last_error()
         raise Nas3dError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+class option:
+    """context manager: run a block with one kernel-selection option of the library changed
+    (include/nas3d_b200.h: nas3d_set_option); parity tests A/B kernel variants with it"""
+
+    def __init__(self, name, value):
+        self.name, self.value = name.encode(), int(value)
+
+    def __enter__(self):
+        lib = load()
+        self.prev = lib.nas3d_get_option(self.name)
+        if self.prev < 0:
+            check(self.prev, "get_option(%s)" % self.name.decode())
+        check(lib.nas3d_set_option(self.name, self.value), "set_option(%s)" % self.name.decode())
+        return self
+
+    def __exit__(self, *exc):
+        check(load().nas3d_set_option(self.name, self.prev), "set_option")
+        return False
 
 
 def launch_count():

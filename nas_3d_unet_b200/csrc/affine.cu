@@ -542,11 +542,10 @@ int nas3d_affine_sum_fwd(int nterms, const float* const* x, const int* ld_x,
   const int C4 = C / 4;
   const long long per_sample = V * C4;
   NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_fwd: sample too large for 32-bit indexing");
-  // ring-staged kernel for big sums of <= 3 terms; default on (NAS3D_AFFINE_RING=0: the register-
-  // staged kernel), read per call so tests can toggle.  Measured on B200: affine_sum_fwd 1.62 -> 1.50
-  // ms per searched-net step, 420.7 -> 426.4 patches/s (profiles/r1f_ab_affine_ring.json)
-  const char* ring_env = getenv("NAS3D_AFFINE_RING");
-  if (!(ring_env && ring_env[0] == '0') && nterms <= 3 && per_sample * N >= ring_min_elems() &&
+  // ring-staged kernel for big sums of <= 3 terms (option affine_ring = 0: the register-staged
+  // kernel).  Measured on B200: affine_sum_fwd 1.62 -> 1.50 ms per searched-net step, 420.7 -> 426.4
+  // patches/s (profiles/r1f_ab_affine_ring.json)
+  if (g_opt.affine_ring && nterms <= 3 && per_sample * N >= ring_min_elems() &&
       (C4 == 3 || (C4 & (C4 - 1)) == 0) && C4 <= 256) {
     int rc = nterms == 1 ? launch_fwd_ring<1>(T, out, ld_out, N, V, C, C4, per_sample, (cudaStream_t)stream)
            : nterms == 2 ? launch_fwd_ring<2>(T, out, ld_out, N, V, C, C4, per_sample, (cudaStream_t)stream)
@@ -666,9 +665,9 @@ int nas3d_affine_sum_bwd_apply(int nterms, const float* const* x, const int* ld_
   const int C4 = C / 4;
   const long long per_sample = V * C4;
   NAS3D_REQUIRE(per_sample < (1ll << 31), "affine_sum_bwd_apply: sample too large");
-  // NAS3D_APPLY_RING=1: ring-staged kernel (not yet measured on a B200: opt-in, read per call)
-  const char* ring_env = getenv("NAS3D_APPLY_RING");
-  if (ring_env && ring_env[0] == '1' && nterms <= 2 && per_sample * N >= ring_min_elems() &&
+  // ring-staged kernel (option apply_ring = 0: the register-staged kernel).  Measured on B200:
+  // 426.9 -> 432.7 patches/s on the searched-net step (profiles/r2a_ab_optin_variants.txt)
+  if (g_opt.apply_ring && nterms <= 2 && per_sample * N >= ring_min_elems() &&
       (C4 == 3 || (C4 & (C4 - 1)) == 0) && C4 <= 256 && (nterms < 2 || T.dx[0] != T.dx[1])) {
     int rc = nterms == 1
                  ? launch_bwd_apply_ring<1>(T, dout, ld_dout, N, V, C, C4, per_sample, (cudaStream_t)stream)

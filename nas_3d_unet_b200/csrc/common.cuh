@@ -13,6 +13,22 @@ namespace nas3d {
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
 
+// kernel-selection options (options.cu): read once at load, changed only via nas3d_set_option
+struct Options {
+  int tiled = 1;          // specialised tiled / pointwise conv kernels (0: generic gather kernels)
+  int tma = 1;            // TMA halo staging in conv3_s1 (0: cp.async staging)
+  int tma_merged = 1;     // merged (W,C) inner dimension for dense C=4 TMA tiles
+  int affine_ring = 1;    // cp.async-ring variants of the streaming kernels (big, narrow tensors)
+  int apply_ring = 1;
+  int reduce_ring = 1;
+  int pw_fwd_ring = 1;
+  int reduce_waves = 1;   // whole-wave grid sizing of the backward reductions
+  int ring_min_log2 = 22; // smallest tensor (log2 float4 elements) the ring kernels take
+  int pw_vpt_sfb = 4, pw_vpt_bfs = 2, pw_vpt_mom = 2;   // voxels per thread of the 1x1 kernels
+  int wgrad_split = 0;    // 0 = automatic split of the deep-level wgrad reductions
+};
+extern Options g_opt;
+
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -170,13 +186,8 @@ __device__ __forceinline__ void cta_moments_flush(const double* sm, double* mome
 }
 
 // smallest tensor (float4 elements per launch) the ring-staged streaming kernels take: 2^22 is what
-// was measured (batch 8 at 128^3 / 64^3); NAS3D_RING_MIN_LOG2 lowers it, e.g. to 21 for the
-// per-sample launches of NAS3D_SAMPLE_BLOCK=1
-static inline long long ring_min_elems() {
-  const char* e = getenv("NAS3D_RING_MIN_LOG2");
-  const int l = e ? atoi(e) : 22;
-  return 1ll << (l < 10 ? 10 : (l > 40 ? 40 : l));
-}
+// was measured (batch 8 at 128^3 / 64^3); option ring_min_log2
+static inline long long ring_min_elems() { return 1ll << g_opt.ring_min_log2; }
 
 // odd part / power-of-two part of the float4-group count of a channel dimension
 static inline void split_c4(int C4, int* U, int* P) {

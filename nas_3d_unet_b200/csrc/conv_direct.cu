@@ -16,10 +16,7 @@
 
 namespace nas3d {
 
-static bool tiled_enabled() {
-  const char* e = getenv("NAS3D_DISABLE_TILED");   // read per call so tests can A/B the paths
-  return !(e && e[0] == '1');
-}
+static bool tiled_enabled() { return g_opt.tiled != 0; }   // option: parity tests A/B the paths
 static bool pointwise_shape(const nas3d_conv_desc* d) {
   return tiled_enabled() && d->k == 1 && !d->depthwise && d->pad == 0;
 }

@@ -459,20 +459,13 @@ static void launch_pointwise_vpt(const PwArgs& A, unsigned gy, long long nvox, c
   pointwise_kernel<CO, SRC_IS_BIG, VPT, MOM><<<dim3(gx, gy), PW_T, 0, st>>>(A);
 }
 
-static int pw_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 template <int CO, bool SRC_IS_BIG, bool MOM>
 static void launch_pointwise_co(const PwArgs& A, unsigned gy, cudaStream_t st) {
   const long long nvox = (long long)A.N * A.Ds * A.Hs * A.Ws;
   // big tensors: several voxels per thread, one resident wave of CTAs striding over the tiles;
   // small (deep-level) tensors: 1 voxel per thread, one tile per CTA - they are latency-bound
   if (pointwise_big(nvox)) {
-    static const int vpt_sfb = pw_env("NAS3D_PW_VPT_SFB", 4), vpt_bfs = pw_env("NAS3D_PW_VPT_BFS", 2);
-    static const int vpt_mom = pw_env("NAS3D_PW_VPT_MOM", 2);
-    const int vpt = MOM ? vpt_mom : (SRC_IS_BIG ? vpt_sfb : vpt_bfs);
+    const int vpt = MOM ? g_opt.pw_vpt_mom : (SRC_IS_BIG ? g_opt.pw_vpt_sfb : g_opt.pw_vpt_bfs);
     if (vpt == 1) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 1>(A, gy, nvox, st);
     else if (vpt == 2) launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 2>(A, gy, nvox, st);
     else launch_pointwise_vpt<CO, SRC_IS_BIG, MOM, 4>(A, gy, nvox, st);

@@ -233,8 +233,9 @@ static int pr_launch_m(const PwRingArgs& A, cudaStream_t st) {
 int pointwise_sfb_ring(const nas3d_conv_desc* d, const float* big, const float* w, const float* bias,
                        const float* scale, int relu, int sigmoid, float* small, double* moments,
                        cudaStream_t st, const PwCat* cat) {
-  const char* e = getenv("NAS3D_PW_FWD_RING");       // opt-in until measured (read per call)
-  if (!(e && e[0] == '1')) return NAS3D_ERR_UNSUPPORTED;
+  // measured on B200: conv1x1_cat_fwd 0.79 -> 0.70 ms per searched-net step
+  // (profiles/r2a_ab_optin_variants.txt); option pw_fwd_ring = 0: pointwise_kernel
+  if (!g_opt.pw_fwd_ring) return NAS3D_ERR_UNSUPPORTED;
   if (d->k != 1 || d->stride != 1 || d->pad != 0 || d->depthwise) return NAS3D_ERR_UNSUPPORTED;
   if (d->Db != d->Ds || d->Hb != d->Hs || d->Wb != d->Ws) return NAS3D_ERR_UNSUPPORTED;
   const long long nvox = (long long)d->N * d->Ds * d->Hs * d->Ws;

@@ -439,10 +439,8 @@ static EncodeTiledFn encode_tiled_fn() {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
-    const char* e = getenv("NAS3D_DISABLE_TMA");
-    if (e && e[0] == '1') fn = nullptr;
   }
-  return fn;
+  return g_opt.tma ? fn : nullptr;
 }
 
 // 5-D map of an NDHWC fp32 tensor {C, W, H, D, N} with voxel pitch ld, box {4, bw, bh, bd, 1}
@@ -464,8 +462,7 @@ static bool make_ndhwc_map(CUtensorMap* m, const float* base, int C, int W, int 
 static bool make_ndhwc4_merged_map(CUtensorMap* m, const float* base, int W, int H, int D, int N,
                                    int bw, int bh, int bd) {
   EncodeTiledFn enc = encode_tiled_fn();
-  const char* e = getenv("NAS3D_TMA_MERGED");
-  if (!enc || (e && e[0] == '0') || 4 * bw > 256) return false;
+  if (!enc || !g_opt.tma_merged || 4 * bw > 256) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
   const cuuint32_t box[4] = {(cuuint32_t)(4 * bw), (cuuint32_t)bh, (cuuint32_t)bd, 1};

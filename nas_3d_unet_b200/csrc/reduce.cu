@@ -526,10 +526,7 @@ static int reduce_iters(long long total_per_sample, int N, int zdim, int residen
   long long it = total_per_sample * N * zdim / (want_ctas * RB);
   if (it < 1) it = 1;
   if (it > RITER) it = RITER;
-  static const bool whole_waves = [] {
-    const char* e = getenv("NAS3D_REDUCE_WAVES");    // A/B switch, default on
-    return !(e && e[0] == '0');
-  }();
+  const bool whole_waves = g_opt.reduce_waves != 0;
   if (whole_waves && resident > 0) {
     const long long nz = (long long)N * zdim;
     const long long ctas = ((total_per_sample + RB * it - 1) / (RB * it)) * nz;
@@ -671,11 +668,10 @@ int nas3d_affine_sum_bwd_reduce(int nterms, const float* const* x, const int* ld
   long long total = V * P;
   // TG=2 keeps the fp64 staging array (TG*C*2 doubles) inside 48 KB static smem for C<=768/..;
   // wide tensors are tiny in this network so TG=1 there.
-  // default on (NAS3D_REDUCE_RING=0: the register-staged kernel); read per call so tests can toggle.
+  // option reduce_ring = 0: the register-staged kernel.
   // Measured on B200: affine_sum_bwd_reduce 2.14 -> 1.79 ms per searched-net step, 416.6 -> 420.7
   // patches/s (profiles/r1f_ab_reduce_ring.json)
-  const char* ring_env = getenv("NAS3D_REDUCE_RING");
-  const bool use_ring = !(ring_env && ring_env[0] == '0');
+  const bool use_ring = g_opt.reduce_ring != 0;
   if (use_ring && U == 1 && C <= 64 && total * N >= ring_min_elems()) {
     auto kern = bwd_reduce_ring_kernel<2>;
     const int smem = 3 * RR_S * RB * (int)sizeof(float4);

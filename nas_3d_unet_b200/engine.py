@@ -16,12 +16,11 @@ Vocabulary
 """
 import ctypes as C
 
-import os
-
 import torch
 
 from . import _lib
 from ._lib import ConvDesc, check, int_array, ptr_array
+from .config import cfg
 
 
 class Nas3dDeviceError(RuntimeError):
@@ -37,11 +36,11 @@ _side_streams = {}
 
 def wgrad_stream_enabled():
     """weight-gradient kernels run on a second stream, concurrent with the dgrad / node-backward
-    chain that does not depend on them (NAS3D_WGRAD_STREAM=0 puts everything on one stream)"""
+    chain that does not depend on them (config.cfg.wgrad_stream)"""
     from . import profiling
     if profiling._active is not None:     # per-kernel event timing wants one stream
         return False
-    return os.environ.get("NAS3D_WGRAD_STREAM", "1") != "0"
+    return cfg.wgrad_stream
 
 
 def _side_stream(device, which=0):
@@ -53,12 +52,12 @@ def _side_stream(device, which=0):
 
 
 def n_lanes():
-    """streams the independent edges of a cell node are spread over (NAS3D_LANES, default 4;
+    """streams the independent edges of a cell node are spread over (config.cfg.lanes, default 4;
     1 = everything on the caller's stream)"""
     from . import profiling
     if profiling._active is not None:
         return 1
-    return max(1, min(4, int(os.environ.get("NAS3D_LANES", "4"))))
+    return cfg.lanes
 
 
 class _Laned:
@@ -129,12 +128,11 @@ def _require_cuda(t, what):
 # ----------------------------------------------------------------------------------------
 class Act:
     __slots__ = ("t", "g", "N", "C", "D", "H", "W", "ld", "requires_grad", "S", "bias_param",
-                 "bias_done", "fresh")
+                 "bias_done")
 
     def __init__(self, t, ld, requires_grad=True):
         self.t = t
         self.g = None
-        self.fresh = False   # g is a pre-bound, still unwritten buffer: the first producer overwrites
         self.S = None      # per-(n,c) fp64 {sum, sum^2} if a producer kernel already computed them
         self.bias_param = None   # bias of the conv that produced this tensor (GN-bwd yields its grad)
         self.bias_done = False
@@ -155,9 +153,6 @@ class Act:
         if self.g is None:
             self.g = alloc(self.N, self.C, self.D, self.H, self.W, self.t.device)
             return self.g, 0
-        if self.fresh:
-            self.fresh = False
-            return self.g, 0
         return self.g, 1
 
     def slice(self, c0, c1):
@@ -166,8 +161,7 @@ class Act:
 
 
 def virtual_cat_enabled():
-    import os
-    return os.environ.get("NAS3D_VIRTUAL_CAT", "1") != "0"
+    return cfg.virtual_cat
 
 
 class CatAct:
@@ -320,9 +314,6 @@ class ExecCtx:
         self.lanes = n_lanes()
         self.lane = 0
         self.dirty_lanes = set()
-        self.sample_index = None     # (n, N) while a per-sample section runs (run_per_sample)
-        self.dropout_cache = {}      # whole-batch Dropout3d scales drawn inside per-sample sections
-        self.next_conv_out = None    # one-shot: output Act of the next virtual-concat 1x1 conv
 
     def use(self, *params):
         for p in params:
@@ -352,7 +343,7 @@ class ExecCtx:
     # ---- backward side -------------------------------------------------------------
     def begin_backward(self):
         self.stream = _stream()
-        nside = int(os.environ.get("NAS3D_WGRAD_STREAMS", "1")) if wgrad_stream_enabled() else 0
+        nside = cfg.wgrad_streams if wgrad_stream_enabled() else 0
         # weight-gradient streams (round-robin): keys 100.. keep them apart from the branch lanes
         self.side = [_side_stream(self.device, 100 + i) for i in range(max(0, min(4, nside)))]
         self.side_next = 0
@@ -421,12 +412,12 @@ def _tp(t):
 
 
 def gn_fold_enabled():
-    """NAS3D_GN_FOLD=1: the GroupNorm coefficient kernels are folded into the affine kernels'
+    """cfg.gn_fold: the GroupNorm coefficient kernels are folded into the affine kernels'
     prologues (94 fewer launches per searched-net step).  Off by default: measured on B200 it is
     SLOWER (406 vs 414 patches/s, profiles/r1f_ab_gn_fold_*.json) - the separate 5 us coefficient
     kernels overlap with other stream lanes, while a prologue of dependent fp64 loads / rsqrt /
     two block barriers delays the first load of every CTA of the one-wave streaming kernels."""
-    return os.environ.get("NAS3D_GN_FOLD", "0") == "1"
+    return cfg.gn_fold
 
 
 def _take_gn_jobs(ctx, terms, out):
@@ -631,80 +622,6 @@ def bind_concat(ctx, out, nodes, c_node):
 
 
 # ----------------------------------------------------------------------------------------
-# L2 blocking over samples.  NOT YET RUN ON A B200: opt-in with
-# NAS3D_SAMPLE_BLOCK=1, parity test behind NAS3D_TEST_UNVALIDATED=1.
-#
-# A 4-channel 128^3 activation of one sample is 33.5 MB and the L2 holds 126 MB, but with the whole
-# batch in every launch each tensor (268 MB at batch 8) streams through HBM between its producer and
-# its consumer.  run_per_sample() executes a section of the network (the last up cell + the head:
-# all 128^3 work of the U except the stem) sample by sample, so that within a sample a consumer
-# finds its inputs in L2.  GroupNorm statistics and the Dice loss are per-sample, so the arithmetic
-# is unchanged; parameter gradients accumulate over the samples in the flat bucket as before.
-# ----------------------------------------------------------------------------------------
-def sample_block_enabled():
-    return os.environ.get("NAS3D_SAMPLE_BLOCK", "0") == "1"
-
-
-def sample_view(act, n):
-    """sample n of a batched Act as an Act over the same memory"""
-    v = Act(act.t[n:n + 1], act.ld, act.requires_grad)
-    if act.S is not None:
-        v.S = act.S[n:n + 1]
-    return v
-
-
-def _split_samples(x, splits):
-    if isinstance(x, CatAct):
-        per_part = [_split_samples(p, splits) for p in x.parts]
-        return [CatAct([pp[n] for pp in per_part]) for n in range(x.N)]
-    views = [sample_view(x, n) for n in range(x.N)]
-    splits.append((x, views))
-    return views
-
-
-def run_per_sample(ctx, inputs, body, out):
-    """body(n, *per-sample inputs) runs once per sample; it must write sample n of `out` (a batched
-    Act; run_per_sample hands its sample views to body as the last argument).  Gradients: in the
-    backward the per-sample consumers run BEFORE the batched consumers of the same inputs (they
-    were recorded later), so the batched gradient buffers are allocated up front and every sample
-    view's gradient aliases its slice, the first write overwriting (Act.fresh)."""
-    N = inputs[0].N
-    splits = []
-
-    def zero_unwritten():      # runs after the section's backward: a slice nobody wrote is zero
-        for x, views in splits:
-            for v in views:
-                if v.fresh and v.g is not None:
-                    v.g.zero_()
-                    v.fresh = False
-    ctx.push(zero_unwritten)
-    per = [_split_samples(x, splits) for x in inputs]
-    out_views = [sample_view(out, n) for n in range(N)]
-    try:
-        for n in range(N):
-            ctx.sample_index = (n, N)
-            body(n, *[p[n] for p in per], out_views[n])
-    finally:
-        ctx.sample_index = None
-
-    def bind():                # runs first in the backward
-        if out.g is not None:
-            for n, v in enumerate(out_views):
-                v.g = out.g[n:n + 1]
-        for x, views in splits:
-            if not x.requires_grad:
-                continue
-            fresh = x.g is None
-            if fresh:
-                x.g = alloc(x.N, x.C, x.D, x.H, x.W, x.t.device)
-            for n, v in enumerate(views):
-                v.g = x.g[n:n + 1]
-                v.fresh = fresh
-    ctx.push(bind)
-    return out
-
-
-# ----------------------------------------------------------------------------------------
 # GroupNorm / SE coefficient producers
 # ----------------------------------------------------------------------------------------
 def moments(ctx, x):
@@ -829,12 +746,10 @@ def _umma_enabled(d):
     """tcgen05 path policy (measured, tools/umma_micro.py): it wins 2.5-5x over the CUDA-core
     kernels from 32 channels up; at 16 channels the tiled FFMA kernel is still ahead for
     stride 1, while the stride-2 dilation-1 tiled kernels stop at 8 channels."""
-    import os
-    if os.environ.get("NAS3D_DISABLE_UMMA", "0") == "1":
+    if not cfg.umma:
         return False
-    floor = os.environ.get("NAS3D_UMMA_MIN_C")
-    if floor is not None:
-        return d.Cb >= int(floor)
+    if cfg.umma_min_c is not None:
+        return d.Cb >= cfg.umma_min_c
     return d.Cb >= (16 if (d.stride == 2 and d.dil == 1) else 32)
 
 
@@ -981,13 +896,7 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
     lib = ctx.lib
     ctx.use(m.weight, m.bias)
     mk = new_act_padded if (spec.stride == 1 and fused_pw_bwd_enabled()) else new_act
-    y, ctx.next_conv_out = ctx.next_conv_out, None
-    want = (x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W))
-    if y is None:
-        y = mk(*want, ctx.device)
-    elif (y.N, y.C, y.D, y.H, y.W) != want:
-        raise ValueError("preallocated conv output %s does not match %s"
-                         % ((y.N, y.C, y.D, y.H, y.W), want))
+    y = mk(x.N, spec.cout, spec.out_extent(x.D), spec.out_extent(x.H), spec.out_extent(x.W), ctx.device)
     S = None
     if stats:
         S = torch.empty((y.N, y.C, 2), device=ctx.device, dtype=torch.float64)
@@ -1042,9 +951,9 @@ def _conv_cat(ctx, x, m, spec, in_relu, in_scale, sigmoid, stats):
 
 
 def fused_pw_bwd_enabled():
-    """1x1x1 stride-1 convs: dgrad + wgrad (+ sigmoid backward) in one pass (NAS3D_PW_FUSED_BWD=0:
-    the separate kernels)"""
-    return os.environ.get("NAS3D_PW_FUSED_BWD", "1") != "0"
+    """1x1x1 stride-1 convs: dgrad + wgrad (+ sigmoid backward) in one pass (cfg.pw_fused_bwd =
+    False: the separate kernels)"""
+    return cfg.pw_fused_bwd
 
 
 def _pw_bwd_fused(ctx, d, parts, y, m, in_relu, in_scale, sigmoid):

@@ -78,16 +78,6 @@ class BaseOp(nn.Module):
         if self.dropout is None or not ctx.training or self.dropout.p == 0:
             return None
         p = self.dropout.p
-        if ctx.sample_index is not None:
-            # per-sample section of a batched call (engine.run_per_sample): the mask is drawn once
-            # for the whole batch - the same draw the batched path makes - and sliced per sample
-            n, N = ctx.sample_index
-            full = ctx.dropout_cache.get(id(self))
-            if full is None:
-                noise = torch.empty((N, x.C, 1, 1, 1), device=ctx.device, dtype=torch.float32)
-                full = (noise.zero_() if p >= 1 else noise.bernoulli_(1 - p).div_(1 - p)).view(N, x.C)
-                ctx.dropout_cache[id(self)] = full
-            return full[n:n + 1]
         noise = torch.empty((x.N, x.C, 1, 1, 1), device=ctx.device, dtype=torch.float32)
         if p >= 1:
             return noise.zero_().view(x.N, x.C)

@@ -108,26 +108,9 @@ class SearchedNet(nn.Module):
             for s in skips:
                 print((s.N, s.C, s.D, s.H, s.W))
         skips.pop()
-        cells = list(self.up_cells)
-        # opt-in L2 blocking over samples (engine.run_per_sample): the last up cell and the head -
-        # all 128^3 work of the U except the stem - run sample by sample
-        blocked = (engine.sample_block_enabled() and x.N > 1 and engine.virtual_cat_enabled()
-                   and engine.fused_pw_bwd_enabled() and len(cells) >= 1)
-        for cell in (cells[:-1] if blocked else cells):
+        for cell in self.up_cells:
             s0 = skips.pop()
             s1 = cell._run(ctx, s0, s1, virtual_cat=engine.virtual_cat_enabled())
             if FLAG_DEBUG:
                 print((s1.N, s1.C, s1.D, s1.H, s1.W))
-        if not blocked:
-            return engine.materialize(ctx, self.last_conv[0]._run(ctx, s1, sigmoid=True))
-        s0 = skips.pop()
-        head = self.last_conv[0]
-        out = engine.new_act_padded(x.N, head._specs[0].cout, s0.D, s0.H, s0.W, ctx.device)
-
-        def body(n, a, b, out_n):
-            y = cells[-1]._run(ctx, a, b, virtual_cat=True)
-            ctx.next_conv_out = out_n
-            t = head._run(ctx, y, sigmoid=True)
-            if ctx.next_conv_out is not None or t.x is not out_n or not t.is_identity:
-                raise RuntimeError("sample-blocked head did not write its preallocated output")
-        return engine.run_per_sample(ctx, [s0, s1], body, out)
+        return engine.materialize(ctx, self.last_conv[0]._run(ctx, s1, sigmoid=True))

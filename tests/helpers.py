@@ -67,3 +67,27 @@ def rel_err(a, b):
 
 def gene_to_json(g):
     return json.dumps({'down': [list(t) for t in g.down], 'up': [list(t) for t in g.up]})
+
+
+class variant:
+    """run a block with kernel-selection options changed: engine options (config.EngineConfig
+    fields) and C-ABI library options (nas3d_set_option) by name"""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        import contextlib
+        from nas_3d_unet_b200 import _lib, config
+        self.stack = contextlib.ExitStack()
+        eng = {k: v for k, v in self.kw.items() if k in config.EngineConfig.__slots__}
+        if eng:
+            self.stack.enter_context(config.override(**eng))
+        for k, v in self.kw.items():
+            if k not in eng:
+                self.stack.enter_context(_lib.option(k, int(v)))
+        return self
+
+    def __exit__(self, *exc):
+        self.stack.close()
+        return False

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import nas3d_oracle as O
-from helpers import make_prim, make_searched, make_supernet, prim_inputs, rel_err, tstats
+from helpers import make_prim, make_searched, make_supernet, prim_inputs, rel_err, tstats, variant
 
 pytestmark = pytest.mark.gpu
 
@@ -216,7 +216,6 @@ def test_searched_net_training_mode_dropout_is_torch_rng_compatible():
 def test_tiled_conv_kernels_match_oracle_on_ragged_volume(c, dil):
     """the tiled stride-1 3x3x3 kernels (fwd / dgrad / wgrad) on extents that are not multiples
     of the tile, against the oracle; also cross-checked against the generic gather kernels"""
-    import os
     from nas_3d_unet_b200.prim_ops import ConvOps
     torch.manual_seed(c * 10 + dil)
     op = ConvOps(c, c, dilation=dil, ops_order='weight')
@@ -230,16 +229,13 @@ def test_tiled_conv_kernels_match_oracle_on_ragged_volume(c, dil):
     op = op.cuda()
     outs = {}
     for mode in ("tiled", "generic"):
-        os.environ["NAS3D_DISABLE_TILED"] = "1" if mode == "generic" else "0"
-        try:
+        with variant(tiled=0 if mode == "generic" else 1):
             op.zero_grad()
             xg = x.cuda().requires_grad_(True)
             y = op(xg)
             (y * r.cuda()).sum().backward()
             outs[mode] = (y.detach().cpu(), xg.grad.cpu(), op.conv.weight.grad.cpu().clone(),
                           op.conv.bias.grad.cpu().clone())
-        finally:
-            os.environ["NAS3D_DISABLE_TILED"] = "0"
     for mode, (y, dx, dw, db) in outs.items():
         assert O.max_rel(y, yr) <= 1e-5, mode
         assert O.max_rel(dx, xr.grad) <= 1e-5, mode
@@ -254,7 +250,6 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
     """tensor-core path (tcgen05 kind::tf32 + 3xTF32 compensation, TMEM accumulators) for the
     wide layers: forward and dgrad of every conv flavour against the fp32 oracle at fp32-grade
     tolerance, and against the CUDA-core path"""
-    import os
     from nas_3d_unet_b200.prim_ops import ConvOps
     torch.manual_seed(c + 7 * stride + dil)
     op = ConvOps(c, c, stride=stride, dilation=dil, transposed=transposed, ops_order='weight')
@@ -268,21 +263,17 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
     (yr * r).sum().backward()
     op = op.cuda()
     from nas_3d_unet_b200 import profiling
-    os.environ["NAS3D_UMMA_MIN_C"] = "16"
     for mode in ("umma", "ffma"):
-        os.environ["NAS3D_DISABLE_UMMA"] = "1" if mode == "ffma" else "0"
         prof = profiling.enable()
         try:
-            op.zero_grad()
-            xg = x.cuda().requires_grad_(True)
-            y = op(xg)
-            (y * r.cuda()).sum().backward()
+            with variant(umma_min_c=16, umma=(mode == "umma")):
+                op.zero_grad()
+                xg = x.cuda().requires_grad_(True)
+                y = op(xg)
+                (y * r.cuda()).sum().backward()
             names = [rec[0] for rec in prof.records]
         finally:
             profiling.disable()
-            os.environ["NAS3D_DISABLE_UMMA"] = "0"
-            if mode == "ffma":
-                os.environ.pop("NAS3D_UMMA_MIN_C", None)
         assert ("nas3d_umma_conv" in names) == (mode == "umma"), names
         assert tuple(y.shape) == tuple(yr.shape)
         assert O.max_rel(y, yr) <= 2e-5, (mode, O.max_rel(y, yr))
@@ -294,7 +285,6 @@ def test_tcgen05_stride2_dgrad_on_odd_extents_uses_tap_order():
     """odd input extents (Db != 2*Ds): the stride-2 dgrad cannot use the parity-class
     decomposition; the pre-packed class-order operand must be ignored and the tap-order one
     packed on demand"""
-    import os
     from nas_3d_unet_b200.prim_ops import ConvOps
     torch.manual_seed(11)
     c = 16
@@ -308,16 +298,15 @@ def test_tcgen05_stride2_dgrad_on_odd_extents_uses_tap_order():
     (yr * r).sum().backward()
     op = op.cuda()
     from nas_3d_unet_b200 import profiling
-    os.environ["NAS3D_UMMA_MIN_C"] = "16"
     prof = profiling.enable()
     try:
-        xg = x.cuda().requires_grad_(True)
-        y = op(xg)
-        (y * r.cuda()).sum().backward()
+        with variant(umma_min_c=16):
+            xg = x.cuda().requires_grad_(True)
+            y = op(xg)
+            (y * r.cuda()).sum().backward()
         names = [rec[0] for rec in prof.records]
     finally:
         profiling.disable()
-        os.environ.pop("NAS3D_UMMA_MIN_C", None)
     assert names.count("nas3d_umma_conv") == 2, names
     assert "nas3d_umma_pack_weights" in names and "nas3d_umma_pack_weights_batch" in names, names
     assert O.max_rel(y, yr) <= 2e-5
@@ -329,7 +318,6 @@ def test_tcgen05_stride2_dgrad_on_odd_extents_uses_tap_order():
 def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
     """stride-2 dilation-1 tiled kernels (down_conv / up_conv / stem1 family): fwd, dgrad, wgrad
     on tile-ragged extents against the oracle and the generic gather kernels"""
-    import os
     from nas_3d_unet_b200.prim_ops import ConvOps
     torch.manual_seed(cin * 3 + cout + transposed)
     op = ConvOps(cin, cout, stride=2, transposed=transposed, ops_order='weight')
@@ -343,14 +331,11 @@ def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
     (yr * r).sum().backward()
     op = op.cuda()
     for mode in ("tiled", "generic"):
-        os.environ["NAS3D_DISABLE_TILED"] = "1" if mode == "generic" else "0"
-        try:
+        with variant(tiled=0 if mode == "generic" else 1):
             op.zero_grad()
             xg = x.cuda().requires_grad_(True)
             y = op(xg)
             (y * r.cuda()).sum().backward()
-        finally:
-            os.environ["NAS3D_DISABLE_TILED"] = "0"
         assert O.max_rel(y, yr) <= 1e-5, mode
         assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
         assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
@@ -394,7 +379,6 @@ def test_cuda_graph_step_matches_eager_steps():
 def test_tiled_depthwise_kernels_match_oracle(c, stride, transposed):
     """depthwise-separable ops (dep_conv / down_dep_conv / up_dep_conv): tiled depthwise kernels
     (fwd, dgrad, wgrad) + pointwise conv, ragged extents, against the oracle and the generic path"""
-    import os
     from nas_3d_unet_b200.prim_ops import ConvOps
     torch.manual_seed(c * 5 + stride + transposed)
     op = ConvOps(c, c, stride=stride, transposed=transposed, depthwised=True, ops_order='weight')
@@ -408,14 +392,11 @@ def test_tiled_depthwise_kernels_match_oracle(c, stride, transposed):
     (yr * r).sum().backward()
     op = op.cuda()
     for mode in ("tiled", "generic"):
-        os.environ["NAS3D_DISABLE_TILED"] = "1" if mode == "generic" else "0"
-        try:
+        with variant(tiled=0 if mode == "generic" else 1):
             op.zero_grad()
             xg = x.cuda().requires_grad_(True)
             y = op(xg)
             (y * r.cuda()).sum().backward()
-        finally:
-            os.environ["NAS3D_DISABLE_TILED"] = "0"
         assert O.max_rel(y, yr) <= 1e-5, mode
         assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
         for k in ('depth_conv.weight', 'depth_conv.bias', 'point_conv.weight', 'point_conv.bias'):
@@ -523,55 +504,46 @@ def test_fused_pointwise_backward_matches_torch(cb, cs, nparts, relu, scale, sig
 
 
 def test_fused_pointwise_backward_equals_separate_kernels_in_the_net():
-    """searched-net gradients with the fused 1x1 backward on and off (NAS3D_PW_FUSED_BWD)"""
-    import os
+    """searched-net gradients with the fused 1x1 backward on and off (engine option pw_fused_bwd)"""
     from nas_3d_unet_b200.loss import WeightedDiceLoss
     x, y = O.synthetic_batch(1, 32, seed=3)
     grads = {}
     for mode in ("1", "0"):
-        os.environ["NAS3D_PW_FUSED_BWD"] = mode
-        try:
+        with variant(pw_fused_bwd=int(mode)):
             model = make_searched().cuda()
             model.train()
             torch.manual_seed(11)
             loss = WeightedDiceLoss()(model(x.cuda()), y.cuda())
             loss.backward()
             grads[mode] = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-        finally:
-            os.environ["NAS3D_PW_FUSED_BWD"] = "1"
     assert O.max_rel(grads["1"], grads["0"]) <= REORDER_TOL
 
 
 @pytest.mark.parametrize("net", ["searched", "supernet"])
 def test_folded_groupnorm_coefficients_equal_separate_kernels(net):
-    """NAS3D_GN_FOLD: the affine kernels deriving the GroupNorm coefficients (forward a, b;
+    """engine option gn_fold: the affine kernels deriving the GroupNorm coefficients (forward a, b;
     backward p, q, r and the parameter gradients) in their prologue against the separate
     coefficient kernels: same outputs and gradients (both paths run the same device functions)"""
-    import os
     from nas_3d_unet_b200.loss import WeightedDiceLoss
     x, y = O.synthetic_batch(2, 32, seed=5)
     res = {}
     for mode in ("1", "0"):
-        os.environ["NAS3D_GN_FOLD"] = mode
-        try:
+        with variant(gn_fold=int(mode)):
             model = (make_searched() if net == "searched" else make_supernet(dropout0=True)).cuda()
             pred = model(x.cuda())
             loss = WeightedDiceLoss()(pred, y.cuda())
             loss.backward()
             res[mode] = (pred.detach().clone(),
                          torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
-        finally:
-            os.environ.pop("NAS3D_GN_FOLD", None)
     assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
     assert O.max_rel(res["1"][1], res["0"][1]) <= REORDER_TOL
 
 
 @pytest.mark.parametrize("c,ld", [(4, 4), (4, 8), (8, 8), (16, 16)])
 def test_ring_staged_backward_reduce_matches_torch(c, ld):
-    """NAS3D_REDUCE_RING=1: the cp.async-ring variant of nas3d_affine_sum_bwd_reduce (big narrow
+    """library option reduce_ring: the cp.async-ring variant of nas3d_affine_sum_bwd_reduce (big narrow
     tensors only) against the sums written with torch in fp64 and against the default kernel"""
     import ctypes as C
-    import os
     from nas_3d_unet_b200 import _lib
     from nas_3d_unet_b200._lib import check, int_array, ptr_array
     lib = _lib.load()
@@ -585,8 +557,7 @@ def test_ring_staged_backward_reduce_matches_torch(c, ld):
     b = (torch.randn(N, c, generator=g) * 0.3).to(dev)
     out = {}
     for mode in ("1", "0"):
-        os.environ["NAS3D_REDUCE_RING"] = mode
-        try:
+        with variant(reduce_ring=int(mode)):
             R = torch.full((2, N, c, 2), float("nan"), device=dev, dtype=torch.float64)
             check(lib.nas3d_affine_sum_bwd_reduce(
                 2, ptr_array([x0.data_ptr(), x1.data_ptr()]), int_array([ld, ld]),
@@ -595,8 +566,6 @@ def test_ring_staged_backward_reduce_matches_torch(c, ld):
                 torch.cuda.current_stream().cuda_stream), "affine_sum_bwd_reduce")
             torch.cuda.synchronize()
             out[mode] = R
-        finally:
-            os.environ.pop("NAS3D_REDUCE_RING", None)
     d = dout.double().view(N, V, c)
     xs = [x0[:, :c].double().view(N, V, c), x1[:, :c].double().view(N, V, c)]
     m0 = (a.double()[:, None, :] * xs[0] + b.double()[:, None, :] > 0).double() * d
@@ -608,9 +577,8 @@ def test_ring_staged_backward_reduce_matches_torch(c, ld):
 
 @pytest.mark.parametrize("k,c", [(1, 12), (2, 4), (3, 8), (2, 16)])
 def test_ring_staged_affine_sum_matches_default_kernel(k, c):
-    """NAS3D_AFFINE_RING=1: the cp.async-ring variant of nas3d_affine_sum_fwd (big sums of <= 3
+    """library option affine_ring: the cp.async-ring variant of nas3d_affine_sum_fwd (big sums of <= 3
     terms) against the default kernel and against the same sum written with torch"""
-    import os
     from nas_3d_unet_b200 import _lib
     from nas_3d_unet_b200._lib import check, int_array, ptr_array
     lib = _lib.load()
@@ -625,8 +593,7 @@ def test_ring_staged_affine_sum_matches_default_kernel(k, c):
     relu = [1 if i != 1 else 0 for i in range(k)]
     out = {}
     for mode in ("1", "0"):
-        os.environ["NAS3D_AFFINE_RING"] = mode
-        try:
+        with variant(affine_ring=int(mode)):
             o = torch.full((N * V, c), float("nan"), device=dev)
             check(lib.nas3d_affine_sum_fwd(
                 k, ptr_array([x.data_ptr() for x in xs]), int_array([ld] * k),
@@ -637,8 +604,6 @@ def test_ring_staged_affine_sum_matches_default_kernel(k, c):
                 torch.cuda.current_stream().cuda_stream), "affine_sum_fwd")
             torch.cuda.synchronize()
             out[mode] = o
-        finally:
-            os.environ.pop("NAS3D_AFFINE_RING", None)
     ref = torch.zeros(N, V, c, device=dev)
     for i in range(k):
         v = xs[i][:, :c].view(N, V, c)
@@ -651,13 +616,9 @@ def test_ring_staged_affine_sum_matches_default_kernel(k, c):
     assert O.max_rel(out["1"], ref.view(N * V, c)) <= 1e-5
 
 
-@pytest.mark.skipif(__import__("os").environ.get("NAS3D_TEST_UNVALIDATED") != "1",
-                    reason="opt-in kernel variant written after the round's GPU budget was spent; "
-                           "run with NAS3D_TEST_UNVALIDATED=1 before enabling NAS3D_APPLY_RING")
 @pytest.mark.parametrize("k,c,acc", [(1, 12, 0), (2, 4, 0), (2, 8, 1), (2, 16, 1)])
 def test_ring_staged_affine_bwd_apply_matches_default_kernel(k, c, acc):
-    """NAS3D_APPLY_RING=1 (opt-in): ring-staged nas3d_affine_sum_bwd_apply against the default kernel"""
-    import os
+    """library option apply_ring: ring-staged nas3d_affine_sum_bwd_apply against the default kernel"""
     from nas_3d_unet_b200 import _lib
     from nas_3d_unet_b200._lib import check, int_array, ptr_array
     lib = _lib.load()
@@ -674,8 +635,7 @@ def test_ring_staged_affine_bwd_apply_matches_default_kernel(k, c, acc):
     dx0 = [torch.randn(N * V, ld, generator=g).to(dev) for _ in range(k)]
     out = {}
     for mode in ("1", "0"):
-        os.environ["NAS3D_APPLY_RING"] = mode
-        try:
+        with variant(apply_ring=int(mode)):
             dx = [t.clone() for t in dx0]
             check(lib.nas3d_affine_sum_bwd_apply(
                 k, ptr_array([x.data_ptr() for x in xs]), int_array([ld] * k),
@@ -690,16 +650,11 @@ def test_ring_staged_affine_bwd_apply_matches_default_kernel(k, c, acc):
                 "affine_sum_bwd_apply")
             torch.cuda.synchronize()
             out[mode] = dx
-        finally:
-            os.environ.pop("NAS3D_APPLY_RING", None)
     for i in range(k):
         assert torch.equal(out["1"][i][:, c:], dx0[i][:, c:])          # slice neighbours untouched
         assert O.max_rel(out["1"][i][:, :c], out["0"][i][:, :c]) <= 1e-6
 
 
-@pytest.mark.skipif(__import__("os").environ.get("NAS3D_TEST_UNVALIDATED") != "1",
-                    reason="opt-in kernel variant written after the round's GPU budget was spent; "
-                           "run with NAS3D_TEST_UNVALIDATED=1 before enabling NAS3D_PW_FWD_RING")
 @pytest.mark.parametrize("cin,cout,nparts,relu,scale,sigmoid,stats", [
     (4, 12, 1, False, False, False, True),     # stem0
     (12, 4, 1, True, False, False, True),      # cell preprocess over a dense tensor
@@ -708,10 +663,9 @@ def test_ring_staged_affine_bwd_apply_matches_default_kernel(k, c, acc):
     (12, 8, 1, True, False, False, True),
 ])
 def test_ring_staged_pointwise_forward_matches_default_kernel(cin, cout, nparts, relu, scale, sigmoid, stats):
-    """NAS3D_PW_FWD_RING=1 (opt-in): ring-staged 1x1 forward against the default kernel, outputs and
+    """library option pw_fwd_ring: ring-staged 1x1 forward against the default kernel, outputs and
     fused GroupNorm moments"""
     import ctypes as C
-    import os
     from nas_3d_unet_b200 import _lib
     from nas_3d_unet_b200._lib import ConvDesc, check, int_array, ptr_array
     lib = _lib.load()
@@ -732,8 +686,7 @@ def test_ring_staged_pointwise_forward_matches_default_kernel(cin, cout, nparts,
     st = torch.cuda.current_stream().cuda_stream
     res = {}
     for mode in ("1", "0"):
-        os.environ["NAS3D_PW_FWD_RING"] = mode
-        try:
+        with variant(pw_fwd_ring=int(mode)):
             y = torch.zeros(nv, ldy, device=dev)
             S = torch.zeros(N, cout, 2, device=dev, dtype=torch.float64) if stats else None
             if nparts == 1:
@@ -749,8 +702,6 @@ def test_ring_staged_pointwise_forward_matches_default_kernel(cin, cout, nparts,
                     S.data_ptr() if stats else None, st), "conv1x1_cat_fwd")
             torch.cuda.synchronize()
             res[mode] = (y[:, :cout].clone(), S)
-        finally:
-            os.environ.pop("NAS3D_PW_FWD_RING", None)
     assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
     if stats:
         assert O.max_rel(res["1"][1], res["0"][1]) <= 1e-6
@@ -778,32 +729,3 @@ def test_any_loss_backpropagates_through_the_pitched_head():
         grads.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
     assert float(grads[0].abs().max()) > 0
     assert O.max_rel(grads[0], grads[1]) <= REORDER_TOL
-
-
-@pytest.mark.skipif(__import__("os").environ.get("NAS3D_TEST_UNVALIDATED") != "1",
-                    reason="opt-in execution mode written after the round's GPU budget was spent; "
-                           "run with NAS3D_TEST_UNVALIDATED=1 before enabling NAS3D_SAMPLE_BLOCK")
-@pytest.mark.parametrize("train", [False, True])
-def test_sample_blocked_searched_net_equals_batched(train):
-    """NAS3D_SAMPLE_BLOCK=1 (opt-in): last up cell + head run sample by sample (L2 blocking); same
-    predictions, loss and gradients as the batched walk, with the same Dropout3d draw"""
-    import os
-    from nas_3d_unet_b200.loss import WeightedDiceLoss
-    x, y = O.synthetic_batch(3, 32, seed=9)
-    res = {}
-    for mode in ("1", "0"):
-        os.environ["NAS3D_SAMPLE_BLOCK"] = mode
-        try:
-            model = make_searched().cuda()
-            model.train(train)
-            torch.manual_seed(21)
-            pred = model(x.cuda())
-            loss = WeightedDiceLoss()(pred, y.cuda())
-            loss.backward()
-            res[mode] = (pred.detach().clone(), loss.item(),
-                         torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
-        finally:
-            os.environ.pop("NAS3D_SAMPLE_BLOCK", None)
-    assert O.max_rel(res["1"][0], res["0"][0]) <= 1e-6
-    assert abs(res["1"][1] - res["0"][1]) <= 1e-6
-    assert O.max_rel(res["1"][2], res["0"][2]) <= REORDER_TOL

@@ -2,15 +2,16 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-os.environ["NAS3D_UMMA_MIN_C"] = "16"
+from nas_3d_unet_b200 import config
 from nas_3d_unet_b200.prim_ops import ConvOps
+config.cfg.umma_min_c = 16
 
 def bench(c, s, n=8, stride=1, dil=1, transposed=False, iters=20):
     op = ConvOps(c, c, stride=stride, dilation=dil, transposed=transposed, ops_order='weight').cuda()
     x = torch.randn(n, c, s, s, s, device='cuda').contiguous(memory_format=torch.channels_last_3d)
     res = {}
     for mode in ("umma", "ffma"):
-        os.environ["NAS3D_DISABLE_UMMA"] = "1" if mode == "ffma" else "0"
+        config.cfg.umma = (mode == "umma")
         with torch.no_grad():
             for _ in range(3):
                 y = op(x)
@@ -22,7 +23,7 @@ def bench(c, s, n=8, stride=1, dil=1, transposed=False, iters=20):
             e1.record()
             torch.cuda.synchronize()
         res[mode] = e0.elapsed_time(e1) / iters * 1e3
-    os.environ["NAS3D_DISABLE_UMMA"] = "0"
+    config.cfg.umma = True
     flops = 2.0 * y.numel() * c * 27 if not transposed else 2.0 * x.numel() * c * 27
     print("C=%d S=%d stride=%d dil=%d T=%d: umma %.1f us (%.1f TF)  ffma %.1f us (%.1f TF)" % (
         c, s, stride, dil, transposed, res["umma"], flops / res["umma"] / 1e6, res["ffma"], flops / res["ffma"] / 1e6))
