@@ -324,15 +324,23 @@ int nas3d_add_inplace(float* y, const float* x, long long n, void* stream);
  * bit-exact with the reference's numpy code (same accumulation order).
  *   extract_patches: volume [C][D][H][W] fp32 + corners [B][3] int32 (device) -> NDHWC batch
  *                    [B][Pd][Ph][Pw][ld_out], zeros outside the volume
- *   stitch_labels  : preds [B][Pd][Ph][Pw][ld_pred] (3 channels) -> uint8 labels [D][H][W]
- *                    (mean of overlaps in fp64, >= threshold, {1,2,4} assembly, * skull mask,
- *                    pasted at (off_d,off_h,off_w)); optional fp64 stitched [3][Db][Hb][Wb]
+ *   patch_nonzero  : flags[b] = 1 iff patch b holds a non-zero voxel (the `np.all(data==0)` test of
+ *                    prediction.py:133, on the device: no host sync in the patch loop)
+ *   stitch_labels  : patch_preds_dev = DEVICE table of B pointers, patch b = [Pd][Ph][Pw][ld_pred]
+ *                    (3 channels; patches may live in different buffers - per forward batch, or
+ *                    per rank after an all-gather) -> uint8 labels [D][H][W] (mean of overlaps in
+ *                    fp64 in patch order, >= threshold, {1,2,4} assembly, * skull mask, pasted at
+ *                    (off_d,off_h,off_w)); patch_nonzero_dev (or NULL): a patch with flag 0 counts
+ *                    as an all-zero prediction (prediction.py:134); optional fp64 stitched
+ *                    [3][Db][Hb][Wb]
  *   seg_to_masks   : int16 [N][V] -> fp32 [N][3][V] region masks
  * ------------------------------------------------------------------------------------- */
 int nas3d_extract_patches(const float* volume, int C, int D, int H, int W, const int* corners_dev,
                           int B, int Pd, int Ph, int Pw, float* out, int ld_out, void* stream);
-int nas3d_stitch_labels(const float* preds, int ld_pred, const int* corners_dev, int B, int Pd, int Ph,
-                        int Pw, int Db, int Hb, int Wb, int D, int H, int W, int off_d, int off_h,
+int nas3d_patch_nonzero(const float* volume, int C, int D, int H, int W, const int* corners_dev, int B,
+                        int Pd, int Ph, int Pw, int* flags, void* stream);
+int nas3d_stitch_labels(const float* const* patch_preds_dev, const int* patch_nonzero_dev, int ld_pred,
+                        const int* corners_dev, int B, int Pd, int Ph, int Pw, int Db, int Hb, int Wb, int D, int H, int W, int off_d, int off_h,
                         int off_w, float threshold, int inclusive, const unsigned char* skull_mask,
                         unsigned char* labels, double* stitched, void* stream);
 int nas3d_seg_to_masks(const short* seg, int N, long long V, int inclusive, float* masks, void* stream);

@@ -92,7 +92,8 @@ _SIGNATURES = {
                        c_ll, C.c_float, c_vp],
     "nas3d_extract_patches": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp,
                               c_int, c_vp],
-    "nas3d_stitch_labels": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    "nas3d_patch_nonzero": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "nas3d_stitch_labels": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_int, c_int, C.c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     "nas3d_seg_to_masks": [c_vp, c_int, c_ll, c_int, c_vp, c_vp],
     "nas3d_sigmoid_bwd": [c_vp, c_vp, c_vp, c_ll, c_vp],

@@ -32,8 +32,33 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// patch_nonzero[b] = 1 iff patch b of the volume holds any non-zero voxel (prediction.py:133: an
+// all-zero patch is not run through the net, its prediction is DEFINED as zeros).  One CTA-strided
+// pass; flags must be zeroed by the caller.
+__global__ void __launch_bounds__(256)
+    patch_nonzero_kernel(const float* __restrict__ vol, int C, int D, int H, int W,
+                         const int* __restrict__ corners, int Pd, int Ph, int Pw,
+                         int* __restrict__ flags, long long per_patch) {
+  const int b = blockIdx.y;
+  const int c0 = corners[b * 3 + 0], c1 = corners[b * 3 + 1], c2 = corners[b * 3 + 2];
+  bool any = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_patch && !any;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int pw = (int)(t % Pw); t /= Pw;
+    const int ph = (int)(t % Ph);
+    const int pd = (int)(t / Ph);
+    const int gd = c0 + pd, gh = c1 + ph, gw = c2 + pw;
+    if (gd < 0 || gd >= D || gh < 0 || gh >= H || gw < 0 || gw >= W) continue;
+    const long long v = ((long long)gd * H + gh) * W + gw;
+    for (int c = 0; c < C; ++c) any |= (__ldg(vol + (long long)c * D * H * W + v) != 0.f);
+  }
+  if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) atomicOr(flags + b, 1);
+}
+
 struct StitchArgs {
-  const float* preds;      // [B][Pd][Ph][Pw][ldp], 3 channels used
+  const float* const* preds;   // [B] device table: patch b = [Pd][Ph][Pw][ldp], 3 channels used
+  const int* nonzero;          // [B] or NULL: 0 = the patch prediction counts as all zeros
   const int* corners;      // [B][3] in brain coordinates (may be negative)
   int B, Pd, Ph, Pw, ldp;
   int Db, Hb, Wb;          // brain box
@@ -62,9 +87,10 @@ __global__ void __launch_bounds__(256) stitch_labels_kernel(const StitchArgs A, 
         const int pd = bd - A.corners[b * 3 + 0], ph = bh - A.corners[b * 3 + 1],
                   pw = bw - A.corners[b * 3 + 2];
         if (pd < 0 || pd >= A.Pd || ph < 0 || ph >= A.Ph || pw < 0 || pw >= A.Pw) continue;
-        const float* p = A.preds + ((((long long)b * A.Pd + pd) * A.Ph + ph) * A.Pw + pw) * A.ldp;
-        s0 += (double)__ldg(p); s1 += (double)__ldg(p + 1); s2 += (double)__ldg(p + 2);
         ++cnt;
+        if (A.nonzero && !A.nonzero[b]) continue;       // += 0.0: an exact no-op on the sums
+        const float* p = A.preds[b] + (((long long)pd * A.Ph + ph) * A.Pw + pw) * A.ldp;
+        s0 += (double)__ldg(p); s1 += (double)__ldg(p + 1); s2 += (double)__ldg(p + 2);
       }
       const double c = cnt ? (double)cnt : 1.0;
       const double m0 = s0 / c, m1 = s1 / c, m2 = s2 / c;
@@ -212,14 +238,30 @@ int nas3d_extract_patches(const float* volume, int C, int D, int H, int W, const
   return launched("extract_patches");
 }
 
-int nas3d_stitch_labels(const float* preds, int ld_pred, const int* corners_dev, int B, int Pd, int Ph,
+int nas3d_patch_nonzero(const float* volume, int C, int D, int H, int W, const int* corners_dev, int B,
+                        int Pd, int Ph, int Pw, int* flags, void* stream) {
+  NAS3D_REQUIRE(volume && corners_dev && flags, "patch_nonzero: null pointer");
+  NAS3D_REQUIRE(C >= 1 && B >= 1 && B <= 65535 && Pd > 0 && Ph > 0 && Pw > 0, "patch_nonzero: bad shape");
+  const long long per_patch = (long long)Pd * Ph * Pw;
+  NAS3D_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * B, (cudaStream_t)stream));
+  unsigned gx = (unsigned)((per_patch + 255) / 256);
+  const unsigned cap = (unsigned)(kNumSMs * 16 / B + 1);
+  if (gx > cap) gx = cap;
+  patch_nonzero_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(volume, C, D, H, W, corners_dev,
+                                                                      Pd, Ph, Pw, flags, per_patch);
+  return launched("patch_nonzero");
+}
+
+int nas3d_stitch_labels(const float* const* patch_preds_dev, const int* patch_nonzero_dev, int ld_pred,
+                        const int* corners_dev, int B, int Pd, int Ph,
                         int Pw, int Db, int Hb, int Wb, int D, int H, int W, int off_d, int off_h,
                         int off_w, float threshold, int inclusive, const unsigned char* skull_mask,
                         unsigned char* labels, double* stitched, void* stream) {
+  NAS3D_REQUIRE(patch_preds_dev && corners_dev && labels, "stitch_labels: null pointer");
   NAS3D_REQUIRE(ld_pred >= 3 && B >= 1, "stitch_labels: predictions need 3 channels");
   NAS3D_REQUIRE(off_d >= 0 && off_h >= 0 && off_w >= 0 && off_d + Db <= D && off_h + Hb <= H &&
                     off_w + Wb <= W, "stitch_labels: brain box outside the volume");
-  StitchArgs A{preds, corners_dev, B, Pd, Ph, Pw, ld_pred, Db, Hb, Wb, D, H, W, off_d, off_h, off_w,
+  StitchArgs A{patch_preds_dev, patch_nonzero_dev, corners_dev, B, Pd, Ph, Pw, ld_pred, Db, Hb, Wb, D, H, W, off_d, off_h, off_w,
                threshold, inclusive, skull_mask, labels, stitched};
   const long long total = (long long)D * H * W;
   stitch_labels_kernel<<<g1d(total), 256, 0, (cudaStream_t)stream>>>(A, total);

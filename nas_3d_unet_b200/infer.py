@@ -6,9 +6,13 @@ batched searched-net forward, float64 mean-stitch in patch order, label assembly
     labels = pred.predict(volume, brain_width)        # uint8 (D,H,W) with values {0,1,2,4}
 
 The reference does batch 1 with autograd on and a device->host copy per patch; here nothing
-leaves the device until the uint8 label volume.  With torch.distributed initialised the patches
-of a volume are sharded over the ranks and gathered on every rank before the (deterministic,
-order-preserving) stitch.
+leaves the device until the uint8 label volume and the patch loop has no host synchronisation
+(the reference's `np.all(data==0)` skip is a device flag consumed by the stitch kernel).
+
+Multi-GPU (one process per GPU): `predict_many` shards whole VOLUMES over the ranks when
+there are at least as many volumes as ranks (no communication); `predict` shards the PATCHES of one
+volume round-robin over the ranks and all-gathers the predictions, so every rank runs the same
+deterministic, order-preserving float64 stitch and holds the same labels.
 """
 import numpy as np
 import torch
@@ -67,20 +71,50 @@ def seg_to_masks(seg, inclusive_label=True):
     return out
 
 
+def shard_indices(n, rank, world):
+    """units (patches of a volume, or volumes of a list) owned by `rank`: round-robin"""
+    return list(range(rank, n, world))
+
+
+def gather_patch_predictions(local, n_total, group=None):
+    """local: (n_local, ...) tensor of the predictions of THIS rank's patches (shard_indices order).
+    Returns the n_total per-patch tensors in patch order, identical on every rank.  One
+    all_gather of equal-sized (zero-padded) buffers; works on any backend / device (the CPU
+    tests run it over gloo)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    if local.shape[0] == per:
+        buf = local.contiguous()
+    else:
+        buf = local.new_zeros((per,) + tuple(local.shape[1:]))
+        buf[:local.shape[0]] = local
+    allb = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(allb, buf, group=group)
+    out = [None] * n_total
+    for r in range(world):
+        for j, b in enumerate(shard_indices(n_total, r, world)):
+            out[b] = allb[r][j]
+    return out
+
+
 class SlidingWindowPredictor:
     def __init__(self, model, patch_shape=(128, 128, 128), batch=8, threshold=0.5,
-                 inclusive_label=True, patch_overlap=None):
+                 inclusive_label=True, patch_overlap=None, group=None):
         self.model = model
         self.patch_shape = tuple(int(p) for p in patch_shape)
         self.batch = int(batch)
         self.threshold = float(threshold)
         self.inclusive = bool(inclusive_label)
         self.overlap = patch_overlap
+        self.group = group
 
     @torch.no_grad()
     def predict_patches(self, volume, corners):
         """volume: (C,D,H,W) float32 CUDA; corners: (B,3) ints in volume coordinates.
-        Returns predictions as a (B,3,Pd,Ph,Pw) tensor (channels-last memory)."""
+        Returns (chunks, ld): the raw network outputs, one (nb,3,Pd,Ph,Pw) tensor (NDHWC memory,
+        voxel pitch ld) per forward batch.  All-zero patches are NOT special-cased here
+        (predict() hands their flags to the stitch kernel)."""
         lib = get_lib()
         C, D, H, W = volume.shape
         Pd, Ph, Pw = self.patch_shape
@@ -88,7 +122,7 @@ class SlidingWindowPredictor:
         cdev = torch.as_tensor(np.ascontiguousarray(corners, dtype=np.int32), device=dev)
         B = cdev.shape[0]
         ld = (C + 3) // 4 * 4
-        outs = []
+        chunks, ld_pred = [], None
         was_training = self.model.training
         self.model.eval()
         try:
@@ -99,71 +133,102 @@ class SlidingWindowPredictor:
                                                      cdev[b0:b0 + nb].data_ptr(), nb, Pd, Ph, Pw,
                                                      x.data_ptr(), ld, _stream()), "extract_patches")
                 y = self.model(x.permute(0, 4, 1, 2, 3)[:, :C])
-                # an all-zero patch is not run through the net by the reference: its prediction
-                # is defined as 0 (prediction.py:133-136)
-                empty = ~x.reshape(nb, -1).ne(0).any(dim=1)
-                if bool(empty.any()):
-                    y = y * (~empty).to(y.dtype).view(nb, 1, 1, 1, 1)
-                outs.append(y)
+                l = _ndhwc_pitch(y)
+                if l is None or (ld_pred is not None and l != ld_pred):
+                    y = y.contiguous(memory_format=torch.channels_last_3d)
+                    l = 3
+                ld_pred = l
+                chunks.append(y)
         finally:
             self.model.train(was_training)
-        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        return chunks, ld_pred
 
     @torch.no_grad()
-    def predict(self, volume, brain_width=None, skull_mask=None, return_stitched=False):
+    def predict(self, volume, brain_width=None, skull_mask=None, return_stitched=False,
+                shard_patches=True):
         """volume (C,D,H,W) float32 (CUDA tensor or numpy); brain_width [[d0,h0,w0],[d1,h1,w1]]
-        inclusive bounds (default: whole volume).  Returns uint8 labels (D,H,W) on the device."""
+        inclusive bounds (default: whole volume).  Returns uint8 labels (D,H,W) on the device.
+        With torch.distributed initialised (and shard_patches) the patches are sharded over the
+        ranks of `group`; every rank returns the same labels."""
         import torch.distributed as dist
         lib = get_lib()
         if isinstance(volume, np.ndarray):
             volume = torch.as_tensor(volume, dtype=torch.float32).cuda()
         volume = volume.contiguous()
+        dev = volume.device
         C, D, H, W = volume.shape
         bw = np.asarray(brain_width if brain_width is not None else [[0, 0, 0], [D - 1, H - 1, W - 1]])
         off = bw[0].astype(int)
         bshape = (bw[1] - bw[0] + 1).astype(int)
         corners = patching(bshape, self.patch_shape, overlap=self.overlap)    # brain coordinates
         B = len(corners)
-        vol_corners = corners + off[None, :]
+        Pd, Ph, Pw = self.patch_shape
         # patches outside the brain box are zero-padded exactly as get_data_from_file crops first:
         brain = volume[:, off[0]:off[0] + bshape[0], off[1]:off[1] + bshape[1],
                        off[2]:off[2] + bshape[2]].contiguous()
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        rank = dist.get_rank() if world > 1 else 0
-        mine = list(range(rank, B, world))
-        preds_mine = self.predict_patches(brain, corners[mine]) if mine else None
-        Pd, Ph, Pw = self.patch_shape
-        ld_pred = 3
-        if world > 1:
-            per = (B + world - 1) // world
-            buf = torch.zeros((per, Pd, Ph, Pw, 3), device=volume.device, dtype=torch.float32)
-            if mine:
-                buf[:len(mine)] = preds_mine.permute(0, 2, 3, 4, 1)
-            allb = [torch.empty_like(buf) for _ in range(world)]
-            dist.all_gather(allb, buf)
-            preds = torch.empty((B, Pd, Ph, Pw, 3), device=volume.device, dtype=torch.float32)
-            for r in range(world):
-                idx = list(range(r, B, world))
-                if idx:
-                    preds[idx] = allb[r][:len(idx)]
+        cdev = torch.as_tensor(np.ascontiguousarray(corners, dtype=np.int32), device=dev)
+        # prediction.py:133-136: an all-zero patch is never run through the net, its prediction is
+        # zeros.  Here: a device flag per patch (every rank computes all of them - one pass over
+        # the volume), consumed by the stitch kernel; no host round trip.
+        nonzero = torch.empty((B,), device=dev, dtype=torch.int32)
+        _lib.check(lib.nas3d_patch_nonzero(brain.data_ptr(), C, int(bshape[0]), int(bshape[1]),
+                                           int(bshape[2]), cdev.data_ptr(), B, Pd, Ph, Pw,
+                                           nonzero.data_ptr(), _stream()), "patch_nonzero")
+        world = (dist.get_world_size(self.group)
+                 if shard_patches and dist.is_available() and dist.is_initialized() else 1)
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        mine = shard_indices(B, rank, world)
+        if mine:
+            chunks, ld_pred = self.predict_patches(brain, corners[mine])
         else:
-            ld_pred = _ndhwc_pitch(preds_mine)              # the head output is stored at pitch 4
-            preds = preds_mine.permute(0, 2, 3, 4, 1)       # (B,Pd,Ph,Pw,3) view of the NDHWC data
-            if ld_pred is None:
-                preds = preds.contiguous()
-                ld_pred = 3
-        cdev = torch.as_tensor(np.ascontiguousarray(corners, dtype=np.int32), device=volume.device)
-        labels = torch.empty((D, H, W), device=volume.device, dtype=torch.uint8)
-        stitched = (torch.empty((3,) + tuple(int(b) for b in bshape), device=volume.device,
-                                dtype=torch.float64) if return_stitched else None)
+            chunks, ld_pred = [], 4
+        if world > 1:
+            # every rank must agree on the pitch: the gathered buffers are (.., 4) NDHWC patches
+            local = torch.zeros((len(mine), Pd, Ph, Pw, 4), device=dev, dtype=torch.float32)
+            j = 0
+            for y in chunks:
+                local[j:j + y.shape[0], ..., :3] = y.permute(0, 2, 3, 4, 1)
+                j += y.shape[0]
+            per_patch = gather_patch_predictions(local, B, self.group)
+            ld_pred = 4
+        else:
+            per_patch = [y[i] for y in chunks for i in range(y.shape[0])]
+        keep = (chunks, per_patch)            # the pointer table below does not own its targets
+        table = torch.tensor([t.data_ptr() for t in per_patch], dtype=torch.int64).to(dev, non_blocking=True)
+        labels = torch.empty((D, H, W), device=dev, dtype=torch.uint8)
+        stitched = (torch.empty((3,) + tuple(int(b) for b in bshape), device=dev, dtype=torch.float64)
+                    if return_stitched else None)
         skull = None
         if skull_mask is not None:
-            skull = torch.as_tensor(skull_mask).to(volume.device).to(torch.uint8).contiguous()
+            skull = torch.as_tensor(skull_mask).to(dev).to(torch.uint8).contiguous()
         _lib.check(lib.nas3d_stitch_labels(
-            preds.data_ptr(), ld_pred, cdev.data_ptr(), B, Pd, Ph, Pw, int(bshape[0]), int(bshape[1]),
-            int(bshape[2]), D, H, W, int(off[0]), int(off[1]), int(off[2]), self.threshold,
-            1 if self.inclusive else 0, skull.data_ptr() if skull is not None else None,
-            labels.data_ptr(), stitched.data_ptr() if stitched is not None else None, _stream()),
-            "stitch_labels")
-        del vol_corners
-        return (labels, stitched, preds, corners) if return_stitched else labels
+            table.data_ptr(), nonzero.data_ptr(), ld_pred, cdev.data_ptr(), B, Pd, Ph, Pw,
+            int(bshape[0]), int(bshape[1]), int(bshape[2]), D, H, W, int(off[0]), int(off[1]),
+            int(off[2]), self.threshold, 1 if self.inclusive else 0,
+            skull.data_ptr() if skull is not None else None, labels.data_ptr(),
+            stitched.data_ptr() if stitched is not None else None, _stream()), "stitch_labels")
+        if not return_stitched:
+            del keep
+            return labels
+        # for the tests: the predictions as the reference would hold them (zeros for empty patches)
+        preds = torch.stack([t[..., :3] if world > 1 else t.permute(1, 2, 3, 0) for t in per_patch])
+        preds = preds * nonzero.ne(0).to(preds.dtype).view(B, 1, 1, 1, 1)
+        return labels, stitched, preds, corners
+
+    @torch.no_grad()
+    def predict_many(self, volumes, brain_widths=None, skull_masks=None):
+        """a list of volumes: sharded over the ranks volume by volume when there are at least as
+        many volumes as ranks (each rank runs whole volumes, no communication; returns
+        {volume index: labels} for the volumes THIS rank owns), otherwise patch-sharded one volume
+        at a time (every rank returns every volume's labels)."""
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        n = len(volumes)
+        by_volume = n >= world
+        out = {}
+        for i in (shard_indices(n, rank, world) if by_volume else range(n)):
+            out[i] = self.predict(volumes[i], None if brain_widths is None else brain_widths[i],
+                                  None if skull_masks is None else skull_masks[i],
+                                  shard_patches=not by_volume)
+        return out

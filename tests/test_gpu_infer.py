@@ -73,3 +73,57 @@ def test_seg_to_masks_bit_exact():
     for inc in (True, False):
         got = seg_to_masks(torch.as_tensor(t).cuda(), inc).cpu().numpy()
         np.testing.assert_array_equal(got, O.multi_class_labels(t, inc).astype(np.float32))
+
+
+def test_all_zero_patches_count_as_zero_predictions():
+    """prediction.py:133-136: a patch whose data is all zero is not run through the net, its
+    prediction is zeros (and it still counts in the overlap mean).  Here the flag is computed on
+    the device and consumed by the stitch kernel - same stitched volume, bit for bit."""
+    from nas_3d_unet_b200.infer import SlidingWindowPredictor
+    model = make_searched().cuda()
+    vol = _volume(4, (4, 70, 40, 36))
+    vol[:, 30:] = 0                       # the patches of the second half are empty
+    pred = SlidingWindowPredictor(model, patch_shape=(32, 32, 32), batch=3)
+    labels, stitched, preds, corners = pred.predict(torch.as_tensor(vol).cuda(), return_stitched=True)
+    empty = [b for b, c in enumerate(corners) if np.all(O.get_patch(vol, (32, 32, 32), c) == 0)]
+    assert empty, "the test volume must contain an all-zero patch"
+    for b in range(len(corners)):
+        assert bool((preds[b] == 0).all()) == (b in empty)
+    pl = [preds[b].permute(3, 0, 1, 2).cpu().numpy() for b in range(preds.shape[0])]
+    ref_st = O.stitch(pl, corners.copy(), (3,) + vol.shape[1:])
+    np.testing.assert_array_equal(stitched.cpu().numpy(), ref_st)
+    np.testing.assert_array_equal(labels.cpu().numpy(), O.tumor_pred(ref_st, 0.5, True))
+
+
+def test_brats_shape_volume_at_128_matches_oracle():
+    """BASELINE.json config #5 at full size: 4x240x240x155 volume, 128^3 auto-fit patching = 9
+    patches (corners = SURVEY App. D known answer), batch 4 + 4 + 1 forwards; float64 stitch and
+    the label volume bit-equal to the numpy oracle on the same predictions; patch 0 against the
+    CPU oracle network (logits tolerance 1e-3)."""
+    from nas_3d_unet_b200.infer import SlidingWindowPredictor
+    model = make_searched().cuda()
+    shape = (4, 240, 240, 155)
+    rng = np.random.default_rng(7)
+    vol = (rng.random(shape, dtype=np.float32) * 100 + 10).astype(np.float32)
+    zz, yy, xx = np.meshgrid(*[np.arange(s, dtype=np.float32) for s in shape[1:]], indexing="ij")
+    brain = (((zz - 120) / 85) ** 2 + ((yy - 120) / 100) ** 2 + ((xx - 77) / 65) ** 2) < 1.0   # App. H
+    vol *= brain[None]
+    skull = brain.astype(np.uint8)
+    pred = SlidingWindowPredictor(model, patch_shape=(128, 128, 128), batch=4)
+    labels, stitched, preds, corners = pred.predict(torch.as_tensor(vol).cuda(), skull_mask=skull,
+                                                    return_stitched=True)
+    assert len(corners) == 9
+    np.testing.assert_array_equal(corners, O.patching(shape[1:], (128, 128, 128)))
+    assert corners[3].tolist() == [0, 112, 27] and corners[8].tolist() == [56, 56, 13]   # SURVEY App. D
+    pl = [preds[b].permute(3, 0, 1, 2).cpu().numpy() for b in range(9)]
+    ref_st = O.stitch(pl, corners.copy(), (3,) + shape[1:])
+    np.testing.assert_array_equal(stitched.cpu().numpy(), ref_st)
+    ref_lab = O.tumor_pred(ref_st, 0.5, True) * skull
+    got = labels.cpu().numpy()
+    assert set(np.unique(got)) <= {0, 1, 2, 4}
+    np.testing.assert_array_equal(got, ref_lab)
+    sd = O.leaf_state(model.state_dict())
+    x0 = torch.as_tensor(O.get_patch(vol, (128, 128, 128), corners[0]))[None]
+    with torch.no_grad():
+        ref0 = O.searched_net(sd, x0, 4, 3, O.G0)[0]
+    assert O.max_rel(preds[0].permute(3, 0, 1, 2), ref0) <= 1e-3

@@ -1,33 +1,111 @@
-"""config #5: sliding-window whole-volume inference, synthetic 4x240x240x155 volumes, 128^3 patches
-(9 per volume), searched-G0 net in eval mode.  Prints one JSON line."""
-import json, os, sys, time
+"""config #5: sliding-window whole-volume inference, synthetic 4x240x240x155 volumes,
+128^3 auto-fit patching (9 patches per volume), searched-G0 net in eval mode.  One JSON line.
+
+    python tools/bench_inference.py [NVOL]                      # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N ... tools/bench_inference.py [NVOL]
+
+Under torchrun (one process per GPU, NCCL) it measures BOTH shardings of SURVEY 8e and checks them
+against the single-GPU result, bit for bit:
+  volumes: NVOL (>= N) different volumes dealt round-robin to the ranks, no communication;
+  patches: one volume at a time, its 9 patches dealt to the ranks, predictions all-gathered,
+           every rank runs the same order-preserving float64 stitch (single-volume latency).
+Timed per mode with CUDA events on each rank between barriers; the max over ranks is reported.
+H2D of every volume and D2H of its uint8 labels are inside the timed region."""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
+import torch.distributed as dist
 from nas_3d_unet_b200.searched import SearchedNet
 from nas_3d_unet_b200.genotype import G0
-from nas_3d_unet_b200.infer import SlidingWindowPredictor
+from nas_3d_unet_b200.infer import SlidingWindowPredictor, shard_indices
+
+
+def volume(seed):
+    rng = np.random.default_rng(seed)
+    shape = (4, 240, 240, 155)
+    v = rng.random(shape, dtype=np.float32) * 100 + 10
+    zz, yy, xx = np.meshgrid(*[np.arange(s, dtype=np.float32) for s in shape[1:]], indexing="ij")
+    brain = (((zz - 120) / 85) ** 2 + ((yy - 120) / 100) ** 2 + ((xx - 77) / 65) ** 2) < 1.0
+    return v * brain[None]
+
 
 def main():
-    nvol = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    nvol = int(sys.argv[1]) if len(sys.argv) > 1 else max(6, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = SearchedNet(4, 4, 3, 4, 3, True, G0).cuda().eval()
-    rng = np.random.default_rng(0)
-    vol = (rng.random((4, 240, 240, 155), dtype=np.float32) * 100 + 10)
-    hv = torch.as_tensor(vol).pin_memory()
+    model = SearchedNet(4, 4, 3, 4, 3, True, G0).to(dev).eval()
+    host = [torch.as_tensor(volume(100 + i)).pin_memory() for i in range(nvol)]
     pred = SlidingWindowPredictor(model, (128, 128, 128), batch=9)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return out, ms.item()
+
+    def run_volumes():          # volume-sharded: this rank's volumes, whole, no communication
+        out = {}
+        for i in shard_indices(nvol, rank, world):
+            out[i] = pred.predict(host[i].to(dev, non_blocking=True), shard_patches=False).cpu()
+        return out
+
+    def run_patches():          # patch-sharded: every volume on all ranks together
+        return {i: pred.predict(host[i].to(dev, non_blocking=True)).cpu() for i in range(nvol)}
+
+    def run_single():           # what one GPU alone produces (the truth for the checks)
+        return {i: pred.predict(host[i].to(dev, non_blocking=True), shard_patches=False).cpu()
+                for i in range(nvol)}
+
     for _ in range(2):
-        pred.predict(hv.cuda(non_blocking=True))
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(nvol):
-        lab = pred.predict(hv.cuda(non_blocking=True))     # H2D of the volume inside the timed loop
-        lab_host = lab.cpu()                                # uint8 label volume back to the host
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / nvol
-    print(json.dumps({"metric": "sliding-window inference", "volumes_per_s": 1 / dt, "patches_per_s": 9 / dt,
-                      "ms_per_volume": dt * 1e3, "patch": 128, "patches_per_volume": 9,
-                      "labels": sorted(int(v) for v in torch.unique(lab_host))}))
+        pred.predict(host[0].to(dev), shard_patches=False)
+    line = {"metric": "sliding-window inference, 4x240x240x155 @128^3 (9 patches/volume)",
+            "n_gpus": world, "volumes": nvol, "unit": "volumes/s"}
+    truth, ms1 = timed(run_single)
+    line["per_gpu_alone"] = {"ms_per_volume": ms1 / nvol, "volumes_per_s": nvol / ms1 * 1e3,
+                             "patches_per_s": 9 * nvol / ms1 * 1e3}
+    line["labels"] = sorted(int(v) for v in torch.unique(truth[0]))
+    if world == 1:
+        line["value"] = line["per_gpu_alone"]["volumes_per_s"]
+    else:
+        run_volumes()
+        got_v, msv = timed(run_volumes)
+        run_patches()
+        got_p, msp = timed(run_patches)
+        ok_v = all(torch.equal(got_v[i], truth[i]) for i in got_v)
+        ok_p = all(torch.equal(got_p[i], truth[i]) for i in got_p)
+        flags = torch.tensor([int(ok_v), int(ok_p)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        line["volume_sharded"] = {"ms_total": msv, "volumes_per_s": nvol / msv * 1e3,
+                                  "patches_per_s": 9 * nvol / msv * 1e3,
+                                  "bit_equal_to_single_gpu": bool(flags[0].item())}
+        line["patch_sharded"] = {"ms_per_volume": msp / nvol, "volumes_per_s": nvol / msp * 1e3,
+                                 "bit_equal_to_single_gpu": bool(flags[1].item())}
+        line["value"] = line["volume_sharded"]["volumes_per_s"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        sys.stdout.flush()
+        os._exit(0 if (world == 1 or bool(flags.min().item())) else 1)
+
 
 if __name__ == "__main__":
     main()
