@@ -39,6 +39,10 @@ def parse():
     ap.add_argument("--ref-device", choices=["cpu", "cuda"], default="cpu",
                     help="--impl reference only: cuda = the same torch ops through torch's CUDA "
                          "kernels (informational second baseline, BASELINE.md section 4)")
+    ap.add_argument("--ref-batch", type=int, default=1,
+                    help="--impl reference: patches per timed CPU step (bounded sample of the workload)")
+    ap.add_argument("--no-batch-probe", action="store_true",
+                    help="--impl reference: skip the single extra step at the full batch size")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
     ap.add_argument("--e2e-probe", action="store_true", help="print an e2e overhead breakdown to stderr")
@@ -116,82 +120,153 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference path on the host cores
+# reference arm / cpu baseline: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu"):
-    """times `steps` training steps of the oracle (CPU restatement of the reference) at batch 1;
-    returns (patches_per_s, seconds_per_step, cores, sample description).
-    device="cuda" runs the same torch-op graph through torch's own CUDA kernels (cuDNN) - the
-    reference's intended GPU path (search.py:66-69); informational only, never the baseline."""
+def _reference_modules():
+    """the UNMODIFIED reference's hot-path modules (searched / nas / loss / genotype), imported from
+    /root/reference where it exists or from the bytecode oracle/build_ref.py compiled from it
+    (oracle/_ref travels to the GPU box); None when neither is available"""
+    from oracle import build_ref
+    d = build_ref.reference_dir()
+    if d is None:
+        return None
+    import importlib
+    sys.path.insert(0, d)
+    try:
+        mods = {n: importlib.import_module(n) for n in ("prim_ops", "cell", "genotype", "nas", "searched", "loss")}
+    finally:
+        sys.path.remove(d)
+    if not all(os.path.dirname(os.path.abspath(m.__file__)) == os.path.abspath(d) for m in mods.values()):
+        return None           # something else named nas / searched / loss shadowed them
+    return mods
+
+
+def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu", probe_batch=0):
+    """times `steps` training steps of the reference path on the host cores; returns (patches/s,
+    s/step, cores, kind, sample description, extra).  kind "reference": the reference's own modules
+    (train.py:121-128 / search.py:222-238 loop bodies around them); kind "port": the oracle port
+    when the reference modules are unavailable.  device="cuda" runs the oracle's torch-op graph
+    through torch's own CUDA kernels (cuDNN) - the reference's intended GPU path (search.py:66-69);
+    informational only, never the baseline.  probe_batch > 0 additionally times ONE step at that
+    batch size, to show how CPU patches/s depends on the batch."""
     from oracle import nas3d_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    if workload == "searched":
-        from nas_3d_unet_b200.searched import SearchedNet
-        from nas_3d_unet_b200.genotype import Genotype
-        m = SearchedNet(4, 4, 3, 4, 3, True, Genotype(down=O.G0.down, up=O.G0.up))
-    else:
-        from nas_3d_unet_b200.nas import ShellNet
-        m = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True)
-    sd = O.leaf_state(m.state_dict())       # parameters only; the modules themselves never run
-    if device != "cpu":
-        sd = {k: (v.detach().to(device).requires_grad_(True) if v.is_floating_point() else v.to(device))
-              for k, v in sd.items()}
-    params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-3)
-    x, y = synthetic_host_batch(batch, patch, seed=1234)
-    x, y = x.to(device), y.to(device)
+    mods = _reference_modules() if device == "cpu" else None
     p_drop = 0.5 if workload == "searched" else 0.1
-
-    def one():
-        opt.zero_grad()
-        mask = torch.empty((batch, 12, 1, 1, 1), device=device).bernoulli_(1 - p_drop).div_(1 - p_drop)
+    if mods is not None:
+        kind = "reference"
         if workload == "searched":
-            pred = O.searched_net(sd, x, 4, 3, O.G0, drop_mask=mask)
+            gene = mods["genotype"].Genotype(down=O.G0.down, up=O.G0.up)
+            model = mods["searched"].SearchedNet(4, 4, 3, 4, 3, True, gene)
+            optims = [torch.optim.Adam(model.parameters())]
         else:
-            pred = O.shell_net(sd, x, 4, 3, drop_mask=mask)
-        loss = O.dice_loss(pred, y)
-        loss.backward()
-        opt.step()
-        return loss.item()
+            model = mods["nas"].ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True)
+            optims = [torch.optim.Adam(model.alphas()), torch.optim.Adam(model.kernel.parameters())]
+        model.train()
+        lossf = mods["loss"].WeightedDiceLoss()
 
-    # a search step is two passes (alpha step on the val batch + weight step on the train batch,
-    # search.py:222-238); both cost the same here, so the same pass is timed twice
-    passes = 2 if workload == "supernet" else 1
+        def make_step(b):
+            x, y = synthetic_host_batch(b, patch, seed=1234)
+
+            def one():
+                last = 0.0
+                for opt in optims:          # search: alpha step then weight step (search.py:222-238)
+                    opt.zero_grad()
+                    loss = lossf(model(x), y)
+                    last = loss.item()
+                    loss.backward()
+                    opt.step()
+                return last
+            return one
+    else:
+        kind = "port"
+        if workload == "searched":
+            from nas_3d_unet_b200.searched import SearchedNet
+            from nas_3d_unet_b200.genotype import Genotype
+            m = SearchedNet(4, 4, 3, 4, 3, True, Genotype(down=O.G0.down, up=O.G0.up))
+        else:
+            from nas_3d_unet_b200.nas import ShellNet
+            m = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True)
+        sd = O.leaf_state(m.state_dict())       # parameters only; the modules themselves never run
+        if device != "cpu":
+            sd = {k: (v.detach().to(device).requires_grad_(True) if v.is_floating_point() else v.to(device))
+                  for k, v in sd.items()}
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-3)
+        passes = 2 if workload == "supernet" else 1
+
+        def make_step(b):
+            x, y = synthetic_host_batch(b, patch, seed=1234)
+            x, y = x.to(device), y.to(device)
+
+            def one():
+                last = 0.0
+                for _ in range(passes):
+                    opt.zero_grad()
+                    mask = torch.empty((b, 12, 1, 1, 1), device=device).bernoulli_(1 - p_drop).div_(1 - p_drop)
+                    pred = (O.searched_net(sd, x, 4, 3, O.G0, drop_mask=mask) if workload == "searched"
+                            else O.shell_net(sd, x, 4, 3, drop_mask=mask))
+                    loss = O.dice_loss(pred, y)
+                    loss.backward()
+                    opt.step()
+                    last = loss.item()
+                return last
+            return one
+
+    def sync():
+        if device != "cpu":
+            torch.cuda.synchronize()
+
+    one = make_step(batch)
     for _ in range(warmup):
         one()
-    if device != "cpu":
-        torch.cuda.synchronize()
+    sync()
     t0 = time.perf_counter()
-    for _ in range(steps * passes):
+    for _ in range(steps):
         one()
-    if device != "cpu":
-        torch.cuda.synchronize()
+    sync()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return batch / dt, dt, torch.get_num_threads(), (
-        "%s net, %d step(s) of batch %d at %d^3 (fwd+bwd+Adam), oracle port on %s"
-        % (workload, steps, batch, patch, "CPU" if device == "cpu" else "torch eager CUDA (cuDNN)"))
+    extra = {}
+    if probe_batch and probe_batch != batch:
+        big = make_step(probe_batch)
+        t0 = time.perf_counter()
+        big()
+        sync()
+        dtb = time.perf_counter() - t0
+        extra["batch_scaling"] = {"batch_%d_patches_per_s" % batch: batch / dt,
+                                  "batch_%d_patches_per_s" % probe_batch: probe_batch / dtb,
+                                  "note": "one untimed-warm-up-free step at batch %d" % probe_batch}
+    what = {"reference": "the reference's own modules (unmodified; %s)" % (
+                "imported from /root/reference" if os.path.isdir("/root/reference")
+                else "bytecode compiled from /root/reference by oracle/build_ref.py"),
+            "port": "oracle port"}[kind]
+    sample = ("%s net, %d step(s) of batch %d at %d^3 (fwd + Dice + bwd + Adam), %s on %s"
+              % (workload, steps, batch, patch, what,
+                 "%d host threads" % torch.get_num_threads() if device == "cpu" else "torch eager CUDA (cuDNN)"))
+    return batch / dt, dt, torch.get_num_threads(), kind, sample, extra
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: batch 1 per step (--ref-device cuda: informational torch-eager GPU run, batch
-    # as given)
+    # bounded sample of the workload: ONE patch per timed step (--ref-batch to change; GroupNorm and
+    # Dice are per-sample, so the arithmetic per patch is that of the full batch), plus one probe
+    # step at the full batch so the line shows how CPU patches/s moves with the batch
     on_gpu = args.ref_device == "cuda"
-    v, dt, cores, sample = cpu_reference_steps(args.workload, args.patch, args.steps, args.warmup,
-                                               batch=args.batch if on_gpu else 1,
-                                               device=args.ref_device)
+    b = args.batch if on_gpu else args.ref_batch
+    v, dt, cores, kind, sample, extra = cpu_reference_steps(
+        args.workload, args.patch, args.steps, args.warmup, batch=b, device=args.ref_device,
+        probe_batch=0 if (on_gpu or args.no_batch_probe) else args.batch)
     line = {
         "impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, reference=True),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "device": args.ref_device},
+        "config": workload_config(args),
+        "cpu_baseline": dict({"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                              "batch_per_timed_step": b, "device": args.ref_device}, **extra),
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -207,9 +282,9 @@ def metric_name(args):
     return "supernet %d^3 search patches/s (train+val pair = 1 patch)" % args.patch
 
 
-def workload_config(args, reference=False):
-    """same workload description for both arms; the reference arm times a bounded sample of it
-    (one patch per step - GroupNorm and Dice are per-sample, so CPU patches/s is flat in the batch)"""
+def workload_config(args):
+    """the workload both arms are quoted on (identical dict in both lines); the reference arm times a
+    bounded sample of it and says which in cpu_baseline.sample / batch_per_timed_step"""
     cfg = {
         "workload": ("%s-G0 U-Net training step (fwd + Dice + bwd + Adam), 4x%d^3 patches, "
                      "batch %d per GPU" % (args.workload, args.patch, args.batch))
@@ -222,8 +297,6 @@ def workload_config(args, reference=False):
         "l2": "inputs larger than L2 (%.0f MB of x (fp32) + y (int8 masks) per step per GPU vs 126 MB L2)"
               % (((4 * 4 + 3) * args.patch ** 3 * args.batch) / 1e6),
     }
-    if reference:
-        cfg["reference_sample"] = "each timed step = 1 patch of this workload on the host cores"
     return cfg
 
 
@@ -437,16 +510,16 @@ def run_ours(args):
         # per-kernel timing of rank 0's own replica: the gradient all-reduce must be off here, the
         # other ranks are not stepping (they wait at the barrier below)
         engine.enable_data_parallel(enabled=False)
-        roofline = roofline_pass(step_resident, profiling, args)
+        roofline = roofline_pass(step_resident, profiling, args, ms_per_step)
         engine.enable_data_parallel(enabled=world > 1)
     if world > 1:
         dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, sample = cpu_reference_steps(args.workload, P, steps=3, warmup=1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-               "s_per_step": dt}
+        v, dt, cores, kind, sample, _ = cpu_reference_steps(args.workload, P, steps=3, warmup=1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+               "batch_per_timed_step": 1, "s_per_step": dt}
 
     if rank == 0:
         line = {
@@ -457,6 +530,9 @@ def run_ours(args):
             "voxels_per_s": value * P ** 3,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
+            # the per-family table again at top level (survives parsers that flatten `roofline`)
+            "extra": {"families": roofline["by_kernel"], "summed_roofline": roofline["summed"],
+                      "summed_roofline_vs_graph_step": roofline["summed_vs_graph_step"]} if roofline else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -473,8 +549,9 @@ def run_ours(args):
 
 
 def ncu_traffic(kernel, shape):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this (kernel, shape) from the
-    committed ncu --set full capture (profiles/ncu_traffic.json), or None if not captured"""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this (C-ABI entry, shape) from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json: a profiler figure taken once per
+    round, NOT re-measured by this run), or None if not captured"""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             return json.load(f)["%s|%s" % (kernel, shape)]["dram_bytes_per_launch"]
@@ -482,16 +559,48 @@ def ncu_traffic(kernel, shape):
         return None
 
 
-def roofline_pass(step, profiling, args):
-    """2 extra steps with every C-ABI launch bracketed by CUDA events on the launch stream;
-    the dominant kernel (largest share of the step) is reported against its binding roof."""
-    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+def measure_fma_roof(dev):
+    """fp32 FMA roof of THIS run: the library's probe kernel (packed-FMA chains, no memory traffic)
+    timed with CUDA events, best of 5"""
+    from nas_3d_unet_b200 import _lib
+    lib = _lib.load()
+    n = 148 * 8 * 256
+    out = torch.empty(n, device=dev, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    best = None
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flops = lib.nas3d_probe_fma(out.data_ptr(), n, 2048, st)
+        e1.record()
+        torch.cuda.synchronize()
+        if flops <= 0:
+            return None
+        tf = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        best = tf if best is None or tf > best else best
+    return best
+
+
+def roofline_pass(step, profiling, args, ms_per_step):
+    """2 extra eager steps with every C-ABI launch bracketed by CUDA events on the launch stream.
+    Reported: the DOMINANT C-ABI FAMILY (largest share of the step's kernel time) against its
+    binding roof, the per-family table, and the summed roofline of SURVEY 8d:
+        summed = sum_k max(F_k / compute_roof_k, B_k / HBM) / sum_k t_k
+    with F_k / B_k the algorithmic flops / bytes of launch k (profiling.py) and compute_roof_k the
+    pipe the kernel runs on: fp32 FMA for the CUDA-core convolutions, TF32 tensor (= measured bf16
+    / 2) for the tcgen05 ones; everything else is HBM-only."""
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         with open(pk) as f:
             j = json.load(f)
         peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j.get("bf16_tflops_sustained", j["bf16_tflops"]),
-                 "src": "measured"}
+                 "src": "MEASURED_PEAKS.json (sustained bf16)"}
+    fma_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+    fma_measured = measure_fma_roof(torch.device("cuda", torch.cuda.current_device()))
+    fma_roof = fma_measured or fma_nominal
+    tf32_roof = peaks["bf16_tflops"] / 2.0
+    hbm = peaks["hbm_gbs"]
     prof = profiling.enable()
     try:
         nsteps = 2
@@ -500,39 +609,87 @@ def roofline_pass(step, profiling, args):
         rows = prof.summary()
     finally:
         profiling.disable()
+
+    def roofs(r):
+        """(roof seconds, bound) of one (kernel, shape) row"""
+        t_mem = r["bytes"] / (hbm * 1e9)
+        if r["flops"] <= 0:
+            return t_mem, "hbm"
+        if r["kernel"] == "nas3d_umma_conv":
+            t_c, b = r["flops"] / (tf32_roof * 1e12), "tensor"
+        else:
+            t_c, b = r["flops"] / (fma_roof * 1e12), "fp32_fma"
+        return (t_c, b) if t_c >= t_mem else (t_mem, "hbm")
+
     total_ms = sum(r["ms"] for r in rows)
-    by_kernel = {}
+    fam = {}
     for r in rows:
-        a = by_kernel.setdefault(r["kernel"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
+        t_roof, bound = roofs(r)
+        a = fam.setdefault(r["kernel"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0,
+                                         "roof_ms": 0.0, "bound_ms": {}})
         a["ms"] += r["ms"]; a["bytes"] += r["bytes"]; a["flops"] += r["flops"]; a["launches"] += r["launches"]
-    top = rows[0]
-    # fp32 FFMA roof of the CUDA cores: 148 SMs x 128 lanes x 2 flop x 1.965 GHz
-    fp32_tflops = 148 * 128 * 2 * 1.965e9 / 1e12
+        a["roof_ms"] += t_roof * 1e3
+        a["bound_ms"][bound] = a["bound_ms"].get(bound, 0.0) + t_roof * 1e3
+    roof_ms_total = sum(a["roof_ms"] for a in fam.values())
+    order = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
+    name, top = order[0]
+    bound = max(top["bound_ms"].items(), key=lambda kv: kv[1])[0]
     ach_gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
     ach_tf = top["flops"] / (top["ms"] * 1e-3) / 1e12
-    hbm_frac = ach_gbs / peaks["hbm_gbs"]
+    if bound == "hbm":
+        achieved, peak, unit, src = ach_gbs, hbm, "GB/s", peaks["src"]
+    elif bound == "tensor":
+        achieved, peak, unit, src = ach_tf, tf32_roof, "TFLOP/s", peaks["src"] + " / 2 for TF32"
+    else:
+        achieved, peak, unit = ach_tf, fma_roof, "TFLOP/s"
+        src = ("fp32 FMA roof measured in this run by nas3d_probe_fma (packed FFMA2 chains)"
+               if fma_measured else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz")
+    # the family's heaviest shape: per-launch figures (what one ncu capture of it shows)
+    trow = max((r for r in rows if r["kernel"] == name), key=lambda r: r["ms"])
+    t_roof, t_bound = roofs(trow)
+    top_shape = {"shape": trow["shape"], "launches_per_step": trow["launches"] // nsteps,
+                 "avg_launch_ms": trow["ms"] / trow["launches"], "bound": t_bound,
+                 "algorithmic_bytes_per_launch": trow["bytes"] / trow["launches"],
+                 "algorithmic_flops_per_launch": trow["flops"] / trow["launches"],
+                 "achieved_tflops": trow["flops"] / (trow["ms"] * 1e-3) / 1e12,
+                 "achieved_gbps": trow["bytes"] / (trow["ms"] * 1e-3) / 1e9,
+                 "frac_of_binding_roof": t_roof * 1e3 / trow["ms"],
+                 "traffic": ncu_traffic(name, trow["shape"])}
+    table = {}
+    for k, v in order:
+        b = max(v["bound_ms"].items(), key=lambda kv: kv[1])[0]
+        table[k] = {"ms_per_step": v["ms"] / nsteps, "launches_per_step": v["launches"] // nsteps,
+                    "share": v["ms"] / total_ms if total_ms else None,
+                    "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0,
+                    "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] else 0.0,
+                    "bound": b, "frac_of_binding_roof": (v["roof_ms"] / v["ms"]) if v["ms"] else None}
     out = {
-        "bound": "hbm", "kernel": top["kernel"], "shape": top["shape"],
-        "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac,
-        "peak_source": peaks["src"], "traffic": ncu_traffic(top["kernel"], top["shape"]),
+        "bound": bound, "kernel": name, "scope": "all launches of this C-ABI entry point in the step",
+        "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+        "frac_of_binding_roof_per_launch_sum": top["roof_ms"] / top["ms"],
+        "peak_source": src, "traffic": top_shape["traffic"], "top_shape": top_shape,
         "share_of_step": top["ms"] / total_ms if total_ms else None,
-        # all shapes of the same kernel: the figure the ncu launch list (profiles/*_ncu_launch_summary.csv)
-        # reports for this kernel name
-        "kernel_share_of_step": by_kernel[top["kernel"]]["ms"] / total_ms if total_ms else None,
+        "launches_per_step": top["launches"] // nsteps,
         "avg_launch_ms": top["ms"] / top["launches"],
-        "achieved_tflops": ach_tf, "fp32_ffma_peak_tflops": fp32_tflops,
-        "frac_of_fp32_ffma": ach_tf / fp32_tflops,
-        "step_hbm_frac": (sum(r["bytes"] for r in rows) / (total_ms * 1e-3) / 1e9) / peaks["hbm_gbs"],
+        "achieved_tflops": ach_tf, "achieved_gbps": ach_gbs,
+        "fp32_fma_roof_tflops": {"measured_this_run": fma_measured, "nominal": fma_nominal},
+        "tf32_tensor_roof_tflops": tf32_roof, "hbm_roof_gbps": hbm,
+        "frac_of_hbm": ach_gbs / hbm, "frac_of_tf32_tensor": ach_tf / tf32_roof,
+        # SURVEY 8d: whole step against the sum of its kernels' binding roofs
+        "summed": roof_ms_total / total_ms if total_ms else None,
+        "summed_vs_graph_step": (roof_ms_total / nsteps) / ms_per_step if ms_per_step else None,
+        "summed_roof_ms_per_step": roof_ms_total / nsteps,
+        "step_hbm_frac": (sum(r["bytes"] for r in rows) / (total_ms * 1e-3) / 1e9) / hbm,
         "kernel_ms_per_step": total_ms / nsteps,
-        "by_kernel": {k: {"ms_per_step": v["ms"] / nsteps, "launches_per_step": v["launches"] // nsteps,
-                          "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0,
-                          "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] else 0.0}
-                      for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]["ms"])},
+        "by_kernel": table,
     }
     if args.profile_out:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        for r in rows:
+            t_roof, b = roofs(r)
+            r["roof_ms"], r["bound"] = t_roof * 1e3, b
         with open(args.profile_out, "w") as f:
-            json.dump({"steps": nsteps, "rows": rows[:60]}, f, indent=1)
+            json.dump({"steps": nsteps, "rows": rows[:80]}, f, indent=1)
     return out
 
 

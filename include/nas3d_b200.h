@@ -41,6 +41,12 @@ int nas3d_version(void);
 const char* nas3d_last_error(void);
 /* number of kernels this library has launched in this process (bench.py: gpu_launches) */
 unsigned long long nas3d_launch_count(void);
+/* launches of ONE kernel variant, by the label the dispatcher counts it under (e.g.
+ * "conv3_s1_tma_merged", "wgrad3_s1", "affine_sum_bwd_apply_ring", "umma_conv"): lets the parity
+ * tests assert WHICH kernel served a call.  nas3d_launch_labels writes the newline-separated list of
+ * labels seen so far into buf (cap bytes, NUL-terminated) and returns the bytes needed. */
+unsigned long long nas3d_launch_count_of(const char* label);
+int nas3d_launch_labels(char* buf, int cap);
 
 /* Kernel-selection options (csrc/options.cu).  The reference has one code path per op; here
  * several kernels may serve the same op (tiled vs generic gather, cp.async-ring vs register
@@ -51,6 +57,12 @@ unsigned long long nas3d_launch_count(void);
  * reduce_ring, pw_fwd_ring, reduce_waves, ring_min_log2, pw_vpt_sfb, pw_vpt_bfs, pw_vpt_mom,
  * wgrad_split.  set: 0 or NAS3D_ERR_ARG (unknown name / value out of range); get: the value
  * (>= 0) or NAS3D_ERR_ARG. */
+/* Roofline probe: one launch of pure packed-fp32-FMA chains (no memory traffic) over all SMs;
+ * returns the flops it executes (> 0) or a negative status.  bench.py times it with CUDA events
+ * to state the fp32-FMA roof of THIS run next to the FFMA-bound conv kernels.  out: scratch of at
+ * least 148*8*256 floats. */
+long long nas3d_probe_fma(float* out, long long out_floats, int iters, void* stream);
+
 int nas3d_set_option(const char* name, int value);
 int nas3d_get_option(const char* name);
 

@@ -34,6 +34,9 @@ _SIGNATURES = {
     "nas3d_version": [],
     "nas3d_last_error": [],
     "nas3d_launch_count": [],
+    "nas3d_launch_count_of": [C.c_char_p],
+    "nas3d_launch_labels": [C.c_char_p, c_int],
+    "nas3d_probe_fma": [c_vp, c_ll, c_int, c_vp],
     "nas3d_set_option": [C.c_char_p, c_int],
     "nas3d_get_option": [C.c_char_p],
     "nas3d_ncdhw_to_ndhwc": [c_vp, c_vp, c_int, c_int, c_ll, c_int, c_vp],
@@ -102,6 +105,8 @@ _SIGNATURES = {
 _RESTYPES = {
     "nas3d_last_error": C.c_char_p,
     "nas3d_launch_count": C.c_ulonglong,
+    "nas3d_launch_count_of": C.c_ulonglong,
+    "nas3d_probe_fma": C.c_longlong,
     "nas3d_umma_packed_floats": C.c_longlong,
 }
 
@@ -156,6 +161,18 @@ class option:
 
 def launch_count():
     return int(load().nas3d_launch_count())
+
+
+def launch_counts():
+    """{kernel-variant label: launches so far} (nas3d_launch_labels / nas3d_launch_count_of)"""
+    lib = load()
+    n = lib.nas3d_launch_labels(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.nas3d_launch_labels(buf, n + 1)
+    out = {}
+    for name in buf.value.decode().split():
+        out[name] = int(lib.nas3d_launch_count_of(name.encode()))
+    return out
 
 
 def ptr_array(ptrs):

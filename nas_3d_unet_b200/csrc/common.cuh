@@ -37,9 +37,34 @@ inline int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// per-kernel-variant launch counters (nas3d_launch_count_of): keyed by the address of the label
+// literal, so the launch path is a short pointer scan; labels with equal text are summed on read
+struct VariantCounter {
+  std::atomic<const char*> name;
+  std::atomic<unsigned long long> n;
+};
+constexpr int kMaxVariants = 192;
+extern VariantCounter g_variants[kMaxVariants];
+
+inline void count_variant(const char* what) {
+  for (int i = 0; i < kMaxVariants; ++i) {
+    const char* cur = g_variants[i].name.load(std::memory_order_relaxed);
+    if (cur == nullptr) {
+      const char* expect = nullptr;
+      if (g_variants[i].name.compare_exchange_strong(expect, what)) cur = what;
+      else cur = expect;
+    }
+    if (cur == what) {
+      g_variants[i].n.fetch_add(1, std::memory_order_relaxed);
+      return;
+    }
+  }
+}
+
 // call after every kernel launch
 inline int launched(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_variant(what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(NAS3D_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return NAS3D_OK;

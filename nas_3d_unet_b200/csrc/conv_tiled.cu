@@ -502,7 +502,7 @@ static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   }
   if (tma) kern_tma<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A, tmap);
   else kern_cp<<<(unsigned)blocks, TS::THREADS, TS::SMEM, st>>>(A, tmap);
-  return launched("conv3_s1");
+  return launched(!tma ? "conv3_s1_cpasync" : (A.tma_merged ? "conv3_s1_tma_merged" : "conv3_s1_tma5d"));
 }
 
 template <int DIL, int TH, int TD, int NWARP, int TWT, bool BIAS>

@@ -5,6 +5,7 @@
 // 128-bit loads; fp32 partials over <=32 elements per thread, fp64 from there on
 // (GroupNorm statistics of inputs up to ~110 in magnitude cancel badly in fp32).
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "gn_coef.cuh"
 
@@ -12,6 +13,7 @@ namespace nas3d {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+VariantCounter g_variants[kMaxVariants];
 
 constexpr int RB = 256;     // threads per reduction block
 constexpr int RITER = 32;   // super-elements per thread
@@ -572,6 +574,31 @@ extern "C" {
 int nas3d_version(void) { return 100; }
 const char* nas3d_last_error(void) { return g_err; }
 unsigned long long nas3d_launch_count(void) { return g_launches.load(); }
+unsigned long long nas3d_launch_count_of(const char* label) {
+  unsigned long long n = 0;
+  if (!label) return 0;
+  for (int i = 0; i < kMaxVariants; ++i) {
+    const char* cur = g_variants[i].name.load(std::memory_order_relaxed);
+    if (cur && strcmp(cur, label) == 0) n += g_variants[i].n.load(std::memory_order_relaxed);
+  }
+  return n;
+}
+int nas3d_launch_labels(char* buf, int cap) {
+  int used = 0;
+  if (buf && cap > 0) buf[0] = 0;
+  for (int i = 0; i < kMaxVariants; ++i) {
+    const char* cur = g_variants[i].name.load(std::memory_order_relaxed);
+    if (!cur) continue;
+    const int len = (int)strlen(cur);
+    if (buf && used + len + 2 <= cap) {
+      memcpy(buf + used, cur, len);
+      buf[used + len] = '\n';
+      buf[used + len + 1] = 0;
+    }
+    used += len + 1;
+  }
+  return used + 1;
+}
 
 int nas3d_moments_nc(const float* x, int N, long long V, int C, int ld, double* S, void* stream) {
   int U, P, logP;

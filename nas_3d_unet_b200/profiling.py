@@ -103,7 +103,9 @@ class ProfiledLib:
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
         if not name.startswith("nas3d_") or name in ("nas3d_last_error", "nas3d_version",
-                                                       "nas3d_launch_count",
+                                                       "nas3d_launch_count", "nas3d_launch_count_of",
+                                                       "nas3d_launch_labels", "nas3d_set_option",
+                                                       "nas3d_get_option", "nas3d_probe_fma",
                                                        "nas3d_umma_packed_floats",
                                                        "nas3d_umma_pack_mode",
                                                        "nas3d_conv1x1_bwd_fused_supported"):
