@@ -396,7 +396,7 @@ def run_ours(args):
     if args.graph == "on":
         from nas_3d_unet_b200.graph import GraphedStep
         ex = (dx, dy) if args.workload == "searched" else (dx, dy, dvx, dvy)
-        graphed = GraphedStep(step_fn, ex, warmup=max(args.warmup, 3), optimizers=opts)
+        graphed = GraphedStep(step_fn, ex, warmup=max(args.warmup, 3), optimizers=opts, buffers=2)
 
     def host_batches(n):
         """what a data pipeline hands the step loop: pinned host tensors"""
@@ -411,12 +411,13 @@ def run_ours(args):
         with the previous step by nas_3d_unet_b200.data.DevicePrefetcher), loss value out (D2H)"""
         from nas_3d_unet_b200.data import DevicePrefetcher
         last = 0.0
+        if graphed is not None:
+            # GraphedStep.stream: batch i+1 goes H2D straight into the idle static input set while
+            # graph i runs; every step's loss comes back to the host (4 bytes), read one step late
+            for last in graphed.stream(host_batches(nsteps)):
+                pass
+            return last
         for batch in DevicePrefetcher(host_batches(nsteps), dev):
-            if graphed is not None:
-                # the prefetched device batch is copied into the graph's static inputs (D2D, cheap);
-                # the NEXT batch's PCIe transfer overlaps this replay on the copy stream
-                last = graphed(*batch).reshape(-1)[-1].item()
-                continue
             if args.workload == "searched":
                 x, y = batch
                 opts[0].zero_grad()

@@ -666,6 +666,21 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
     else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
     rc = NAS3D_OK;
   }
+  if (!done && tiled_enabled() && !big_scale && !big_relu) {
+    rc = umma_wgrad(d, small, big, dW, st);        // wide dense 3x3x3: tcgen05 split-K GEMM
+    if (rc == NAS3D_OK) {
+      done = true;
+      if (d_bias_small) {                          // not followed by a GroupNorm: column sums of dy
+        const int C4 = A.Cs / 4;
+        const long long per_block = 64LL * (256 / C4);
+        colsum_kernel<<<(unsigned)((nvox + per_block - 1) / per_block), 256, sizeof(float) * A.Cs, st>>>(
+            small, nvox, A.Cs, A.lds, d_bias_small);
+        rc = launched("colsum");
+        if (rc) return rc;
+      }
+    } else if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    rc = NAS3D_OK;
+  }
   if (!done && dw3_shape(d) && !big_scale && !big_relu) {
     S2Args S = s2_args(d, big, small, nullptr);
     S.dW = dW; S.dbias_small = d_bias_small;

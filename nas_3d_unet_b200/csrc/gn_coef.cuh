@@ -92,8 +92,23 @@ __device__ __forceinline__ void gn_bwd_coef_body(const GnBwdBatch& B, int k, int
   double* shB = sc.dB;
   const double* Rn = B.R[k] + (long long)n * C * 2;
   __syncthreads();
+  // The group mean enters every term as (R2 - mu*R1) = sum dout*(x - mu): with |mu| >> std the two
+  // products cancel, and a mean rounded to fp32 leaves a COHERENT error eps*|mu*R1| (measured at
+  // 128^3: 1.3e-3 of a deep-level dgamma, 6x the reference's own fp32 error, whose per-voxel
+  // roundings average out).  So mu is recomputed in fp64 from the moment sums S where they are
+  // given.  The G fp64 means are parked in sc.red (32 doubles) until the block reduction at the end
+  // needs it; norms with more than 32 groups (none in this network) keep the fp32 mean.
+  double* shMu = sc.red;
+  const bool mu64 = B.S[k] != nullptr && G <= 32;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    if (mu64) {
+      const double* Sn = B.S[k] + (long long)n * C * 2;
+      double sx = 0.0;
+      for (int c = g * cg; c < (g + 1) * cg; ++c) sx += Sn[c * 2];
+      mu = sx * inv_m;
+      shMu[g] = mu;
+    }
     double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
     double A = 0.0, Bq = 0.0;
     for (int c = g * cg; c < (g + 1) * cg; ++c) {
@@ -108,7 +123,8 @@ __device__ __forceinline__ void gn_bwd_coef_body(const GnBwdBatch& B, int k, int
   double dwp = 0.0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     int g = c / cg;
-    double mu = mean_rstd[((long long)n * G + g) * 2 + 0];
+    const double mu_f = mean_rstd[((long long)n * G + g) * 2 + 0];     // the mean b was built from
+    const double mu = mu64 ? shMu[g] : mu_f;
     double rho = mean_rstd[((long long)n * G + g) * 2 + 1];
     double r1 = Rn[c * 2], r2 = Rn[c * 2 + 1];
     double qq = -rho * rho * shB[g] * inv_m;
@@ -122,10 +138,13 @@ __device__ __forceinline__ void gn_bwd_coef_body(const GnBwdBatch& B, int k, int
       atomicAdd(&B.dbeta[k][c], (float)(wv * r1));
       if (B.dbias[k])
         atomicAdd(&B.dbias[k][c], (float)(pp * r1 + wv * qq * B.S[k][((long long)n * C + c) * 2] + rr * V));
-      dwp += (double)B.a[k][(long long)n * C + c] * r2 + (double)B.b[k][(long long)n * C + c] * r1;
+      // d alpha = <dout, a*x + b> = a*(R2 - mu*R1) + beta*R1 with beta = b + mu_f*a
+      const double av = (double)B.a[k][(long long)n * C + c], bv = (double)B.b[k][(long long)n * C + c];
+      dwp += av * (r2 - mu * r1) + (bv + mu_f * av) * r1;
     }
   }
   if (B.dw[k] && side) {   // `side` is uniform over the block
+    __syncthreads();       // shMu (sc.red) has been read by everyone before the reduction reuses it
     double tot = gn_block_sum(dwp, sc.red);
     if (threadIdx.x == 0) atomicAdd(B.dw[k], (float)tot);
   }

@@ -12,16 +12,25 @@ activations come from the graph's private memory pool, inputs are copied into st
     step = GraphedStep(lambda x, y: train_step(model, lossf, optim, x, y), (x0, y0))
     for x, y in batches:
         loss = step(x, y)          # device scalar; loss.item() when needed
+
+Host-fed loops use `stream()`: with `buffers=2` the step is captured twice over two static input
+sets (one memory pool - the replays are serial), the pinned-host batch i+1 is copied STRAIGHT into
+the idle set on a copy stream while graph i runs (no device-to-device staging copy), and the loss
+of step i is read back one step late from a pinned slot, so the host never drains the GPU queue:
+
+    for loss_value in step.stream(host_batches):      # python floats, in step order
+        ...
 """
 import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, warmup=3, optimizers=()):
+    def __init__(self, step_fn, example_inputs, warmup=3, optimizers=(), buffers=1):
         """step_fn(*tensors) -> tensor or tuple of tensors; it must do the COMPLETE step
         (zero_grad ... optimizer.step).  `warmup` eager steps run first (they are real steps).
         `optimizers`: optim.FlatAdam instances whose lr etc. are re-read before every replay, so
-        ReduceLROnPlateau keeps working on a captured step."""
+        ReduceLROnPlateau keeps working on a captured step.  `buffers` = 2 captures a second graph
+        over a second set of static inputs for stream()."""
         self.optimizers = [o for o in optimizers if hasattr(o, "sync")]
         try:   # warm-up runs on a side stream, which torch would flag for every AccumulateGrad node
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -39,6 +48,14 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = step_fn(*self.static_in)
+        self.sets = [(self.static_in, self.graph, self.static_out)]
+        for _ in range(1, max(1, int(buffers))):
+            ins = [t.detach().clone() for t in example_inputs]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.graph.pool()):
+                out = step_fn(*ins)
+            self.sets.append((ins, g, out))
+        self._copy_stream = None
 
     def load(self, *inputs):
         """copy a batch (host-pinned or device tensors) into the static input buffers"""
@@ -55,3 +72,75 @@ class GraphedStep:
     def __call__(self, *inputs):
         self.load(*inputs)
         return self.replay()
+
+    def stream(self, host_batches, scalar=lambda out: out.reshape(-1)[-1]):
+        """run every batch of `host_batches` (tuples of pinned host tensors shaped like the example
+        inputs) through the captured step; yields `scalar(step output)` of each step as a python
+        float, in order, each value one step late (after the NEXT step has been enqueued).
+        Per step the timeline holds: one H2D of the batch into the idle static input set (copy
+        stream, overlapping the running graph), one graph launch, one 4-byte D2H."""
+        dev = self.static_in[0].device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._pinned = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in self.sets]
+        cs = self._copy_stream
+        nset = len(self.sets)
+        consumed = [None] * nset          # main-stream event: graph k has read its inputs
+        it = iter(host_batches)
+
+        def issue(k, batch):
+            ins = self.sets[k][0]
+            with torch.cuda.stream(cs):
+                if consumed[k] is not None:
+                    cs.wait_event(consumed[k])
+                for s, h in zip(ins, batch):
+                    s.copy_(h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return ev
+
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        ready = issue(0, nxt)
+        pending = None                    # (event, pinned slot) of the previous step's scalar
+        i = 0
+        while ready is not None:
+            k = i % nset
+            cur_ready = ready
+            ready = None
+            if nset > 1:                  # prefetch batch i+1 into the other set while graph k runs
+                try:
+                    ready = issue((i + 1) % nset, next(it))
+                except StopIteration:
+                    pass
+            main.wait_event(cur_ready)
+            for o in self.optimizers:
+                o.sync()
+            self.sets[k][1].replay()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            consumed[k] = ev
+            slot = self._pinned[k]
+            slot.copy_(scalar(self.sets[k][2]).detach().reshape(1), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if nset == 1:                 # single set: the next H2D has to wait for this replay
+                try:
+                    ready = issue(0, next(it))
+                except StopIteration:
+                    pass
+            if pending is not None:
+                pending[0].synchronize()
+                yield float(pending[1])
+            # the slot is overwritten nset steps from now; its value is read (above) before that
+            pending = (done, slot) if nset > 1 else None
+            if nset == 1:
+                done.synchronize()
+                yield float(slot)
+            i += 1
+        if pending is not None:
+            pending[0].synchronize()
+            yield float(pending[1])

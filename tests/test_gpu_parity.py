@@ -281,6 +281,44 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
         assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
 
 
+@pytest.mark.parametrize("c", [16, 32, 64])
+@pytest.mark.parametrize("stride,dil,transposed", [(1, 1, False), (1, 2, False), (2, 1, False),
+                                                   (2, 1, True), (2, 2, False), (2, 2, True)])
+def test_tcgen05_wgrad_matches_oracle_and_ffma_kernels(c, stride, dil, transposed):
+    """weight gradient of the wide dense convs as a tcgen05 split-K GEMM (MN-major operands straight
+    from NDHWC, 3xTF32, TMEM accumulators, conv_umma_wgrad.cu) against the fp32 oracle and against
+    the CUDA-core wgrad kernels (library option umma_wgrad = 0), on extents that are not multiples
+    of anything; several K chunks per CTA and a ragged last stage"""
+    from nas_3d_unet_b200 import _lib
+    from nas_3d_unet_b200.prim_ops import ConvOps
+    torch.manual_seed(c + 11 * stride + dil)
+    op = ConvOps(c, c, stride=stride, dilation=dil, transposed=transposed, ops_order='weight')
+    g = torch.Generator().manual_seed(5 * c + stride)
+    s_in = (9, 13, 11) if not transposed else (5, 7, 6)
+    x = torch.randn(3, c, *s_in, generator=g) * 2.0
+    sd = O.leaf_state(op.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = O.conv_ops(sd, '', xr, 3, stride, dil, transposed, order='weight')
+    r = torch.randn(yr.shape, generator=g)
+    (yr * r).sum().backward()
+    op = op.cuda()
+    res = {}
+    for mode in (1, 0):
+        with variant(umma_wgrad=mode):
+            n0 = _lib.launch_counts().get("umma_wgrad", 0)
+            op.zero_grad()
+            y = op(x.cuda().requires_grad_(True))
+            (y * r.cuda()).sum().backward()
+            torch.cuda.synchronize()
+            used = _lib.launch_counts().get("umma_wgrad", 0) - n0
+        assert (used == 1) == (mode == 1), (mode, used)
+        res[mode] = (op.conv.weight.grad.detach().cpu().clone(), op.conv.bias.grad.detach().cpu().clone())
+    for mode, (dw, db) in res.items():
+        assert O.max_rel(dw, sd['conv.weight'].grad) <= 2e-5, (mode, O.max_rel(dw, sd['conv.weight'].grad))
+        assert O.max_rel(db, sd['conv.bias'].grad) <= 2e-5, mode
+    assert O.max_rel(res[1][0], res[0][0]) <= 2e-5
+
+
 def test_tcgen05_stride2_dgrad_on_odd_extents_uses_tap_order():
     """odd input extents (Db != 2*Ds): the stride-2 dgrad cannot use the parity-class
     decomposition; the pre-packed class-order operand must be ignored and the tap-order one
@@ -372,6 +410,42 @@ def test_cuda_graph_step_matches_eager_steps():
     replayed = [g(x, y).item() for _ in range(2)]     # steps 4 and 5
     assert eager[0] > eager[-1]                        # it trains
     np.testing.assert_allclose(replayed, eager[3:5], rtol=0, atol=2e-5)
+
+
+def test_streamed_double_buffered_graph_steps_match_eager_steps():
+    """GraphedStep(buffers=2).stream(): host batches copied straight into two alternating static
+    input sets, two captured graphs over one memory pool, losses read back one step late - the
+    same loss sequence as eager steps over the same (different per step) batches"""
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    from nas_3d_unet_b200.graph import GraphedStep
+    batches = [O.synthetic_batch(2, 32, seed=30 + i) for i in range(5)]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in batches]
+
+    def make():
+        m = make_searched().cuda()
+        m.train()
+        m.last_conv[0].dropout.p = 0.0
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+        lossf = WeightedDiceLoss()
+
+        def step(xx, yy):
+            opt.zero_grad(set_to_none=True)
+            loss = lossf(m(xx), yy)
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+
+    x0, y0 = batches[0][0].cuda(), batches[0][1].cuda()
+    step = make()
+    eager = [step(x0, y0).item() for _ in range(2)]            # the two warm-up steps of the capture
+    eager += [step(x.cuda(), y.cuda()).item() for x, y in batches]
+    g = GraphedStep(make(), (x0, y0), warmup=2, buffers=2)
+    streamed = list(g.stream(iter(host)))
+    assert len(streamed) == len(batches)
+    np.testing.assert_allclose(streamed, eager[2:], rtol=0, atol=2e-5)
+    # an odd and an even number of batches both drain completely
+    assert len(list(g.stream(iter(host[:2])))) == 2 and len(list(g.stream(iter(host[:1])))) == 1
 
 
 @pytest.mark.parametrize("c", [4, 8, 16])
