@@ -119,6 +119,7 @@ struct UwArgs {
   int stride, dil, pad;
   long long nvox;          // N * Ds * Hs * Ws (the K extent of the GEMM)
   int chunk;               // small voxels per CTA, a multiple of KB
+  int debug;
 };
 
 template <int C>
@@ -245,6 +246,12 @@ __global__ void __launch_bounds__(256) umma_wgrad_kernel(const UwArgs A) {
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      if (A.debug && blockIdx.x == 0 && blockIdx.y == 0 && j == 0) {
+        const float* fa = reinterpret_cast<const float*>(a_hi);
+        const float* fb = reinterpret_cast<const float*>(b_sm);
+        printf("uw dbg: tmem_base %08x nstage %d chunk %d a_hi[0..3] %g %g %g %g  a_hi[row1] %g  b[0..3] %g %g %g %g\n",
+               tmem_base, nstage, A.chunk, fa[0], fa[1], fa[2], fa[3], fa[4], fb[0], fb[1], fb[2], fb[3]);
+      }
       const uint32_t a_hi_s = uw::smem_u32(a_hi), a_lo_s = uw::smem_u32(a_lo), b_s = uw::smem_u32(b_sm);
 #pragma unroll
       for (int t = 0; t < TILES; ++t) {
@@ -282,6 +289,8 @@ __global__ void __launch_bounds__(256) umma_wgrad_kernel(const UwArgs A) {
         uw::tmem_ld8(trow + (uint32_t)(t * NCOL + c8 * 8), hi);
         uw::tmem_ld8(trow + (uint32_t)(t * NCOL + C + c8 * 8), lo);
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (A.debug && blockIdx.x == 0 && blockIdx.y == 0 && t == 0 && c8 == 0 && row < 2)
+          printf("uw dbg: row %d tap %d cb %d hi %g %g lo %g %g\n", row, tap, cb, hi[0], hi[1], lo[0], lo[1]);
         if (tap < 27) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) atomicAdd(dst + (long long)(c8 * 8 + i) * C * 27, hi[i] + lo[i]);
@@ -334,6 +343,7 @@ int umma_wgrad(const nas3d_conv_desc* d, const float* small, const float* big, f
   A.stride = d->stride; A.dil = d->dil; A.pad = d->pad;
   A.nvox = (long long)d->N * d->Ds * d->Hs * d->Ws;
   A.chunk = 0;
+  A.debug = g_opt.umma_wgrad_debug;
   if (A.nvox >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;
   switch (d->Cb) {
     case 16: return launch_umma_wgrad<16>(A, st);

@@ -14,13 +14,17 @@ snapshot (like our own built .so) so that
 
     python oracle/build_ref.py            # no-op (exit 0) when /root/reference is absent
 
-CPython imports `name.pyc` files found directly in a sys.path directory (sourceless import), so
-`sys.path.insert(0, "oracle/_ref")` is all a user of the compiled reference needs.  The bytecode is
-tied to the interpreter's minor version; the GPU box runs this same image.
+The artefacts are stored as `<module>.bytecode` (snapshot tools tend to drop `*.pyc`);
+reference_dir() materialises them as `<module>.pyc` in a per-process temporary directory, from which
+CPython imports them like any sourceless module (`sys.path.insert(0, reference_dir())`).  The
+bytecode is tied to the interpreter's minor version; the GPU box runs this same image.
 """
+import atexit
 import os
 import py_compile
+import shutil
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("NAS3D_REFERENCE_DIR", "/root/reference")
@@ -37,9 +41,12 @@ def build(verbose=True):
     for name in sorted(os.listdir(REF_SRC)):
         if not name.endswith(".py"):
             continue
-        out = os.path.join(REF_OUT, name + "c")
+        out = os.path.join(REF_OUT, name[:-3] + ".bytecode")
         py_compile.compile(os.path.join(REF_SRC, name), cfile=out, doraise=True, optimize=0)
         built.append(out)
+    for stale in os.listdir(REF_OUT):
+        if stale.endswith(".pyc"):
+            os.remove(os.path.join(REF_OUT, stale))
     with open(os.path.join(REF_OUT, "PYTHON_VERSION"), "w") as f:
         f.write("%d.%d\n" % sys.version_info[:2])
     if verbose:
@@ -52,12 +59,25 @@ def reference_dir():
     (this container) or the compiled copy (GPU box); None if neither exists / version mismatch"""
     if os.path.isdir(REF_SRC) and os.path.exists(os.path.join(REF_SRC, "prim_ops.py")):
         return REF_SRC
+    global _materialised
+    if _materialised is not None:
+        return _materialised
     ver = os.path.join(REF_OUT, "PYTHON_VERSION")
-    if os.path.exists(ver) and os.path.exists(os.path.join(REF_OUT, "prim_ops.pyc")):
-        with open(ver) as f:
-            if f.read().strip() == "%d.%d" % sys.version_info[:2]:
-                return REF_OUT
-    return None
+    if not (os.path.exists(ver) and os.path.exists(os.path.join(REF_OUT, "prim_ops.bytecode"))):
+        return None
+    with open(ver) as f:
+        if f.read().strip() != "%d.%d" % sys.version_info[:2]:
+            return None
+    d = tempfile.mkdtemp(prefix="nas3d_ref_")
+    atexit.register(shutil.rmtree, d, ignore_errors=True)
+    for name in os.listdir(REF_OUT):
+        if name.endswith(".bytecode"):
+            shutil.copyfile(os.path.join(REF_OUT, name), os.path.join(d, name[:-len(".bytecode")] + ".pyc"))
+    _materialised = d
+    return d
+
+
+_materialised = None
 
 
 if __name__ == "__main__":
