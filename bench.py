@@ -45,6 +45,8 @@ def parse():
                     help="--impl reference: skip the single extra step at the full batch size")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
+    ap.add_argument("--graph-buffers", type=int, default=2, choices=[1, 2],
+                    help="static input sets / captured graphs (2: H2D straight into the idle set, GraphedStep.stream)")
     ap.add_argument("--e2e-probe", action="store_true", help="print an e2e overhead breakdown to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -396,7 +398,11 @@ def run_ours(args):
     if args.graph == "on":
         from nas_3d_unet_b200.graph import GraphedStep
         ex = (dx, dy) if args.workload == "searched" else (dx, dy, dvx, dvy)
-        graphed = GraphedStep(step_fn, ex, warmup=max(args.warmup, 3), optimizers=opts, buffers=2)
+        graphed = GraphedStep(step_fn, ex, warmup=max(args.warmup, 3), optimizers=opts,
+                              # two captured supernet-128^3 steps (2 x ~12 000 kernel nodes) crash the driver in
+                              # cudaGraphLaunch (B200, driver 580): the supernet keeps one graph; its batch of 1
+                              # makes the H2D of a step 33 MB, so the double buffer would buy nothing there
+                              buffers=args.graph_buffers if args.workload == "searched" else 1)
 
     def host_batches(n):
         """what a data pipeline hands the step loop: pinned host tensors"""

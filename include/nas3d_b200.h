@@ -117,7 +117,16 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
 /* dW[cs][cb][tap] += sum_{n,o} small[o,cs] * f(big[o*s-p+t*d, cb]);
  * d_bias_small[cs] += sum small (if non-NULL);  d_bias_big[cb] += sum big (if non-NULL).
  * dW / d_bias must be zero-initialised by the caller (they are accumulated with atomics so
- * they can live directly in the flat gradient bucket that NCCL all-reduces). */
+ * they can live directly in the flat gradient bucket that NCCL all-reduces).
+ * _ws variant: with `workspace` (workspace_floats >= nas3d_conv_wgrad_workspace_floats(d, prologue
+ * present); that query returns 0 for shapes that need none) the wide dense 3x3x3 convs (C = 16 /
+ * 32 / 64) run as a tcgen05 split-K GEMM whose K splits are reduced in a fixed order through the
+ * workspace (deterministic, no atomics on dW).  The workspace is scratch: owned by the caller
+ * (torch's allocator), not retained. nas3d_conv_wgrad == _ws without a workspace. */
+long long nas3d_conv_wgrad_workspace_floats(const nas3d_conv_desc* d, int has_prologue);
+int nas3d_conv_wgrad_ws(const nas3d_conv_desc* d, const float* small, const float* big,
+                        const float* big_scale, int big_relu, float* dW, float* d_bias_small,
+                        float* d_bias_big, float* workspace, long long workspace_floats, void* stream);
 int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,
                      const float* big_scale, int big_relu, float* dW, float* d_bias_small,
                      float* d_bias_big, void* stream);

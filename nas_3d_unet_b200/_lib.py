@@ -45,6 +45,8 @@ _SIGNATURES = {
     "nas3d_conv_big_from_small": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
                                   c_int, c_vp, c_vp],
     "nas3d_conv_wgrad": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
+    "nas3d_conv_wgrad_ws": [C.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],
+    "nas3d_conv_wgrad_workspace_floats": [C.POINTER(ConvDesc), c_int],
     "nas3d_conv1x1_cat_fwd": [C.POINTER(ConvDesc), c_int, _PP, _PI, c_vp, c_vp, c_vp, c_int, c_int,
                               c_vp, c_vp, c_vp],
     "nas3d_conv1x1_cat_dgrad": [C.POINTER(ConvDesc), c_int, _PP, _PI, _PI, c_vp, c_vp, _PP, _PI, c_vp,
@@ -107,6 +109,7 @@ _RESTYPES = {
     "nas3d_launch_count": C.c_ulonglong,
     "nas3d_launch_count_of": C.c_ulonglong,
     "nas3d_probe_fma": C.c_longlong,
+    "nas3d_conv_wgrad_workspace_floats": C.c_longlong,
     "nas3d_umma_packed_floats": C.c_longlong,
 }
 

@@ -649,9 +649,21 @@ int nas3d_conv_big_from_small(const nas3d_conv_desc* d, const float* small, cons
   return rc ? rc : moments_fallback(moments, big, d->N, Vb, d->Cb, d->ld_big, stream);
 }
 
+long long nas3d_conv_wgrad_workspace_floats(const nas3d_conv_desc* d, int has_prologue) {
+  if (!d || has_prologue || !tiled_enabled()) return 0;
+  return umma_wgrad_workspace_floats(d);
+}
+
 int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* big,
                      const float* big_scale, int big_relu, float* dW, float* d_bias_small,
                      float* d_bias_big, void* stream) {
+  return nas3d_conv_wgrad_ws(d, small, big, big_scale, big_relu, dW, d_bias_small, d_bias_big, nullptr, 0,
+                             stream);
+}
+
+int nas3d_conv_wgrad_ws(const nas3d_conv_desc* d, const float* small, const float* big,
+                        const float* big_scale, int big_relu, float* dW, float* d_bias_small,
+                        float* d_bias_big, float* workspace, long long workspace_floats, void* stream) {
   ConvArgs A;
   int rc = fill_args(d, &A);
   if (rc) return rc;
@@ -667,7 +679,7 @@ int nas3d_conv_wgrad(const nas3d_conv_desc* d, const float* small, const float* 
     rc = NAS3D_OK;
   }
   if (!done && tiled_enabled() && !big_scale && !big_relu) {
-    rc = umma_wgrad(d, small, big, dW, st);        // wide dense 3x3x3: tcgen05 split-K GEMM
+    rc = umma_wgrad(d, small, big, dW, workspace, workspace_floats, st);   // wide dense 3x3x3: tcgen05 split-K GEMM
     if (rc == NAS3D_OK) {
       done = true;
       if (d_bias_small) {                          // not followed by a GroupNorm: column sums of dy

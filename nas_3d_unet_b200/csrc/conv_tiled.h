@@ -88,7 +88,9 @@ int tiled_dw_s2_bfs(const S2Args& A, cudaStream_t st);
 int tiled_dw_wgrad(const S2Args& A, int stride, cudaStream_t st);
 
 // tcgen05 weight gradient of the wide dense 3x3x3 convs (conv_umma_wgrad.cu)
-int umma_wgrad(const nas3d_conv_desc* d, const float* small, const float* big, float* dW, cudaStream_t st);
+int umma_wgrad(const nas3d_conv_desc* d, const float* small, const float* big, float* dW,
+               float* workspace, long long ws_floats, cudaStream_t st);
+long long umma_wgrad_workspace_floats(const nas3d_conv_desc* d);
 
 // return NAS3D_ERR_UNSUPPORTED (without error text) when the shape is not covered
 int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st);

@@ -26,7 +26,6 @@ static const OptEntry kOptions[] = {
     {"pw_vpt_mom", &Options::pw_vpt_mom, 1, 4},
     {"umma_wgrad", &Options::umma_wgrad, 0, 1},
     {"umma_wgrad_min_c", &Options::umma_wgrad_min_c, 16, 128},
-    {"umma_wgrad_debug", &Options::umma_wgrad_debug, 0, 1},
 };
 
 static const OptEntry* find_option(const char* name) {

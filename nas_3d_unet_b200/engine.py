@@ -991,6 +991,15 @@ def _pw_bwd_fused(ctx, d, parts, y, m, in_relu, in_scale, sigmoid):
     return True
 
 
+def _wgrad_workspace(ctx, d, prologue):
+    """scratch for the split-K partial sums of the tcgen05 weight gradient (wide dense 3x3x3 convs);
+    (None, 0) for every other shape"""
+    n = int(ctx.lib.nas3d_conv_wgrad_workspace_floats(C.byref(d), 1 if prologue else 0))
+    if n <= 0:
+        return None, 0
+    return torch.empty(n, device=ctx.device, dtype=torch.float32), n
+
+
 def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
     if y.g is None:
         return
@@ -1011,11 +1020,12 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
     dy = _GradView(dy_t, y)
     dW = ctx.gptr(m.weight)
     db = ctx.gptr(m.bias) if (m.bias is not None and not y.bias_done) else None
-    wst = ctx.fork_wgrad(dy_t)
     if not spec.transposed:
         d = _desc(spec, x, dy)
-        check(lib.nas3d_conv_wgrad(C.byref(d), dy.ptr, x.ptr, _tp(in_scale), 1 if in_relu else 0,
-                                   dW, db, None, wst), "conv_wgrad")
+        ws, nws = _wgrad_workspace(ctx, d, in_relu or in_scale is not None)
+        wst = ctx.fork_wgrad(dy_t, ws)
+        check(lib.nas3d_conv_wgrad_ws(C.byref(d), dy.ptr, x.ptr, _tp(in_scale), 1 if in_relu else 0,
+                                      dW, db, None, _tp(ws), nws, wst), "conv_wgrad")
         if x.requires_grad:
             g, acc = x.grad_slot()
             gv = _GradView(g, x)
@@ -1031,7 +1041,9 @@ def _conv_bwd(ctx, x, y, m, spec, in_relu, in_scale, sigmoid):
                       "conv dgrad")
     else:
         d = _desc(spec, dy, x)
-        check(lib.nas3d_conv_wgrad(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, wst),
+        ws, nws = _wgrad_workspace(ctx, d, False)
+        wst = ctx.fork_wgrad(dy_t, ws)
+        check(lib.nas3d_conv_wgrad_ws(C.byref(d), x.ptr, dy.ptr, None, 0, dW, None, db, _tp(ws), nws, wst),
               "convT wgrad")
         if x.requires_grad:
             g, acc = x.grad_slot()

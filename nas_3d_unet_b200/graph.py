@@ -14,7 +14,7 @@ activations come from the graph's private memory pool, inputs are copied into st
         loss = step(x, y)          # device scalar; loss.item() when needed
 
 Host-fed loops use `stream()`: with `buffers=2` the step is captured twice over two static input
-sets (one memory pool - the replays are serial), the pinned-host batch i+1 is copied STRAIGHT into
+sets, the pinned-host batch i+1 is copied STRAIGHT into
 the idle set on a copy stream while graph i runs (no device-to-device staging copy), and the loss
 of step i is read back one step late from a pinned slot, so the host never drains the GPU queue:
 
@@ -25,12 +25,16 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, warmup=3, optimizers=(), buffers=1):
+    def __init__(self, step_fn, example_inputs, warmup=3, optimizers=(), buffers=1, share_pool=False):
         """step_fn(*tensors) -> tensor or tuple of tensors; it must do the COMPLETE step
         (zero_grad ... optimizer.step).  `warmup` eager steps run first (they are real steps).
         `optimizers`: optim.FlatAdam instances whose lr etc. are re-read before every replay, so
         ReduceLROnPlateau keeps working on a captured step.  `buffers` = 2 captures a second graph
-        over a second set of static inputs for stream()."""
+        over a second set of static inputs for stream(); each graph gets its own memory pool unless
+        `share_pool` (sharing is only valid if the graphs are always replayed alternately).
+        Measured limit on B200 / driver 580: two instantiated graphs of a supernet 128^3 search step
+        (~12 000 kernel nodes each) segfault inside cudaGraphLaunch, with shared or separate pools;
+        one such graph, or two searched-net graphs (~530 nodes each), are fine."""
         self.optimizers = [o for o in optimizers if hasattr(o, "sync")]
         try:   # warm-up runs on a side stream, which torch would flag for every AccumulateGrad node
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -52,7 +56,7 @@ class GraphedStep:
         for _ in range(1, max(1, int(buffers))):
             ins = [t.detach().clone() for t in example_inputs]
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.graph.pool()):
+            with torch.cuda.graph(g, pool=(self.graph.pool() if share_pool else None)):
                 out = step_fn(*ins)
             self.sets.append((ins, g, out))
         self._copy_stream = None

@@ -34,7 +34,8 @@ def _conv_work(d, wgrad=False):
 
 def _work(name, args):
     """(algorithmic bytes, flops, tag) of one call"""
-    if name in ("nas3d_conv_small_from_big", "nas3d_conv_big_from_small", "nas3d_conv_wgrad"):
+    if name in ("nas3d_conv_small_from_big", "nas3d_conv_big_from_small", "nas3d_conv_wgrad",
+                "nas3d_conv_wgrad_ws"):
         return _conv_work(args[0])
     if name == "nas3d_conv1x1_bwd_fused":
         # reads dsmall + big once, writes dbig: the fused pair does the flops of dgrad AND wgrad
@@ -106,6 +107,7 @@ class ProfiledLib:
                                                        "nas3d_launch_count", "nas3d_launch_count_of",
                                                        "nas3d_launch_labels", "nas3d_set_option",
                                                        "nas3d_get_option", "nas3d_probe_fma",
+                                                       "nas3d_conv_wgrad_workspace_floats",
                                                        "nas3d_umma_packed_floats",
                                                        "nas3d_umma_pack_mode",
                                                        "nas3d_conv1x1_bwd_fused_supported"):

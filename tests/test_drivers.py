@@ -56,6 +56,7 @@ def test_reference_drivers_run_unchanged_on_this_package(tmp_path):
     dropin = os.path.join(ROOT, "nas_3d_unet_b200", "dropin")
     with H.driver_environment(str(tmp_path), impl_dir=dropin) as env:
         res = H.run_drivers(env)
-    assert os.path.dirname(res.model_file) == dropin, res.model_file
+    # the drivers' `from nas import ShellNet` went through the dropin shim to THIS package's class
+    assert os.path.dirname(res.model_file) == os.path.join(ROOT, "nas_3d_unet_b200"), res.model_file
     assert _lib.launch_count() - n0 > 1000, "the drivers' steps did not run on the nas3d kernels"
     _check(res)

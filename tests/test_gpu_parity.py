@@ -304,7 +304,7 @@ def test_tcgen05_wgrad_matches_oracle_and_ffma_kernels(c, stride, dil, transpose
     op = op.cuda()
     res = {}
     for mode in (1, 0):
-        with variant(umma_wgrad=mode):
+        with variant(umma_wgrad=mode, umma_wgrad_min_c=16):
             n0 = _lib.launch_counts().get("umma_wgrad", 0)
             op.zero_grad()
             y = op(x.cuda().requires_grad_(True))
