@@ -4,8 +4,14 @@
     python tools/bench_inference.py [NVOL]                      # 1 GPU
     python -m torch.distributed.run --nproc-per-node N ... tools/bench_inference.py [NVOL]
 
-Under torchrun (one process per GPU, NCCL) it measures BOTH shardings of SURVEY 8e and checks them
-against the single-GPU result, bit for bit:
+Under torchrun (one process per GPU, NCCL) it measures BOTH shardings of SURVEY 8e and checks their
+label volumes against the single-GPU result.  The network forward is not bit-reproducible from run to
+run (fp32 atomics of the split-K tcgen05 convs at the deep levels reorder sums at the 1e-7 level), and
+a RANDOM-INIT net puts most probabilities within 1e-3 of the 0.5 threshold, so a handful of voxels per
+volume flips label even between two runs on the same GPU: the line reports that run-to-run baseline
+(`rerun_mismatch_voxels`) next to the mismatches of each sharding; a gather / ordering bug would
+flip whole patches (millions of voxels).  The ordering itself is proven bit-exactly with
+deterministic stand-in predictions over gloo in tests/test_infer_shard_gloo.py.
   volumes: NVOL (>= N) different volumes dealt round-robin to the ranks, no communication;
   patches: one volume at a time, its 9 patches dealt to the ranks, predictions all-gathered,
            every rank runs the same order-preserving float64 stitch (single-volume latency).
@@ -78,7 +84,14 @@ def main():
         pred.predict(host[0].to(dev), shard_patches=False)
     line = {"metric": "sliding-window inference, 4x240x240x155 @128^3 (9 patches/volume)",
             "n_gpus": world, "volumes": nvol, "unit": "volumes/s"}
+    def mismatches(a, b):
+        return int(sum(int((a[i] != b[i]).sum()) for i in a))
+
+    nvox = 240 * 240 * 155
     truth, ms1 = timed(run_single)
+    again, _ = timed(run_single)
+    line["rerun_mismatch_voxels"] = mismatches(again, truth)
+    line["voxels_per_volume"] = nvox
     line["per_gpu_alone"] = {"ms_per_volume": ms1 / nvol, "volumes_per_s": nvol / ms1 * 1e3,
                              "patches_per_s": 9 * nvol / ms1 * 1e3}
     line["labels"] = sorted(int(v) for v in torch.unique(truth[0]))
@@ -89,15 +102,17 @@ def main():
         got_v, msv = timed(run_volumes)
         run_patches()
         got_p, msp = timed(run_patches)
-        ok_v = all(torch.equal(got_v[i], truth[i]) for i in got_v)
-        ok_p = all(torch.equal(got_p[i], truth[i]) for i in got_p)
-        flags = torch.tensor([int(ok_v), int(ok_p)], device=dev)
-        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        mm = torch.tensor([mismatches(got_v, truth), mismatches(got_p, truth)], device=dev)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX)           # worst rank
+        tol = max(10 * (line["rerun_mismatch_voxels"] + 1), int(1e-5 * nvox * nvol))
+        flags = (mm <= tol).to(torch.int32)
         line["volume_sharded"] = {"ms_total": msv, "volumes_per_s": nvol / msv * 1e3,
                                   "patches_per_s": 9 * nvol / msv * 1e3,
-                                  "bit_equal_to_single_gpu": bool(flags[0].item())}
+                                  "label_mismatch_voxels_vs_single_gpu": int(mm[0].item()),
+                                  "within_rerun_noise": bool(flags[0].item())}
         line["patch_sharded"] = {"ms_per_volume": msp / nvol, "volumes_per_s": nvol / msp * 1e3,
-                                 "bit_equal_to_single_gpu": bool(flags[1].item())}
+                                 "label_mismatch_voxels_vs_single_gpu": int(mm[1].item()),
+                                 "within_rerun_noise": bool(flags[1].item())}
         line["value"] = line["volume_sharded"]["volumes_per_s"]
     if rank == 0:
         print(json.dumps(line), flush=True)
