@@ -47,6 +47,11 @@ def parse():
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
     ap.add_argument("--graph-buffers", type=int, default=2, choices=[1, 2],
                     help="static input sets / captured graphs (2: H2D straight into the idle set, GraphedStep.stream)")
+    ap.add_argument("--drivers-loop", action="store_true",
+                    help="additionally time the loop body of the UNCHANGED reference drivers (train.py:113-128 / "
+                         "search.py:211-238: numpy batch -> torch.as_tensor(device, float) every step, eager "
+                         "modules, torch.optim.Adam, fp32 labels, loss.item() in the step) and add it to the "
+                         "line as `drivers_loop`")
     ap.add_argument("--e2e-probe", action="store_true", help="print an e2e overhead breakdown to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -512,6 +517,45 @@ def run_ours(args):
     e2e = {"value": patches_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
+    drivers_loop = None
+    if args.drivers_loop:
+        # what a user gets WITHOUT touching the reference drivers: their own step loop, verbatim, on
+        # fresh replicas of the modules (eager, torch Adam, pageable numpy batches, fp32 labels)
+        import numpy as np
+        torch.manual_seed(0)
+        if args.workload == "searched":
+            from nas_3d_unet_b200.searched import SearchedNet
+            from nas_3d_unet_b200.genotype import G0
+            dmodel = SearchedNet(4, 4, 3, 4, 3, True, G0).to(dev)
+            dopts = [torch.optim.Adam(dmodel.parameters())]
+        else:
+            from nas_3d_unet_b200.nas import ShellNet
+            dmodel = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True).to(dev)
+            dopts = [torch.optim.Adam(dmodel.alphas()), torch.optim.Adam(dmodel.kernel.parameters())]
+        dmodel.train()
+        nx, ny = hx.numpy().copy(), hy.numpy().astype(np.int8)        # what generator.convert_data yields
+
+        def driver_step():
+            last = 0.0
+            for opt in dopts:
+                x = torch.as_tensor(nx, device=dev, dtype=torch.float)
+                y_truth = torch.as_tensor(ny, device=dev, dtype=torch.float)
+                opt.zero_grad()
+                y_pred = dmodel(x)
+                loss = lossf(y_pred, y_truth)
+                last += loss.item()
+                loss.backward()
+                opt.step()
+            return last
+        for _ in range(3):
+            driver_step()
+        nst = max(3, args.steps // 2)
+        ms_d = timed(driver_step, nst) / nst
+        drivers_loop = {"value": patches_per_step / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d,
+                        "what": "reference driver loop body unchanged: eager modules, torch.optim.Adam, "
+                                "torch.as_tensor of numpy batches (fp32 x, int8 -> fp32 labels), loss.item() per step"}
+        del dmodel, dopts
+
     roofline = None
     if not args.no_roofline and rank == 0:
         # per-kernel timing of rank 0's own replica: the gradient all-reduce must be off here, the
@@ -536,7 +580,7 @@ def run_ours(args):
             "config": dict(workload_config(args), cuda_graph=(graphed is not None)),
             "voxels_per_s": value * P ** 3,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "drivers_loop": drivers_loop,
             # the per-family table again at top level (survives parsers that flatten `roofline`)
             "extra": {"families": roofline["by_kernel"], "summed_roofline": roofline["summed"],
                       "summed_roofline_vs_graph_step": roofline["summed_vs_graph_step"]} if roofline else None,

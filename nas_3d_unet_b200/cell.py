@@ -41,16 +41,23 @@ class MixedOp(nn.Module):
         if alpha.ncol < len(self._ops):
             raise ValueError("alpha row has %d weights for %d candidate ops" % (alpha.ncol, len(self._ops)))
         terms = []
+        # every family holds a candidate that needs the per-(n,c) moments of x (identity / se_conv /
+        # down_se_conv / up_se_conv share them through x.S): produce them BEFORE the candidates fork
+        # onto streams of their own
+        if x.S is None:
+            x.S = engine.moments(ctx, x)
         for k, op in enumerate(self._ops):
-            t = op._run(ctx, x)
-            if t.alpha is not None:      # cannot happen for the 15 primitives
-                t = engine.Term(engine.materialize(ctx, t))
+            with ctx.on_sublane(k):
+                t = op._run(ctx, x)
+                if t.alpha is not None:      # cannot happen for the 15 primitives
+                    t = engine.Term(engine.materialize(ctx, t))
             t.alpha = (alpha, row, k)
             terms.append(t)
         return terms
 
     def _run(self, ctx, x, alpha1, alpha2):
         terms = self._terms(ctx, x, alpha1, alpha2, 0)
+        ctx.join_lanes()             # the candidates' forward streams (engine.ExecCtx.on_sublane)
         t0 = terms[0].x
         out = engine.new_act(t0.N, t0.C, t0.D, t0.H, t0.W, ctx.device)
         return engine.affine_sum(ctx, terms, out)

@@ -10,8 +10,8 @@ import os
 
 
 class EngineConfig:
-    __slots__ = ("wgrad_stream", "wgrad_streams", "lanes", "virtual_cat", "gn_fold", "umma",
-                 "umma_min_c", "pw_fused_bwd")
+    __slots__ = ("wgrad_stream", "wgrad_streams", "lanes", "candidate_lanes", "virtual_cat", "gn_fold",
+                 "umma", "umma_min_c", "pw_fused_bwd")
 
     def __init__(self, env=os.environ):
         def flag(name, default):
@@ -27,6 +27,8 @@ class EngineConfig:
         self.wgrad_streams = max(1, min(4, integer("NAS3D_WGRAD_STREAMS", 1)))
         # stream lanes the independent edges of a cell node are spread over (1 = caller's stream)
         self.lanes = max(1, min(4, integer("NAS3D_LANES", 4)))
+        # supernet: the K candidate ops of a MixedOp run their FORWARD on streams of their own
+        self.candidate_lanes = flag("NAS3D_CANDIDATE_LANES", False)
         # cell outputs stay a virtual concat of their node buffers (cell.py:82 never copies)
         self.virtual_cat = flag("NAS3D_VIRTUAL_CAT", True)
         # GroupNorm coefficient kernels folded into the affine kernels' prologues.  Off: measured

@@ -80,8 +80,9 @@ class _Lane:
     caller's stream wait for the lanes.  Tensors allocated inside belong to the lane's allocator
     pool; they are only freed when the tape dies, after every stream has been joined."""
 
-    def __init__(self, ctx, k):
+    def __init__(self, ctx, k, forward_only=False):
         self.ctx, self.k = ctx, k
+        self.forward_only = forward_only     # tape entries keep the ENCLOSING lane (see on_sublane)
         self.tctx = None
 
     def __enter__(self):
@@ -93,17 +94,19 @@ class _Lane:
         ev = torch.cuda.Event()
         ev.record(main)
         lane.wait_event(ev)
-        self.saved = (ctx.stream, ctx.lane)
+        self.saved = (ctx.stream, ctx.lane, ctx.tape_lane)
         self.tctx = torch.cuda.stream(lane)
         self.tctx.__enter__()
         ctx.stream = lane.cuda_stream
         ctx.lane = k
+        if not self.forward_only:
+            ctx.tape_lane = k
         ctx.dirty_lanes.add(k)
         return self
 
     def __exit__(self, *exc):
         if self.tctx is not None:
-            self.ctx.stream, self.ctx.lane = self.saved
+            self.ctx.stream, self.ctx.lane, self.ctx.tape_lane = self.saved
             self.tctx.__exit__(*exc)
         return False
 
@@ -312,7 +315,8 @@ class ExecCtx:
         self.packed = {}
         self.pending_gn = []
         self.lanes = n_lanes()
-        self.lane = 0
+        self.lane = 0                # stream lane the forward is running on (tags GroupNorm jobs)
+        self.tape_lane = 0           # lane the backward of the entries being recorded will run on
         self.dirty_lanes = set()
 
     def use(self, *params):
@@ -322,10 +326,19 @@ class ExecCtx:
 
     def push(self, fn):
         if self.record:
-            self.tape.append(fn if self.lane == 0 else _Laned(fn, self.lane))
+            self.tape.append(fn if self.tape_lane == 0 else _Laned(fn, self.tape_lane))
 
     def on_lane(self, k):
         return _Lane(self, k % self.lanes)
+
+    def on_sublane(self, idx):
+        """FORWARD-only concurrency for the candidate ops of one MixedOp (cell.py:30): they read
+        the same input, so their dgrads accumulate into ONE gradient buffer and must stay serial -
+        the tape entries recorded inside keep the enclosing lane - but their forward kernels are
+        independent and run on a stream of their own (joined with the other lanes at the node)."""
+        if self.lanes <= 1 or not cfg.candidate_lanes:
+            return _Lane(self, 0)
+        return _Lane(self, 8 + (self.lane % 8) * 8 + (idx % 8), forward_only=True)
 
     def join_lanes(self, mark=False):
         """the caller's stream waits for every lane used since the last join; with mark=True the

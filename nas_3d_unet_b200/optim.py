@@ -15,6 +15,13 @@ parameters (nothing is uploaded; a captured CUDA graph keeps them as node consta
 lr / betas / eps / weight_decay and the step counter live in a device array, so a step captured in a
 CUDA graph (graph.GraphedStep) keeps counting and sees scheduler updates after `sync()`.
 Fails loudly (RuntimeError) for CPU tensors - there is no CPU fallback.
+
+Deviation from torch.optim.Adam, by design: the step counter is ONE value per param group (advanced
+by every `step()`), exported as every parameter's `step` in `state_dict()`; torch counts per
+parameter and skips parameters whose grad is None.  The reference loops give every parameter of a
+group a gradient on every step (search.py:222-238, train.py:121-128), where the two are identical; a
+torch Adam checkpoint with differing per-parameter steps loads with the group's maximum, and a
+parameter that is frozen for some steps gets the group's (larger) bias correction afterwards.
 """
 import ctypes as C
 

@@ -148,6 +148,22 @@ def test_supernet_matches_reference(golden_nets):
         assert e <= GRAD_TOL, (k, e)
 
 
+def test_supernet_with_candidate_lanes_matches_reference(golden_nets):
+    """engine option candidate_lanes: the K candidate ops of every MixedOp run their forward on
+    streams of their own (their backward stays serial on the edge's lane: they accumulate into one
+    input gradient) - same outputs, alpha and weight gradients as the golden reference run"""
+    G = golden_nets
+    with variant(candidate_lanes=True):
+        s = make_supernet().cuda()
+        x, y = O.synthetic_batch(1, 32, seed=3)
+        pred, loss = _run_net(s, x, y)
+        torch.cuda.synchronize()
+    _check_net(G, 'supernet32', s, pred, loss)
+    for k in ('alpha1_down', 'alpha1_up', 'alpha2_down', 'alpha2_up'):
+        e = rel_err(getattr(s, k).grad.cpu().numpy(), G['supernet32/dalpha/' + k])
+        assert e <= GRAD_TOL, (k, e)
+
+
 def test_search_steps_match_reference(golden_nets):
     """search.py:222-238 verbatim against our modules: alpha step on a val batch, w step on a
     train batch, torch Adam for both."""

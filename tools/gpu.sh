@@ -38,7 +38,7 @@ for cmd in "$@"; do
     test:*)  timeout 900 python -m pytest tests -m gpu -q -rA -k "$arg" > gpurun_out/${TAG}_pytest_k$i.log 2>&1
              echo "pytest -k '$arg' rc=$?"; grep -v "^PASSED" gpurun_out/${TAG}_pytest_k$i.log | tail -40 | cut -c1-400 ;;
     smoke)   timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3 ;;
-    bench)   timeout 900 python bench.py --steps 20 --warmup 5 --profile-out gpurun_out/${TAG}_kernels_per_shape.json \
+    bench)   timeout 900 python bench.py --steps 20 --warmup 5 --drivers-loop --profile-out gpurun_out/${TAG}_kernels_per_shape.json \
                  > gpurun_out/${TAG}_bench_searched128_b8_n1.json 2> gpurun_out/${TAG}_bench.err
              echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err | cut -c1-300; summ gpurun_out/${TAG}_bench_searched128_b8_n1.json ;;
     ab:*)    env $arg timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
