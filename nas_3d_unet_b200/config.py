@@ -27,8 +27,9 @@ class EngineConfig:
         self.wgrad_streams = max(1, min(4, integer("NAS3D_WGRAD_STREAMS", 1)))
         # stream lanes the independent edges of a cell node are spread over (1 = caller's stream)
         self.lanes = max(1, min(4, integer("NAS3D_LANES", 4)))
-        # supernet: the K candidate ops of a MixedOp run their FORWARD on streams of their own
-        self.candidate_lanes = flag("NAS3D_CANDIDATE_LANES", False)
+        # supernet: the K candidate ops of a MixedOp run their FORWARD on streams of their own (measured
+        # on B200: search step 26.1 -> 19.6 ms at 64^3, 42.4 -> 36.6 ms at 128^3, profiles/r3f_*)
+        self.candidate_lanes = flag("NAS3D_CANDIDATE_LANES", True)
         # cell outputs stay a virtual concat of their node buffers (cell.py:82 never copies)
         self.virtual_cat = flag("NAS3D_VIRTUAL_CAT", True)
         # GroupNorm coefficient kernels folded into the affine kernels' prologues.  Off: measured

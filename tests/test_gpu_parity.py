@@ -148,12 +148,14 @@ def test_supernet_matches_reference(golden_nets):
         assert e <= GRAD_TOL, (k, e)
 
 
-def test_supernet_with_candidate_lanes_matches_reference(golden_nets):
-    """engine option candidate_lanes: the K candidate ops of every MixedOp run their forward on
-    streams of their own (their backward stays serial on the edge's lane: they accumulate into one
-    input gradient) - same outputs, alpha and weight gradients as the golden reference run"""
+@pytest.mark.parametrize("lanes_on", [True, False])
+def test_supernet_with_candidate_lanes_matches_reference(golden_nets, lanes_on):
+    """engine option candidate_lanes (default on): the K candidate ops of every MixedOp run their
+    forward on streams of their own (their backward stays serial on the edge's lane: they accumulate
+    into one input gradient) - same outputs, alpha and weight gradients as the golden reference run,
+    with the option on and off"""
     G = golden_nets
-    with variant(candidate_lanes=True):
+    with variant(candidate_lanes=lanes_on):
         s = make_supernet().cuda()
         x, y = O.synthetic_batch(1, 32, seed=3)
         pred, loss = _run_net(s, x, y)
