@@ -504,7 +504,24 @@ def run_ours(args):
         def stream_dev():
             for _ in graphed.stream(dev_batches * args.steps):
                 pass
+        side = torch.cuda.Stream(device=dev)
+        scratch = torch.empty_like(hx, device=dev)
+
+        def alt_with_copy(frac, from_host):
+            n = int(hx.shape[0] * frac) or 1
+            src = hx[:n] if from_host else dx[:n]
+
+            def fn():
+                for i in range(args.steps):
+                    with torch.cuda.stream(side):
+                        scratch[:n].copy_(src, non_blocking=True)
+                    graphed.sets[i % nset][1].replay()
+                torch.cuda.current_stream().wait_stream(side)
+            return fn
         for name, fn in (("alternating replays, no copies", alt), ("stream(), device-resident batches", stream_dev),
+                         ("replays + unrelated H2D of x (268 MB)", alt_with_copy(1.0, True)),
+                         ("replays + unrelated H2D of x/4 (67 MB)", alt_with_copy(0.25, True)),
+                         ("replays + unrelated D2D of x (268 MB)", alt_with_copy(1.0, False)),
                          ("stream(), pinned host batches", lambda: run_e2e(args.steps))):
             fn()
             print("e2e-probe %-36s %.3f ms/step" % (name, timed(fn, 1) / args.steps), file=sys.stderr)

@@ -55,7 +55,7 @@ int nas3d_launch_labels(char* buf, int cap);
  * (NAS3D_<UPPERCASE NAME>) when the library is loaded and changed afterwards only here; no launch
  * path reads the environment.  Names: tiled, tma, tma_merged, affine_ring, apply_ring,
  * reduce_ring, pw_fwd_ring, reduce_waves, ring_min_log2, pw_vpt_sfb, pw_vpt_bfs, pw_vpt_mom,
- * umma_wgrad, umma_wgrad_min_c.  set: 0 or NAS3D_ERR_ARG (unknown name / value out of range); get: the value
+ * umma_split_k, umma_wgrad, umma_wgrad_min_c.  set: 0 or NAS3D_ERR_ARG (unknown name / value out of range); get: the value
  * (>= 0) or NAS3D_ERR_ARG. */
 /* Roofline probe: one launch of pure packed-fp32-FMA chains (no memory traffic) over all SMs;
  * returns the flops it executes (> 0) or a negative status.  bench.py times it with CUDA events
@@ -373,6 +373,10 @@ int nas3d_seg_to_masks(const short* seg, int N, long long V, int inclusive, floa
  * base + stride_d*d + stride_h*h + stride_w*w (signed; identity = {0, H*W, W, 1}).  N <= 64.
  * seg / y_out may both be NULL. */
 int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, int H, int W,
+                        const int* index_map, int inclusive, float* x_out, int ld_out,
+                        signed char* y_out, void* stream);
+/* same with the segmentation as int8 (the label values 0, 1, 2, 4 fit): 1 byte per voxel over PCIe */
+int nas3d_stage_patches_seg8(const float* x, const signed char* seg, int N, int C, int D, int H, int W,
                         const int* index_map, int inclusive, float* x_out, int ld_out,
                         signed char* y_out, void* stream);
 

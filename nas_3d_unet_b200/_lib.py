@@ -69,6 +69,8 @@ _SIGNATURES = {
                                 _PP, _PP, _PP, _PP, _PP, _PP, _PP, c_vp],
     "nas3d_stage_patches": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, _PI, c_int, c_vp, c_int, c_vp,
                             c_vp],
+    "nas3d_stage_patches_seg8": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, _PI, c_int, c_vp, c_int, c_vp,
+                            c_vp],
     "nas3d_adam_chunk_floats": [],
     "nas3d_adam_flat_step": [c_vp, c_vp, c_vp, _PP, c_int, _PI, c_vp, c_vp, c_vp],
     "nas3d_se_excite": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp],

@@ -25,6 +25,8 @@ struct Options {
   int reduce_waves = 1;   // whole-wave grid sizing of the backward reductions
   int ring_min_log2 = 22; // smallest tensor (log2 float4 elements) the ring kernels take
   int pw_vpt_sfb = 4, pw_vpt_bfs = 2, pw_vpt_mom = 2;   // voxels per thread of the 1x1 kernels
+  int umma_split_k = 1;   // tcgen05 fwd / dgrad: split the taps over CTAs (fp32 atomics) when the voxel tiles alone
+                          // cannot fill the machine; 0 = one CTA walks all taps of its tile (bit-reproducible)
   int umma_wgrad = 1;     // tcgen05 weight gradient of the wide dense 3x3x3 convs (conv_umma_wgrad.cu)
   int umma_wgrad_min_c = 32;   // ... always from this channel count up; 16 channels only for small K
 };

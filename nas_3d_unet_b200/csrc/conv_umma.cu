@@ -557,7 +557,7 @@ int nas3d_umma_conv(const nas3d_conv_desc* d, int produce_big, const float* src,
   const long long tiles = (A.nvox + 127) / 128;
   const int Cprod = produce_big ? d->Cb : d->Cs;
   int splits = 1;
-  if (!A.cls && tiles < kNumSMs && A.ldd == Cprod) {
+  if (g_opt.umma_split_k && !A.cls && tiles < kNumSMs && A.ldd == Cprod) {
     splits = (int)(kNumSMs / tiles);
     if (splits > 9) splits = 9;
     if (splits < 1) splits = 1;

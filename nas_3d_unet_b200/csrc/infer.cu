@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256)
 constexpr int kStageMaxN = 64;
 struct StageArgs {
   const float* x;        // [N][C][V] planar (what np.asarray(x_list) uploads)
-  const short* seg;      // [N][V] or NULL
+  const void* seg;       // [N][V] int16 (as stored) or int8 (values 0,1,2,4 fit: half the PCIe bytes), or NULL
+  int seg_bytes;         // 2 | 1
   float* xo;             // [N][V][ld]
   signed char* yo;       // [N][3][V] or NULL
   int N, C, D, H, W, ld, inclusive;
@@ -174,7 +175,9 @@ __global__ void __launch_bounds__(256) stage_patches_kernel(const __grid_constan
       for (int c = a.C; c < a.ld; ++c) o[c] = 0.f;
     }
     if (a.seg != nullptr) {
-      const short t = __ldg(a.seg + (long long)n * V + src);
+      const long long si = (long long)n * V + src;
+      const short t = a.seg_bytes == 2 ? __ldg(static_cast<const short*>(a.seg) + si)
+                                       : (short)__ldg(static_cast<const signed char*>(a.seg) + si);
       signed char c0, c1, c2;
       if (a.inclusive) {
         c0 = (t == 1 || t == 4); c1 = (t == 1 || t == 2); c2 = (t == 4);   // WT quirk, see below
@@ -198,9 +201,9 @@ using namespace nas3d;
 
 extern "C" {
 
-int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, int H, int W,
-                        const int* index_map, int inclusive, float* x_out, int ld_out,
-                        signed char* y_out, void* stream) {
+static int stage_patches_impl(const float* x, const void* seg, int seg_bytes, int N, int C, int D, int H, int W,
+                              const int* index_map, int inclusive, float* x_out, int ld_out,
+                              signed char* y_out, void* stream) {
   NAS3D_REQUIRE(x && x_out && index_map, "stage_patches: null pointer");
   NAS3D_REQUIRE(N >= 1 && N <= kStageMaxN, "stage_patches: batch %d outside [1,%d]", N, kStageMaxN);
   NAS3D_REQUIRE(C >= 1 && ld_out >= C && D > 0 && H > 0 && W > 0, "stage_patches: bad shape");
@@ -208,7 +211,7 @@ int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, i
   const long long V = (long long)D * H * W;
   NAS3D_REQUIRE(V < (1ll << 31), "stage_patches: patch too large");
   StageArgs a;
-  a.x = x; a.seg = seg; a.xo = x_out; a.yo = y_out;
+  a.x = x; a.seg = seg; a.seg_bytes = seg_bytes; a.xo = x_out; a.yo = y_out;
   a.N = N; a.C = C; a.D = D; a.H = H; a.W = W; a.ld = ld_out; a.inclusive = inclusive;
   for (int n = 0; n < N; ++n) {
     const int* m = index_map + 4 * n;
@@ -227,6 +230,18 @@ int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, i
                 "stage_patches: x_out must be 16-byte aligned");
   stage_patches_kernel<<<g1d(V * N), 256, 0, (cudaStream_t)stream>>>(a);
   return launched("stage_patches");
+}
+
+int nas3d_stage_patches(const float* x, const short* seg, int N, int C, int D, int H, int W,
+                        const int* index_map, int inclusive, float* x_out, int ld_out,
+                        signed char* y_out, void* stream) {
+  return stage_patches_impl(x, seg, 2, N, C, D, H, W, index_map, inclusive, x_out, ld_out, y_out, stream);
+}
+
+int nas3d_stage_patches_seg8(const float* x, const signed char* seg, int N, int C, int D, int H, int W,
+                             const int* index_map, int inclusive, float* x_out, int ld_out,
+                             signed char* y_out, void* stream) {
+  return stage_patches_impl(x, seg, 1, N, C, D, H, W, index_map, inclusive, x_out, ld_out, y_out, stream);
 }
 
 int nas3d_extract_patches(const float* volume, int C, int D, int H, int W, const int* corners_dev,

@@ -24,6 +24,7 @@ static const OptEntry kOptions[] = {
     {"pw_vpt_sfb", &Options::pw_vpt_sfb, 1, 4},
     {"pw_vpt_bfs", &Options::pw_vpt_bfs, 1, 4},
     {"pw_vpt_mom", &Options::pw_vpt_mom, 1, 4},
+    {"umma_split_k", &Options::umma_split_k, 0, 1},
     {"umma_wgrad", &Options::umma_wgrad, 0, 1},
     {"umma_wgrad_min_c", &Options::umma_wgrad_min_c, 16, 128},
 };

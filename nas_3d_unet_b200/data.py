@@ -65,7 +65,8 @@ def index_map(key, shape):
 
 def stage_batch(x, seg=None, keys=None, inclusive_label=True):
     """device-side batch assembly: x (N,C,D,H,W) float32 CUDA (planar, as uploaded), seg (N,1,D,H,W)
-    int16 CUDA or None, keys = one permutation key per sample (or None = no permutation).
+    int16 (as the h5 files store it) or int8 (the labels 0, 1, 2, 4 fit: 1 byte per voxel over PCIe)
+    CUDA or None, keys = one permutation key per sample (or None = no permutation).
     Returns (x in channels_last_3d memory - what the stem reads without a layout pass,
              y (N,3,D,H,W) int8 region masks or None)  [generator.py:195-248]"""
     if not x.is_cuda or x.dtype != torch.float32:
@@ -73,8 +74,8 @@ def stage_batch(x, seg=None, keys=None, inclusive_label=True):
     x = x.contiguous()
     N, C, D, H, W = x.shape
     if seg is not None:
-        if not seg.is_cuda or seg.dtype != torch.int16 or seg.numel() != N * D * H * W:
-            raise TypeError("stage_batch: seg must be CUDA int16 of shape (N,1,D,H,W)")
+        if not seg.is_cuda or seg.dtype not in (torch.int16, torch.int8) or seg.numel() != N * D * H * W:
+            raise TypeError("stage_batch: seg must be CUDA int16 or int8 of shape (N,1,D,H,W)")
         seg = seg.contiguous()
     if keys is None:
         keys = [None] * N
@@ -89,7 +90,8 @@ def stage_batch(x, seg=None, keys=None, inclusive_label=True):
     lib = _lib.load()
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.nas3d_stage_patches(
+        fn = lib.nas3d_stage_patches_seg8 if (seg is not None and seg.dtype == torch.int8) else lib.nas3d_stage_patches
+        _lib.check(fn(
             x.data_ptr(), seg.data_ptr() if seg is not None else None, N, C, D, H, W,
             _lib.int_array(maps), 1 if inclusive_label else 0, xo.data_ptr(), ld,
             yo.data_ptr() if yo is not None else None, st), "stage_patches")

@@ -100,7 +100,7 @@ def gather_patch_predictions(local, n_total, group=None):
 
 class SlidingWindowPredictor:
     def __init__(self, model, patch_shape=(128, 128, 128), batch=8, threshold=0.5,
-                 inclusive_label=True, patch_overlap=None, group=None):
+                 inclusive_label=True, patch_overlap=None, group=None, deterministic=False):
         self.model = model
         self.patch_shape = tuple(int(p) for p in patch_shape)
         self.batch = int(batch)
@@ -108,6 +108,11 @@ class SlidingWindowPredictor:
         self.inclusive = bool(inclusive_label)
         self.overlap = patch_overlap
         self.group = group
+        # the reference's CPU inference is bit-reproducible; ours is too once the tcgen05 convs of the
+        # deep levels stop splitting their taps over CTAs (fp32 atomics reorder sums at the 1e-7 level,
+        # which flips a handful of labels per volume where a probability sits on the threshold).
+        # deterministic=True costs ~10 % of a volume's time (18.0 -> 20.0 ms at 240x240x155, measured)
+        self.deterministic = bool(deterministic)
 
     @torch.no_grad()
     def predict_patches(self, volume, corners):
@@ -125,6 +130,8 @@ class SlidingWindowPredictor:
         chunks, ld_pred = [], None
         was_training = self.model.training
         self.model.eval()
+        split_k = _lib.option("umma_split_k", 0 if self.deterministic else 1)
+        split_k.__enter__()
         try:
             for b0 in range(0, B, self.batch):
                 nb = min(self.batch, B - b0)
@@ -140,6 +147,7 @@ class SlidingWindowPredictor:
                 ld_pred = l
                 chunks.append(y)
         finally:
+            split_k.__exit__(None, None, None)
             self.model.train(was_training)
         return chunks, ld_pred
 

@@ -53,6 +53,9 @@ def test_stage_batch_permutation_and_labels_bit_exact():
         ref_s = np.stack([seg[n] if k is None else O.permute_data(seg[n], k) for n, k in enumerate(keys)])
         np.testing.assert_array_equal(xo.cpu().numpy(), ref_x)
         np.testing.assert_array_equal(yo.cpu().numpy(), O.multi_class_labels(ref_s, inclusive))
+        # the same segmentation sent as int8 (1 byte per voxel over PCIe): identical masks
+        _, yo8 = stage_batch(torch.as_tensor(x).cuda(), torch.as_tensor(seg.astype(np.int8)).cuda(), keys, inclusive)
+        assert torch.equal(yo8, yo)
     # non-cubic patch, flips only, odd channel count, no labels
     x2 = rng.standard_normal((2, 3, 6, 10, 12)).astype(np.float32)
     k2 = [((0, 0), 1, 0, 1, 0), ((0, 0), 0, 1, 0, 0)]

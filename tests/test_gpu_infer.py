@@ -127,3 +127,16 @@ def test_brats_shape_volume_at_128_matches_oracle():
     with torch.no_grad():
         ref0 = O.searched_net(sd, x0, 4, 3, O.G0)[0]
     assert O.max_rel(preds[0].permute(3, 0, 1, 2), ref0) <= 1e-3
+
+
+def test_deterministic_predictor_is_bit_reproducible():
+    """SlidingWindowPredictor(deterministic=True): no split-K atomics in the tcgen05 convs - two runs
+    give identical float64 stitched probabilities and labels (the reference's CPU path is
+    bit-reproducible; the default predictor trades that for ~10 % speed)"""
+    from nas_3d_unet_b200.infer import SlidingWindowPredictor
+    model = make_searched().cuda()
+    vol = torch.as_tensor(_volume(6, (4, 70, 66, 40))).cuda()
+    pred = SlidingWindowPredictor(model, patch_shape=(32, 32, 32), batch=5, deterministic=True)
+    l1, s1, _, _ = pred.predict(vol, return_stitched=True)
+    l2, s2, _, _ = pred.predict(vol, return_stitched=True)
+    assert torch.equal(s1, s2) and torch.equal(l1, l2)

@@ -5,12 +5,12 @@
     python -m torch.distributed.run --nproc-per-node N ... tools/bench_inference.py [NVOL]
 
 Under torchrun (one process per GPU, NCCL) it measures BOTH shardings of SURVEY 8e and checks their
-label volumes against the single-GPU result.  The network forward is not bit-reproducible from run to
-run (fp32 atomics of the split-K tcgen05 convs at the deep levels reorder sums at the 1e-7 level), and
-a RANDOM-INIT net puts most probabilities within 1e-3 of the 0.5 threshold, so a handful of voxels per
-volume flips label even between two runs on the same GPU: the line reports that run-to-run baseline
-(`rerun_mismatch_voxels`) next to the mismatches of each sharding; a gather / ordering bug would
-flip whole patches (millions of voxels).  The ordering itself is proven bit-exactly with
+label volumes against the single-GPU result, voxel for voxel.  Throughput is timed with the default
+predictor; the CHECKS run a second, `deterministic=True` predictor (no split-K atomics in the tcgen05
+convs: the forward is bit-reproducible, at ~10 % of the speed), so their expected mismatch count is 0
+- `rerun_mismatch_voxels` is the same-GPU run-to-run baseline of that predictor.  (With the default
+predictor a random-init net, whose probabilities sit within 1e-3 of the threshold, flips 3-9 of 35.7 M
+voxels from run to run: profiles/r3c / r3i.)  The gather ordering is additionally proven with
 deterministic stand-in predictions over gloo in tests/test_infer_shard_gloo.py.
   volumes: NVOL (>= N) different volumes dealt round-robin to the ranks, no communication;
   patches: one volume at a time, its 9 patches dealt to the ranks, predictions all-gathered,
@@ -49,6 +49,7 @@ def main():
     model = SearchedNet(4, 4, 3, 4, 3, True, G0).to(dev).eval()
     host = [torch.as_tensor(volume(100 + i)).pin_memory() for i in range(nvol)]
     pred = SlidingWindowPredictor(model, (128, 128, 128), batch=9)
+    pred_det = SlidingWindowPredictor(model, (128, 128, 128), batch=9, deterministic=True)
 
     def barrier():
         if world > 1:
@@ -67,17 +68,17 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return out, ms.item()
 
-    def run_volumes():          # volume-sharded: this rank's volumes, whole, no communication
+    def run_volumes(p=pred):    # volume-sharded: this rank's volumes, whole, no communication
         out = {}
         for i in shard_indices(nvol, rank, world):
-            out[i] = pred.predict(host[i].to(dev, non_blocking=True), shard_patches=False).cpu()
+            out[i] = p.predict(host[i].to(dev, non_blocking=True), shard_patches=False).cpu()
         return out
 
-    def run_patches():          # patch-sharded: every volume on all ranks together
-        return {i: pred.predict(host[i].to(dev, non_blocking=True)).cpu() for i in range(nvol)}
+    def run_patches(p=pred):    # patch-sharded: every volume on all ranks together
+        return {i: p.predict(host[i].to(dev, non_blocking=True)).cpu() for i in range(nvol)}
 
-    def run_single():           # what one GPU alone produces (the truth for the checks)
-        return {i: pred.predict(host[i].to(dev, non_blocking=True), shard_patches=False).cpu()
+    def run_single(p=pred):     # what one GPU alone produces (the truth for the checks)
+        return {i: p.predict(host[i].to(dev, non_blocking=True), shard_patches=False).cpu()
                 for i in range(nvol)}
 
     for _ in range(2):
@@ -88,9 +89,11 @@ def main():
         return int(sum(int((a[i] != b[i]).sum()) for i in a))
 
     nvox = 240 * 240 * 155
-    truth, ms1 = timed(run_single)
-    again, _ = timed(run_single)
-    line["rerun_mismatch_voxels"] = mismatches(again, truth)
+    _, ms1 = timed(run_single)
+    truth = run_single(pred_det)
+    line["rerun_mismatch_voxels"] = mismatches(run_single(pred_det), truth)
+    _, msd = timed(lambda: run_single(pred_det))
+    line["deterministic_ms_per_volume"] = msd / nvol
     line["voxels_per_volume"] = nvox
     line["per_gpu_alone"] = {"ms_per_volume": ms1 / nvol, "volumes_per_s": nvol / ms1 * 1e3,
                              "patches_per_s": 9 * nvol / ms1 * 1e3}
@@ -99,20 +102,20 @@ def main():
         line["value"] = line["per_gpu_alone"]["volumes_per_s"]
     else:
         run_volumes()
-        got_v, msv = timed(run_volumes)
+        _, msv = timed(run_volumes)
         run_patches()
-        got_p, msp = timed(run_patches)
-        mm = torch.tensor([mismatches(got_v, truth), mismatches(got_p, truth)], device=dev)
+        _, msp = timed(run_patches)
+        mm = torch.tensor([mismatches(run_volumes(pred_det), truth), mismatches(run_patches(pred_det), truth)],
+                          device=dev)
         dist.all_reduce(mm, op=dist.ReduceOp.MAX)           # worst rank
-        tol = max(10 * (line["rerun_mismatch_voxels"] + 1), int(1e-5 * nvox * nvol))
-        flags = (mm <= tol).to(torch.int32)
+        flags = (mm <= line["rerun_mismatch_voxels"]).to(torch.int32)      # expected: 0 == 0
         line["volume_sharded"] = {"ms_total": msv, "volumes_per_s": nvol / msv * 1e3,
                                   "patches_per_s": 9 * nvol / msv * 1e3,
                                   "label_mismatch_voxels_vs_single_gpu": int(mm[0].item()),
-                                  "within_rerun_noise": bool(flags[0].item())}
+                                  "bit_equal_to_single_gpu": bool(flags[0].item())}
         line["patch_sharded"] = {"ms_per_volume": msp / nvol, "volumes_per_s": nvol / msp * 1e3,
                                  "label_mismatch_voxels_vs_single_gpu": int(mm[1].item()),
-                                 "within_rerun_noise": bool(flags[1].item())}
+                                 "bit_equal_to_single_gpu": bool(flags[1].item())}
         line["value"] = line["volume_sharded"]["volumes_per_s"]
     if rank == 0:
         print(json.dumps(line), flush=True)
