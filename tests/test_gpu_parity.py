@@ -821,3 +821,76 @@ def test_any_loss_backpropagates_through_the_pitched_head():
         grads.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
     assert float(grads[0].abs().max()) > 0
     assert O.max_rel(grads[0], grads[1]) <= REORDER_TOL
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_searched_net_with_random_genotypes_matches_oracle(seed):
+    """genotypes other than G0: derived with get_gene() from random alphas, so pools, SE convs,
+    depthwise-separable, dilated and plain (transposed) convs all appear inside the U-Net wiring;
+    logits, Dice and flat gradient against the live fp32 oracle at 32^3"""
+    from nas_3d_unet_b200.nas import ShellNet
+    from nas_3d_unet_b200.searched import SearchedNet
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    torch.manual_seed(seed)
+    shell = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True)
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(100 + seed)
+        for p in shell.alphas():
+            p.copy_(2.0 * torch.randn(p.shape, generator=g))
+    gene = shell.get_gene()
+    og = O.get_gene(O.leaf_state(shell.state_dict()), 3)
+    assert [tuple(t) for t in gene.down] == [tuple(t) for t in og.down]
+    assert [tuple(t) for t in gene.up] == [tuple(t) for t in og.up]
+    torch.manual_seed(seed)
+    m = SearchedNet(4, 4, 3, 4, 3, True, gene)
+    m.eval()
+    x, y = O.synthetic_batch(2, 32, seed=seed, brain_like=True)
+    sd = O.leaf_state(m.state_dict())
+    ref = O.searched_net(sd, x, 4, 3, O.Genotype(down=list(gene.down), up=list(gene.up)))
+    ref_loss = O.dice_loss(ref, y)
+    ref_loss.backward()
+    m = m.cuda()
+    pred = m(x.cuda())
+    loss = WeightedDiceLoss()(pred, y.cuda())
+    loss.backward()
+    flat_o = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu()
+    flat_r = torch.cat([sd[k].grad.reshape(-1) for k, _ in m.named_parameters()])
+    print(seed, [n for n, _ in gene.down], [n for n, _ in gene.up],
+          "logits %.2e dice %.2e grad %.2e" % (O.max_rel(pred, ref), abs(loss.item() - ref_loss.item()),
+                                                O.max_rel(flat_o, flat_r)))
+    assert O.max_rel(pred, ref) <= LOGIT_TOL
+    assert abs(loss.item() - ref_loss.item()) <= DICE_TOL
+    assert O.max_rel(flat_o, flat_r) <= GRAD_TOL
+
+
+def test_supernet_small_config_with_shared_normal_alphas_matches_oracle():
+    """a non-default ShellNet: depth 2, 2 nodes per cell, no channel doubling, normal_w_share=True
+    (alpha1_up aliases alpha1_down, nas.py:108-113: its gradient is the SUM over both uses)"""
+    from nas_3d_unet_b200.nas import ShellNet
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    torch.manual_seed(4)
+    s = ShellNet(4, 4, 3, 2, 2, normal_w_share=True, channel_change=False)
+    s.kernel.last_conv[0].dropout.p = 0.0
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(8)
+        for p in s.alphas():
+            p.copy_(0.5 * torch.randn(p.shape, generator=g))
+    x, y = O.synthetic_batch(2, 16, seed=6)
+    sd = O.leaf_state(s.state_dict())
+    ref = O.shell_net(sd, x, 2, 2)
+    ref_loss = O.dice_loss(ref, y)
+    ref_loss.backward()
+    s = s.cuda()
+    pred = s(x.cuda())
+    loss = WeightedDiceLoss()(pred, y.cuda())
+    loss.backward()
+    assert s.alpha1_up is s.alpha1_down
+    assert O.max_rel(pred, ref) <= LOGIT_TOL and abs(loss.item() - ref_loss.item()) <= DICE_TOL
+    shared = sd['alpha1_down'].grad + sd['alpha1_up'].grad
+    assert O.max_rel(s.alpha1_down.grad, shared) <= GRAD_TOL
+    for k in ('alpha2_down', 'alpha2_up'):
+        assert O.max_rel(getattr(s, k).grad, sd[k].grad) <= GRAD_TOL, k
+    names = [k for k, _ in s.named_parameters() if k.startswith('kernel.')]
+    flat_o = torch.cat([dict(s.named_parameters())[k].grad.reshape(-1) for k in names]).cpu()
+    flat_r = torch.cat([sd[k].grad.reshape(-1) for k in names])
+    assert O.max_rel(flat_o, flat_r) <= GRAD_TOL
