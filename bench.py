@@ -45,6 +45,10 @@ def parse():
                     help="--impl reference: skip the single extra step at the full batch size")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step as one CUDA graph (nas_3d_unet_b200.graph.GraphedStep)")
+    ap.add_argument("--labels", default="seg8", choices=["seg8", "masks"],
+                    help="what crosses PCIe next to x: seg8 = the int8 segmentation (1 byte per voxel), region "
+                         "masks assembled and x re-laid out on the device by data.stage_batch (SURVEY 8 f2); "
+                         "masks = three int8 {0,1} masks per voxel as generator.py:230-248 yields them")
     ap.add_argument("--graph-buffers", type=int, default=2, choices=[1, 2],
                     help="static input sets / captured graphs (2: H2D straight into the idle set, GraphedStep.stream)")
     ap.add_argument("--drivers-loop", action="store_true",
@@ -62,15 +66,25 @@ def parse():
 # ------------------------------------------------------------------------------------------
 # synthetic data: background 0 / brain U(10,110); labels nested blobs
 # ------------------------------------------------------------------------------------------
-def synthetic_host_batch(batch, patch, seed):
+def synthetic_host_batch(batch, patch, seed, with_seg=False):
+    """x (B,4,P,P,P) fp32; y (B,3,P,P,P) fp32 region masks = get_multi_class_labels(seg,
+    inclusive_label=True) (generator.py:230-248, with its logical_or quirk) of a segmentation of nested
+    blobs 2 > 1 > 4; with_seg also returns that segmentation (B,1,P,P,P) int8"""
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(batch, 4, patch, patch, patch, generator=g) * 100 + 10
     zz, yy, xx = torch.meshgrid(*[torch.arange(patch, dtype=torch.float32)] * 3, indexing="ij")
     c = (patch - 1) / 2
     r2 = ((zz - c) ** 2 + (yy - c) ** 2 + (xx - c) ** 2) / (patch / 2) ** 2
     x = x * (r2 < 0.9).float()
-    y = torch.stack([(r2 < 0.05), (r2 < 0.15), (r2 < 0.02)]).float().unsqueeze(0).repeat(batch, 1, 1, 1, 1)
-    return x.contiguous(), y.contiguous()
+    seg = torch.zeros_like(r2, dtype=torch.int8)
+    seg[r2 < 0.15] = 2
+    seg[r2 < 0.05] = 1
+    seg[r2 < 0.02] = 4
+    y = torch.stack([(seg == 1) | (seg == 4), (seg == 1) | (seg == 2), seg == 4]).float()
+    y = y.unsqueeze(0).repeat(batch, 1, 1, 1, 1).contiguous()
+    if with_seg:
+        return x.contiguous(), y, seg.reshape(1, 1, patch, patch, patch).repeat(batch, 1, 1, 1, 1).contiguous()
+    return x.contiguous(), y
 
 
 class ClockSampler:
@@ -301,8 +315,9 @@ def workload_config(args):
         "patch": args.patch, "batch_per_gpu": args.batch,
         "global_batch": args.batch * args.gpus,
         "parallelism": "dp%d" % args.gpus,
-        "l2": "inputs larger than L2 (%.0f MB of x (fp32) + y (int8 masks) per step per GPU vs 126 MB L2)"
-              % (((4 * 4 + 3) * args.patch ** 3 * args.batch) / 1e6),
+        "l2": "inputs larger than L2 (%.0f MB of x (fp32) + %s per step per GPU vs 126 MB L2)"
+              % (((4 * 4 + (1 if args.labels == "seg8" else 3)) * args.patch ** 3 * args.batch) / 1e6,
+                 "int8 segmentation (masks assembled on the device)" if args.labels == "seg8" else "y (int8 masks)"),
     }
     return cfg
 
@@ -351,30 +366,43 @@ def run_ours(args):
     model.train()
 
     B, P = args.batch, args.patch
-    hx, hy = synthetic_host_batch(B, P, seed=1234 + rank)
-    # labels travel as int8 {0,1} masks, which is what generator.py:230-248 hands the drivers
-    hx, hy = hx.pin_memory(), hy.to(torch.int8).pin_memory()
+    staged = args.labels == "seg8"
+    hx, hmask, hseg = synthetic_host_batch(B, P, seed=1234 + rank, with_seg=True)
+    # labels travel as the int8 segmentation (the device assembles the masks) or as int8 {0,1} masks,
+    # which is what generator.py:230-248 hands the drivers
+    hx, hy = hx.pin_memory(), (hseg if staged else hmask.to(torch.int8)).pin_memory()
     if args.workload == "supernet":
-        hvx, hvy = synthetic_host_batch(B, P, seed=4321 + rank)
-        hvx, hvy = hvx.pin_memory(), hvy.to(torch.int8).pin_memory()
+        hvx, hvmask, hvseg = synthetic_host_batch(B, P, seed=4321 + rank, with_seg=True)
+        hvx, hvy = hvx.pin_memory(), (hvseg if staged else hvmask.to(torch.int8)).pin_memory()
+
+    def prep(x, y):
+        """device-side batch assembly (data.stage_batch: NCDHW -> channels-last, int8 seg -> int8 masks)"""
+        if not staged:
+            return x, y
+        from nas_3d_unet_b200.data import stage_batch
+        return stage_batch(x, y, None, True)
     dx, dy = hx.to(dev), hy.to(dev)
     if args.workload == "supernet":
         dvx, dvy = hvx.to(dev), hvy.to(dev)
     patches_per_step = B * world
 
+    def fwd_loss(x, y):
+        xs, ys = prep(x, y)
+        return lossf(model(xs), ys)
+
     def step_resident():
         if args.workload == "searched":
             opts[0].zero_grad()
-            loss = lossf(model(dx), dy)
+            loss = fwd_loss(dx, dy)
             loss.backward()
             opts[0].step()
         else:
             opts[0].zero_grad()
-            vl = lossf(model(dvx), dvy)
+            vl = fwd_loss(dvx, dvy)
             vl.backward()
             opts[0].step()
             opts[1].zero_grad()
-            loss = lossf(model(dx), dy)
+            loss = fwd_loss(dx, dy)
             loss.backward()
             opts[1].step()
         return loss
@@ -382,13 +410,14 @@ def run_ours(args):
     def step_fn(*batch):
         """one complete step on device tensors; returns the (last) loss tensor"""
         if args.workload == "searched":
-            x, y = batch
+            x, y = prep(*batch)
             opts[0].zero_grad(set_to_none=True)
             loss = lossf(model(x), y)
             loss.backward()
             opts[0].step()
             return loss
-        x, y, vx, vy = batch
+        x, y = prep(*batch[:2])
+        vx, vy = prep(*batch[2:])
         opts[0].zero_grad(set_to_none=True)
         vl = lossf(model(vx), vy)
         vl.backward()
@@ -430,14 +459,15 @@ def run_ours(args):
             return last
         for batch in DevicePrefetcher(host_batches(nsteps), dev):
             if args.workload == "searched":
-                x, y = batch
+                x, y = prep(*batch)
                 opts[0].zero_grad()
                 loss = lossf(model(x), y)
                 last = loss.item()
                 loss.backward()
                 opts[0].step()
             else:
-                x, y, vx, vy = batch
+                x, y = prep(*batch[:2])
+                vx, vy = prep(*batch[2:])
                 opts[0].zero_grad()
                 vl = lossf(model(vx), vy)
                 last = vl.item()
@@ -551,7 +581,7 @@ def run_ours(args):
             dmodel = ShellNet(4, 4, 3, 4, 3, normal_w_share=False, channel_change=True).to(dev)
             dopts = [torch.optim.Adam(dmodel.alphas()), torch.optim.Adam(dmodel.kernel.parameters())]
         dmodel.train()
-        nx, ny = hx.numpy().copy(), hy.numpy().astype(np.int8)        # what generator.convert_data yields
+        nx, ny = hx.numpy().copy(), hmask.numpy().astype(np.int8)     # what generator.convert_data yields
 
         def driver_step():
             last = 0.0
