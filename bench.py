@@ -39,8 +39,12 @@ def parse():
     ap.add_argument("--ref-device", choices=["cpu", "cuda"], default="cpu",
                     help="--impl reference only: cuda = the same torch ops through torch's CUDA "
                          "kernels (informational second baseline, BASELINE.md section 4)")
-    ap.add_argument("--ref-batch", type=int, default=1,
-                    help="--impl reference: patches per timed CPU step (bounded sample of the workload)")
+    ap.add_argument("--ref-batch", type=int, default=0,
+                    help="--impl reference: patches per timed CPU step; 0 = the workload's own batch if "
+                         "(steps + warmup) of them fit --ref-budget seconds, else the largest power of two that "
+                         "does (bounded sample of the workload; the line says which)")
+    ap.add_argument("--ref-budget", type=float, default=240.0,
+                    help="--impl reference: wall-clock budget in seconds used to size the CPU step's batch")
     ap.add_argument("--no-batch-probe", action="store_true",
                     help="--impl reference: skip the single extra step at the full batch size")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
@@ -162,7 +166,8 @@ def _reference_modules():
     return mods
 
 
-def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu", probe_batch=0):
+def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu", probe_batch=0,
+                        full_batch=None, budget_s=240.0):
     """times `steps` training steps of the reference path on the host cores; returns (patches/s,
     s/step, cores, kind, sample description, extra).  kind "reference": the reference's own modules
     (train.py:121-128 / search.py:222-238 loop bodies around them); kind "port": the oracle port
@@ -239,6 +244,21 @@ def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu", p
         if device != "cpu":
             torch.cuda.synchronize()
 
+    if batch <= 0:
+        # size the sample: one batch-1 step (it doubles as a warm-up), then the largest batch whose
+        # (steps + warmup) steps fit the budget.  Measured on the 16-thread GPU box: a batch-8 step costs
+        # 4.6x a batch-1 step (0.63 -> 1.09 patches/s), hence the 0.6 per extra patch.
+        t0 = time.perf_counter()
+        make_step(1)()
+        sync()
+        t1 = time.perf_counter() - t0
+        batch = 1
+        b = full_batch or 1
+        while b > 1:
+            if (steps + warmup) * t1 * (1 + 0.6 * (b - 1)) <= budget_s:
+                batch = b
+                break
+            b //= 2
     one = make_step(batch)
     for _ in range(warmup):
         one()
@@ -265,6 +285,7 @@ def cpu_reference_steps(workload, patch, steps, warmup, batch=1, device="cpu", p
     sample = ("%s net, %d step(s) of batch %d at %d^3 (fwd + Dice + bwd + Adam), %s on %s"
               % (workload, steps, batch, patch, what,
                  "%d host threads" % torch.get_num_threads() if device == "cpu" else "torch eager CUDA (cuDNN)"))
+    extra["batch"] = batch
     return batch / dt, dt, torch.get_num_threads(), kind, sample, extra
 
 
@@ -272,14 +293,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample of the workload: ONE patch per timed step (--ref-batch to change; GroupNorm and
-    # Dice are per-sample, so the arithmetic per patch is that of the full batch), plus one probe
-    # step at the full batch so the line shows how CPU patches/s moves with the batch
+    # the workload's own batch per timed step when (steps + warmup) of them fit the time budget
+    # (--ref-budget, default 4 minutes), else a bounded sample at a smaller batch - CPU patches/s is NOT
+    # flat in the batch (0.63 at batch 1, 1.09 at batch 8 on the 16-thread box), so the line states the
+    # batch it timed and, when that is not the full one, a single probe step at the full batch
     on_gpu = args.ref_device == "cuda"
-    b = args.batch if on_gpu else args.ref_batch
     v, dt, cores, kind, sample, extra = cpu_reference_steps(
-        args.workload, args.patch, args.steps, args.warmup, batch=b, device=args.ref_device,
-        probe_batch=0 if (on_gpu or args.no_batch_probe) else args.batch)
+        args.workload, args.patch, args.steps, args.warmup, batch=args.batch if on_gpu else args.ref_batch,
+        device=args.ref_device, probe_batch=0 if (on_gpu or args.no_batch_probe) else args.batch,
+        full_batch=args.batch, budget_s=args.ref_budget)
+    b = extra.pop("batch")
     line = {
         "impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -616,9 +639,11 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, kind, sample, _ = cpu_reference_steps(args.workload, P, steps=3, warmup=1)
+        # bounded sample for the default run: about 20 s of CPU work at whatever batch fits
+        v, dt, cores, kind, sample, ex = cpu_reference_steps(args.workload, P, steps=2, warmup=0, batch=0,
+                                                             full_batch=B, budget_s=20.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
-               "batch_per_timed_step": 1, "s_per_step": dt}
+               "batch_per_timed_step": ex["batch"], "s_per_step": dt}
 
     if rank == 0:
         line = {

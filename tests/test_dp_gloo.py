@@ -79,5 +79,5 @@ def test_reference_arm_prints_on_rank0_only():
     assert line["impl"] == "reference" and line["unit"] == "patches/s" and line["value"] > 0
     # the reference's own modules where they (or their compiled copy, oracle/_ref) exist, else the port
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
-    assert line["cpu_baseline"]["batch_per_timed_step"] == 1
+    assert line["cpu_baseline"]["batch_per_timed_step"] in (1, 2, 4, 8)      # the batch it timed, stated
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2
