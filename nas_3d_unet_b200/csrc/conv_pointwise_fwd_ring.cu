@@ -1,12 +1,17 @@
 // Ring-staged forward of the big stride-1 1x1x1 convolutions (stems, cell preprocess convs over a
 // dense tensor or a virtual concat, the 12->3 head):  small[v,cs] = act(bias + sum_cb f(big[v,cb]) W[cs][cb]).
 //
-// STATUS: written after the round-1 GPU budget was spent - NOT YET RUN ON A B200.  It is only taken
-// when NAS3D_PW_FWD_RING=1 (conv_pointwise.cu: pointwise_sfb) and its parity test is behind
-// NAS3D_TEST_UNVALIDATED=1.  Motivation: the register-staged pointwise_kernel
-// runs these shapes at 3.3-5.1 TB/s (ncu: long_scoreboard at 18-25 % occupancy, 96-162 registers),
-// while the same per-thread cp.async ring took bwd_reduce / affine_sum_fwd / the fused 1x1 backward
-// to 5.2-6.3 TB/s.
+// Validated and on by default since round 2 (library option pw_fwd_ring; parity test
+// test_ring_staged_pointwise_forward_matches_default_kernel).  Motivation: the register-staged
+// pointwise_kernel runs these shapes at 3.3-5.1 TB/s (ncu: long_scoreboard at 18-25 % occupancy,
+// 96-162 registers), while the same per-thread cp.async ring took bwd_reduce / affine_sum_fwd / the
+// fused 1x1 backward to 5.2-6.3 TB/s.
+//
+// Outputs wider than one float4 per voxel (CO = 8, 12) written straight from a thread-per-voxel
+// mapping make every 128-bit store instruction of a warp touch all the 32-byte sectors of its
+// 32 x CO x 4-byte region half-filled (the 4 -> 12 stem ran at 2.9 TB/s); for a dense destination the
+// warp therefore transposes its 32 x CO outputs through a private shared-memory patch and stores
+// CO/4 fully contiguous 512-byte rows instead.
 //
 // One thread per voxel, a CTA walks a contiguous range of PR_T-voxel tiles; the Q = Cin/4 float4
 // channel groups of a thread's next PR_S-1 voxels are in flight as cp.async copies into the
@@ -50,8 +55,11 @@ __device__ __forceinline__ void pr_cp16(void* dst, const void* src) {
 template <int CO, int Q, bool MOM>
 __global__ void __launch_bounds__(PR_T)
     pw_fwd_ring_kernel(const __grid_constant__ PwRingArgs A, int tiles_per_cta) {
-  extern __shared__ __align__(16) float4 pr_ring[];          // [Q][PR_S][PR_T] then weights
+  extern __shared__ __align__(16) float4 pr_ring[];          // [Q][PR_S][PR_T], weights, output patches
   float* Wsm = reinterpret_cast<float*>(pr_ring + Q * PR_S * PR_T);   // [Cin = 4Q][CO]
+  // per-warp output patch [32 voxels][CO] (CO > 4, dense destination): see the header
+  float4* const opatch = reinterpret_cast<float4*>(Wsm + 4 * Q * CO) + (threadIdx.x >> 5) * (32 * CO / 4);
+  const bool via_patch = CO > 4 && A.ld_dst == CO;
   __shared__ double sm_mom[2 * CO];
   constexpr int CIN = 4 * Q;
   if (threadIdx.x < 2 * CO) sm_mom[threadIdx.x] = 0.0;
@@ -187,8 +195,21 @@ __global__ void __launch_bounds__(PR_T)
           if (A.sigmoid) o[e] = 1.f / (1.f + __expf(-o[e]));
           if (MOM) { ms[cj] += o[e]; mq[cj] += o[e] * o[e]; }
         }
-        if (4 * j4 < A.ld_dst) st4(pdst + 4 * j4, make_float4(o[0], o[1], o[2], o[3]));
+        if (via_patch) opatch[(threadIdx.x & 31) * (CO / 4) + j4] = make_float4(o[0], o[1], o[2], o[3]);
+        else if (4 * j4 < A.ld_dst) st4(pdst + 4 * j4, make_float4(o[0], o[1], o[2], o[3]));
       }
+    }
+    if (via_patch) {       // warp-uniform; tiles are whole warps of voxels except at the very end
+      __syncwarp();
+      const unsigned lane = threadIdx.x & 31;
+      const unsigned wv0 = v - lane;                               // first voxel of this warp's patch
+      float* wdst = pdst - (long long)lane * CO;
+#pragma unroll
+      for (int j = 0; j < CO / 4; ++j) {
+        const unsigned idx = lane + 32 * j;                        // float4 index inside the patch
+        if (wv0 + idx / (CO / 4) < vend) st4(wdst + 4 * idx, opatch[idx]);
+      }
+      __syncwarp();
     }
     if (MOM && ++since_flush == PR_FLUSH) partials_to_cta();
     v += PR_T;
@@ -206,7 +227,8 @@ __global__ void __launch_bounds__(PR_T)
 template <int CO, int Q, bool MOM>
 static int pr_launch(const PwRingArgs& A, cudaStream_t st) {
   auto kern = pw_fwd_ring_kernel<CO, Q, MOM>;
-  const int smem = Q * PR_S * PR_T * (int)sizeof(float4) + 4 * Q * CO * (int)sizeof(float);
+  const int smem = Q * PR_S * PR_T * (int)sizeof(float4) + 4 * Q * CO * (int)sizeof(float) +
+                   (CO > 4 ? PR_T * CO * (int)sizeof(float) : 0);
   static int resident = -1;
   if (resident < 0) {
     NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
