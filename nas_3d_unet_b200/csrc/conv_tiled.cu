@@ -443,29 +443,30 @@ static EncodeTiledFn encode_tiled_fn() {
   return g_opt.tma ? fn : nullptr;
 }
 
-// 5-D map of an NDHWC fp32 tensor {C, W, H, D, N} with voxel pitch ld, box {4, bw, bh, bd, 1}
-static bool make_ndhwc_map(CUtensorMap* m, const float* base, int C, int W, int H, int D, int N,
-                           int ld, int bw, int bh, int bd) {
+// 5-D map of an NDHWC fp32 tensor {C, W, H, D, N} with voxel pitch ld, box {bc, bw, bh, bd, 1}
+bool make_ndhwc_map(CUtensorMap* m, const float* base, int C, int W, int H, int D, int N,
+                    int ld, int bw, int bh, int bd, int bc) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   const cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4,
                                  (cuuint64_t)D * H * W * ld * 4};
-  const cuuint32_t box[5] = {4, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
   const cuuint32_t es[5] = {1, 1, 1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// 4-D map {W*4, H, D, N} of a DENSE 4-channel NDHWC tensor (ld == 4), box {4*bw, bh, bd, 1}
-static bool make_ndhwc4_merged_map(CUtensorMap* m, const float* base, int W, int H, int D, int N,
-                                   int bw, int bh, int bd) {
+// 4-D map {W*c, H, D, N} of a DENSE c-channel NDHWC tensor (ld == c), box {c*bw, bh, bd, 1}
+bool make_ndhwc_merged_map(CUtensorMap* m, const float* base, int c, int W, int H, int D, int N,
+                           int bw, int bh, int bd) {
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || !g_opt.tma_merged || 4 * bw > 256) return false;
-  const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  const cuuint32_t box[4] = {(cuuint32_t)(4 * bw), (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  if (!enc || !g_opt.tma_merged || c * bw > 256) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W * c, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * c * 4, (cuuint64_t)H * W * c * 4,
+                                 (cuuint64_t)D * H * W * c * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)(c * bw), (cuuint32_t)bh, (cuuint32_t)bd, 1};
   const cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -493,7 +494,7 @@ static int launch_conv3(const TiledArgs& A0, cudaStream_t st) {
   A.tma_merged = 0;
   bool tma = false;
   if (C == 4 && A.xs == 1 && A.ldx == 4 &&
-      make_ndhwc4_merged_map(&tmap, A.x, A.W, A.H, A.D, A.N, TS::PW, TS::PH, TS::PD)) {
+      make_ndhwc_merged_map(&tmap, A.x, 4, A.W, A.H, A.D, A.N, TS::PW, TS::PH, TS::PD)) {
     tma = true;
     A.tma_merged = 1;
   } else {

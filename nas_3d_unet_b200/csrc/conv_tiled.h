@@ -1,5 +1,6 @@
 // argument blocks of the tiled 3x3x3 kernels (conv_tiled.cu), shared with conv_direct.cu
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/nas3d_b200.h"
 
@@ -91,6 +92,13 @@ int tiled_dw_wgrad(const S2Args& A, int stride, cudaStream_t st);
 int umma_wgrad(const nas3d_conv_desc* d, const float* small, const float* big, float* dW,
                float* workspace, long long ws_floats, cudaStream_t st);
 long long umma_wgrad_workspace_floats(const nas3d_conv_desc* d);
+
+// TMA tensor maps of NDHWC fp32 tensors (conv_tiled.cu); false = not available (option tma = 0,
+// no driver entry point, or the box does not fit)
+bool make_ndhwc_map(CUtensorMap* m, const float* base, int C, int W, int H, int D, int N, int ld,
+                    int bw, int bh, int bd, int bc = 4);
+bool make_ndhwc_merged_map(CUtensorMap* m, const float* base, int c, int W, int H, int D, int N,
+                           int bw, int bh, int bd);
 
 // return NAS3D_ERR_UNSUPPORTED (without error text) when the shape is not covered
 int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t st);

@@ -16,6 +16,8 @@
 //    voxels; per parity class only the taps that land on the lattice are visited (27/8 per voxel);
 //  * wgrad: a lane walks along small w with a 3-wide window over the big row (2 new loads/step).
 // HBM/L2-bound by construction (8 big voxels per small voxel): AI = 6.75 FLOP/B at C = 4.
+#include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 #include "conv_tiled.h"
 
@@ -418,6 +420,231 @@ __global__ void __launch_bounds__(WgS2Shape<TWT>::THREADS)
 }
 
 // =========================================================================================
+// wgrad, TMA-staged and double-buffered (the default; the cp.async kernel above is the fallback
+// when no tensor map can be made)
+// =========================================================================================
+// ncu of the cp.async kernel (profiles/r3x_ncu_full_s2_family.csv): FFMA2 is 23 % of the issued
+// instructions, the per-element LDGSTS staging (47 instructions and 10.6 shared-memory wavefronts
+// per copy) costs as many shared-memory cycles as all operand reads of the FMA loop, nothing
+// overlaps (stage -> wait -> barrier -> FMAs), and the x reads take 6 wavefronts instead of 4.
+// Here one thread issues two cp.async.bulk.tensor copies per tile (haloed big tile, dy tile) into
+// the buffer the CTA is NOT computing on; out-of-volume voxels are zero-filled by the TMA unit
+// (= the conv padding, and dy = 0 outside contributes nothing), so the instruction stream is
+// the FMA loop alone.  CSV = 2 keeps 8 output channels per lane (96 accumulators): twice the
+// FMAs per x operand read, and the x tile is re-staged half as often.
+//
+// lane -> (kd, kh, row j): with the dense TMA tile (row pitch 2TW+1 = 1, plane pitch
+// 13(2TW+1) = 5 mod 8 sixteen-byte bank groups) this permutation gives every quarter-warp 8
+// distinct bank groups (or the same address); bias / idle lanes duplicate a neighbour's address.
+// byte = kd | kh << 2 | j << 4 | role << 6   (role 0: tap lane, 1: bias lane, 2: idle)
+#define S2T(kd, kh, j) ((kd) | (kh) << 2 | (j) << 4)
+__constant__ unsigned char kS2LaneTap[32] = {
+    S2T(2, 1, 2), S2T(2, 1, 1), S2T(2, 0, 1), S2T(0, 0, 0), S2T(1, 1, 0), S2T(0, 1, 0), S2T(2, 2, 0), S2T(0, 1, 1),
+    S2T(2, 2, 1), S2T(0, 0, 1), S2T(1, 1, 1), S2T(0, 2, 1), S2T(0, 2, 0), S2T(2, 0, 2), S2T(0, 0, 2), S2T(2, 0, 2) | 64,
+    S2T(1, 0, 2), S2T(0, 1, 2), S2T(1, 2, 2), S2T(1, 2, 1), S2T(1, 1, 2), S2T(0, 2, 2), S2T(1, 2, 1) | 64, 128,
+    S2T(1, 0, 1), S2T(2, 2, 2), S2T(1, 0, 0), S2T(2, 1, 0), S2T(1, 2, 0), S2T(2, 0, 0), S2T(1, 0, 0) | 64, 128};
+#undef S2T
+
+template <int TWT, int CSV>
+struct WgS2TmaShape {
+  // Tile ring: as many stages as let two CTAs share an SM.  Measured (profiles/r4_s2_wgrad.txt):
+  // the 4-channel kernel is bound by shared-memory bandwidth (11 LDS wavefronts per 24 FFMA2 +
+  // the TMA fill: ncu r4c 56 % + ~25 % of the pipe), so neither a third resident CTA (2 stages)
+  // nor 12 output channels per lane (207 registers) beat this shape.
+  static constexpr int NST = CSV == 1 ? 3 : 2;
+  static constexpr int TW = TWT, TH = 6, TD = 2, NWARP = 4;    // consumer warps; + 1 producer warp
+  static constexpr int THREADS = 32 * (NWARP + 1);
+  static constexpr int PD = 2 * TD + 1, PH = 2 * TH + 1, PW = 2 * TW + 1;
+  static constexpr int XPLANE = PH * PW;
+  static constexpr int XBYTES = PD * XPLANE * 16;
+  static constexpr int YW = TW;
+  static constexpr int YROW = YW * CSV;           // float4 per dy row
+  static constexpr int YBYTES = TD * TH * YROW * 16;
+  static constexpr int XPAD = (XBYTES + 127) / 128 * 128, YPAD = (YBYTES + 127) / 128 * 128;
+  static constexpr int STAGE = XPAD + YPAD;
+  static constexpr int RED_TAP = 48 * CSV + 1;    // odd pitch per (kd, kh): the flush is conflict-free
+  static constexpr int NRED = 9 * RED_TAP + 4 * CSV;   // aliases stage 0 after the last tile
+  static constexpr size_t SMEM = NST * STAGE;
+  static_assert(TD * TH == 3 * NWARP, "one 3-row group per warp");
+  static_assert((PW % 8) == 1 && (XPLANE % 8) == 5, "kS2LaneTap assumes these bank-group pitches");
+  static_assert(NRED * 4 <= STAGE, "reduction scratch fits a stage");
+};
+
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "S2_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra S2_DONE;\n\t"
+      "bra S2_WAIT;\n\t"
+      "S2_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+// Warp roles: warps 0..3 run the FMA loop, one lane of warp 4 issues the tensor copies.  full[s]
+// (1 arrival + the copies' bytes) hands a stage to the consumers, empty[s] (one arrival per
+// consumer warp) hands it back; no CTA-wide barrier inside the tile loop.
+template <int TWT, int CSV, bool BIAS>
+__global__ void __launch_bounds__(WgS2TmaShape<TWT, CSV>::THREADS)
+    wgrad3_s2_tma_kernel(const S2Args A, int ntiles, const __grid_constant__ CUtensorMap xmap,
+                         const __grid_constant__ CUtensorMap ymap, int x_merged, int y_merged) {
+  using WS = WgS2TmaShape<TWT, CSV>;
+  constexpr int TW = WS::TW, TH = WS::TH, PW = WS::PW, NST = WS::NST;
+  extern __shared__ __align__(128) unsigned char base[];
+  __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST];
+  float* red = reinterpret_cast<float*>(base);
+
+  const int C4S = A.Cs / (4 * CSV);
+  const int cic = blockIdx.y / C4S, coc = blockIdx.y % C4S;   // cic: 4 big channels, coc: 4*CSV small
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned code = kS2LaneTap[lane];
+  const int kd = code & 3, kh = (code >> 2) & 3, j = (code >> 4) & 3, role = code >> 6;
+  const bool tap_lane = role == 0, active = role < 2;
+
+  float2 acc[CSV][3][4][2];   // [cs chunk][kw][cb][cs pair]: FFMA2 accumulators
+  float4 bsum[CSV];
+#pragma unroll
+  for (int v = 0; v < CSV; ++v) {
+    bsum[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) acc[v][t][a][c] = make_float2(0.f, 0.f);
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NST; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&empty_bar[b])),
+                   "r"(WS::NWARP));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == WS::NWARP) {
+    // ---- producer ---------------------------------------------------------------------------
+    if (lane == 0) {
+      int buf = 0, parity = 0;
+#pragma unroll 1
+      for (long long tile = blockIdx.x, k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+        if (k >= NST)    // the consumers have handed the stage back (its previous use: round k/NST - 1)
+          mbar_wait_parity((unsigned)__cvta_generic_to_shared(&empty_bar[buf]), (unsigned)(parity ^ 1));
+        unsigned b = (unsigned)tile;
+        const int tw = (int)(b % (unsigned)A.tiles_w); b /= (unsigned)A.tiles_w;
+        const int th = (int)(b % (unsigned)A.tiles_h); b /= (unsigned)A.tiles_h;
+        const int td = (int)(b % (unsigned)A.tiles_d);
+        const int n = (int)(b / (unsigned)A.tiles_d);
+        const int w0 = tw * TW, h0 = th * TH, d0 = td * WS::TD;     // small coordinates
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar[buf]);
+        const unsigned dx = (unsigned)__cvta_generic_to_shared(base + buf * WS::STAGE);
+        const unsigned dy = dx + WS::XPAD;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                     "r"((unsigned)(WS::XBYTES + WS::YBYTES))
+                     : "memory");
+        if (x_merged)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dx),
+              "l"(&xmap), "r"((2 * w0 - 1) * 4), "r"(2 * h0 - 1), "r"(2 * d0 - 1), "r"(n), "r"(bar)
+              : "memory");
+        else
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dx),
+              "l"(&xmap), "r"(cic * 4), "r"(2 * w0 - 1), "r"(2 * h0 - 1), "r"(2 * d0 - 1), "r"(n), "r"(bar)
+              : "memory");
+        if (y_merged)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dy),
+              "l"(&ymap), "r"(w0 * 4 * CSV), "r"(h0), "r"(d0), "r"(n), "r"(bar)
+              : "memory");
+        else
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dy),
+              "l"(&ymap), "r"(coc * 4 * CSV), "r"(w0), "r"(h0), "r"(d0), "r"(n), "r"(bar)
+              : "memory");
+        if (++buf == NST) { buf = 0; parity ^= 1; }
+      }
+    }
+  } else {
+    // ---- consumers --------------------------------------------------------------------------
+    const int row = warp * 3 + j;
+    const int pd = row / TH, ph = row % TH;
+    const int xoff = (2 * pd + kd) * WS::XPLANE + (2 * ph + kh) * PW, yoff = row * WS::YROW;
+    int buf = 0, parity = 0;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait_parity((unsigned)__cvta_generic_to_shared(&full_bar[buf]), (unsigned)parity);
+      if (active) {
+        const float4* xr = reinterpret_cast<const float4*>(base + buf * WS::STAGE) + xoff;
+        const float4* yr = reinterpret_cast<const float4*>(base + buf * WS::STAGE + WS::XPAD) + yoff;
+        float4 xa = xr[0];
+#pragma unroll
+        for (int w = 0; w < TW; ++w) {
+          const float4 xb2 = xr[2 * w + 1];
+          const float4 xc = xr[2 * w + 2];
+          const float4 xv3[3] = {xa, xb2, xc};
+#pragma unroll
+          for (int v = 0; v < CSV; ++v) {
+            const float4 g = yr[w * CSV + v];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) outer4(acc[v][kw], xv3[kw], g);
+            if (BIAS) { bsum[v].x += g.x; bsum[v].y += g.y; bsum[v].z += g.z; bsum[v].w += g.w; }
+          }
+          xa = xc;
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(&empty_bar[buf]))
+                     : "memory");
+      if (++buf == NST) { buf = 0; parity ^= 1; }
+    }
+  }
+
+  // ---- flush once per CTA (the ring is idle: every issued tile has been consumed) ----------------
+  __syncthreads();
+  for (int i = threadIdx.x; i < WS::NRED; i += WS::THREADS) red[i] = 0.f;
+  __syncthreads();
+  const int kdkh = kd * 3 + kh;
+  if (warp < WS::NWARP) {
+    if (tap_lane) {
+#pragma unroll
+      for (int v = 0; v < CSV; ++v)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              atomicAdd(&red[kdkh * WS::RED_TAP + (kw * 4 + a) * (4 * CSV) + v * 4 + c],
+                        (c & 1) ? acc[v][kw][a][c >> 1].y : acc[v][kw][a][c >> 1].x);
+    } else if (BIAS && role == 1) {
+#pragma unroll
+      for (int v = 0; v < CSV; ++v) {
+        atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 0], bsum[v].x); atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 1], bsum[v].y);
+        atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 2], bsum[v].z); atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 3], bsum[v].w);
+      }
+    }
+  }
+  __syncthreads();
+  // red[kd,kh][kw][cb][cs] -> dW[cs][cb][tap]
+  for (int i = threadIdx.x; i < 27 * 16 * CSV; i += WS::THREADS) {
+    const int cs = coc * 4 * CSV + i % (4 * CSV), cb = cic * 4 + (i / (4 * CSV)) % 4, t = i / (16 * CSV);
+    atomicAdd(A.dW + ((long long)cs * A.Cb + cb) * 27 + t, red[(t / 3) * WS::RED_TAP + i - (t / 3) * 48 * CSV]);
+  }
+  if (BIAS && A.dbias_small && cic == 0 && threadIdx.x < 4 * CSV)
+    atomicAdd(A.dbias_small + coc * 4 * CSV + threadIdx.x, red[9 * WS::RED_TAP + threadIdx.x]);
+}
+
+// =========================================================================================
 // host side
 // =========================================================================================
 template <int CIN, int COUT, int HG, int DG>
@@ -501,11 +728,59 @@ static int launch_s2_wgrad(const S2Args& A, cudaStream_t st) {
   return A.dbias_small ? launch_s2_wgrad_b<TWT, true>(A, st) : launch_s2_wgrad_b<TWT, false>(A, st);
 }
 
+template <int TWT, int CSV, bool BIAS>
+static int launch_s2_wgrad_tma_b(S2Args A, cudaStream_t st) {
+  using WS = WgS2TmaShape<TWT, CSV>;
+  CUtensorMap xmap, ymap;
+  memset(&xmap, 0, sizeof(xmap));
+  memset(&ymap, 0, sizeof(ymap));
+  int x_merged = 0, y_merged = 0;
+  if (A.Cb == 4 && A.ld_big == 4 &&
+      make_ndhwc_merged_map(&xmap, A.big, 4, A.Wb, A.Hb, A.Db, A.N, WS::PW, WS::PH, WS::PD))
+    x_merged = 1;
+  else if (!make_ndhwc_map(&xmap, A.big, A.Cb, A.Wb, A.Hb, A.Db, A.N, A.ld_big, WS::PW, WS::PH, WS::PD))
+    return NAS3D_ERR_UNSUPPORTED;
+  if (A.Cs == 4 * CSV && A.ld_small == A.Cs &&
+      make_ndhwc_merged_map(&ymap, A.small, A.Cs, A.Ws, A.Hs, A.Ds, A.N, WS::YW, WS::TH, WS::TD))
+    y_merged = 1;
+  else if (!make_ndhwc_map(&ymap, A.small, A.Cs, A.Ws, A.Hs, A.Ds, A.N, A.ld_small, WS::YW, WS::TH, WS::TD,
+                           4 * CSV))
+    return NAS3D_ERR_UNSUPPORTED;
+  A.tiles_w = (A.Ws + WS::TW - 1) / WS::TW;
+  A.tiles_h = (A.Hs + WS::TH - 1) / WS::TH;
+  A.tiles_d = (A.Ds + WS::TD - 1) / WS::TD;
+  auto kern = wgrad3_s2_tma_kernel<TWT, CSV, BIAS>;
+  static int occ = 0;
+  if (!occ) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
+    NAS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WS::THREADS, WS::SMEM));
+    if (occ < 1) occ = 1;
+  }
+  const long long ntiles = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
+  const int pairs = (A.Cb / 4) * (A.Cs / (4 * CSV));
+  long long gx = (long long)kNumSMs * occ / pairs;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  kern<<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, (int)ntiles, xmap, ymap, x_merged, y_merged);
+  return launched(CSV == 2 ? "wgrad3_s2_tma_cs8" : "wgrad3_s2_tma");
+}
+
+template <int TWT>
+static int launch_s2_wgrad_tma(const S2Args& A, cudaStream_t st) {
+  if (A.Cs % 8 == 0)
+    return A.dbias_small ? launch_s2_wgrad_tma_b<TWT, 2, true>(A, st) : launch_s2_wgrad_tma_b<TWT, 2, false>(A, st);
+  return A.dbias_small ? launch_s2_wgrad_tma_b<TWT, 1, true>(A, st) : launch_s2_wgrad_tma_b<TWT, 1, false>(A, st);
+}
+
 int tiled_s2_wgrad(const S2Args& A, cudaStream_t st) {
   const bool ok = A.ld_big % 4 == 0 && A.ld_small % 4 == 0 && aligned16(A.big) && aligned16(A.small) &&
                   A.Db == 2 * A.Ds && A.Hb == 2 * A.Hs && A.Wb == 2 * A.Ws && A.Ws >= 2;
   if (!ok || A.Cb % 4 || A.Cs % 4 || A.Cb > 64 || A.Cs > 64) return NAS3D_ERR_UNSUPPORTED;
   if ((long long)A.Db * A.Hb * A.Wb * A.ld_big >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;
+  if (g_opt.s2_wgrad_tma) {
+    const int rc = A.Ws <= 8 ? launch_s2_wgrad_tma<8>(A, st) : launch_s2_wgrad_tma<16>(A, st);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   if (A.Ws <= 8) return launch_s2_wgrad<8>(A, st);
   if (A.Ws <= 16) return launch_s2_wgrad<16>(A, st);
   return launch_s2_wgrad<32>(A, st);

@@ -403,6 +403,9 @@ class ExecCtx:
 # ----------------------------------------------------------------------------------------
 # Terms and the fused affine-sum
 # ----------------------------------------------------------------------------------------
+MAX_TERMS = 32      # NAS3D_MAX_TERMS (include/nas3d_b200.h:224)
+
+
 class Term:
     __slots__ = ("x", "a", "b", "relu", "kind", "alpha", "aux")
 
@@ -451,7 +454,16 @@ def _take_gn_jobs(ctx, terms, out):
 
 
 def affine_sum(ctx, terms, out):
-    """out = sum_k w_k act_k(a_k x_k + b_k)   (cell.py:30,32,81 / prim_ops.py:75-80,152)"""
+    """out = sum_k w_k act_k(a_k x_k + b_k)   (cell.py:30,32,81 / prim_ops.py:75-80,152)
+
+    The kernels take at most MAX_TERMS terms per launch; a longer list (a supernet node with
+    n_nodes >= 8: 9 states x 4 candidates) is evaluated as a chain - the sum of the first
+    MAX_TERMS terms becomes an identity term of the next launch - so the tape differentiates it
+    like any other node."""
+    while len(terms) > MAX_TERMS:
+        part = new_act(out.N, out.C, out.D, out.H, out.W, ctx.device)
+        affine_sum(ctx, terms[:MAX_TERMS], part)
+        terms = [Term(part)] + list(terms[MAX_TERMS:])
     n = len(terms)
     lib = ctx.lib
     fold = _take_gn_jobs(ctx, terms, out)

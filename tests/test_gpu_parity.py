@@ -369,16 +369,18 @@ def test_tcgen05_stride2_dgrad_on_odd_extents_uses_tap_order():
     assert O.max_rel(xg.grad, xr.grad) <= 2e-5
 
 
+@pytest.mark.parametrize("narrow", [False, True])
 @pytest.mark.parametrize("cin,cout,transposed", [(4, 4, False), (8, 8, False), (4, 12, False),
                                                  (4, 4, True), (8, 8, True)])
-def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
+def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed, narrow):
     """stride-2 dilation-1 tiled kernels (down_conv / up_conv / stem1 family): fwd, dgrad, wgrad
-    on tile-ragged extents against the oracle and the generic gather kernels"""
+    on tile-ragged extents (narrow: the 8-wide wgrad tile) against the oracle, with the TMA and the
+    cp.async weight-gradient kernels and the generic gather kernels"""
     from nas_3d_unet_b200.prim_ops import ConvOps
     torch.manual_seed(cin * 3 + cout + transposed)
     op = ConvOps(cin, cout, stride=2, transposed=transposed, ops_order='weight')
     g = torch.Generator().manual_seed(cin + cout)
-    shape = (5, 6, 18) if transposed else (10, 12, 36)
+    shape = (5, 6, 6 if narrow else 18) if transposed else (10, 12, 12 if narrow else 36)
     x = torch.randn(2, cin, *shape, generator=g)
     sd = O.leaf_state(op.state_dict())
     xr = x.clone().requires_grad_(True)
@@ -386,12 +388,20 @@ def test_tiled_stride2_kernels_match_oracle(cin, cout, transposed):
     r = torch.randn(yr.shape, generator=g)
     (yr * r).sum().backward()
     op = op.cuda()
-    for mode in ("tiled", "generic"):
-        with variant(tiled=0 if mode == "generic" else 1):
+    from nas_3d_unet_b200 import _lib
+    for mode in ("tiled", "tiled_cp_async", "generic"):
+        before = _lib.launch_counts()
+        with variant(tiled=0 if mode == "generic" else 1, s2_wgrad_tma=1 if mode == "tiled" else 0):
             op.zero_grad()
             xg = x.cuda().requires_grad_(True)
             y = op(xg)
             (y * r.cuda()).sum().backward()
+        after = _lib.launch_counts()
+        ran = {k for k, v in after.items() if v > before.get(k, 0)}
+        if mode == "tiled":
+            assert ran & {"wgrad3_s2_tma", "wgrad3_s2_tma_cs8"}, ran
+        elif mode == "tiled_cp_async":
+            assert "wgrad3_s2" in ran, ran
         assert O.max_rel(y, yr) <= 1e-5, mode
         assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
         assert O.max_rel(op.conv.weight.grad, sd['conv.weight'].grad) <= 1e-4, mode
@@ -889,6 +899,45 @@ def test_supernet_small_config_with_shared_normal_alphas_matches_oracle():
     shared = sd['alpha1_down'].grad + sd['alpha1_up'].grad
     assert O.max_rel(s.alpha1_down.grad, shared) <= GRAD_TOL
     for k in ('alpha2_down', 'alpha2_up'):
+        assert O.max_rel(getattr(s, k).grad, sd[k].grad) <= GRAD_TOL, k
+    names = [k for k, _ in s.named_parameters() if k.startswith('kernel.')]
+    flat_o = torch.cat([dict(s.named_parameters())[k].grad.reshape(-1) for k in names]).cpu()
+    flat_r = torch.cat([sd[k].grad.reshape(-1) for k in names])
+    assert O.max_rel(flat_o, flat_r) <= GRAD_TOL
+
+
+def test_supernet_node_with_more_terms_than_one_launch_takes_is_chained(monkeypatch):
+    """n_nodes = 8: the last node of a cell mixes 9 states x 4 non-zero candidates = 36 terms,
+    above NAS3D_MAX_TERMS = 32 (include/nas3d_b200.h) - engine.affine_sum chains two launches"""
+    from nas_3d_unet_b200 import engine
+    from nas_3d_unet_b200.nas import ShellNet
+    from nas_3d_unet_b200.loss import WeightedDiceLoss
+    torch.manual_seed(9)
+    s = ShellNet(4, 4, 3, 2, 8)
+    s.kernel.last_conv[0].dropout.p = 0.0
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(10)
+        for p in s.alphas():
+            p.copy_(0.5 * torch.randn(p.shape, generator=g))
+    x, y = O.synthetic_batch(1, 16, seed=7)
+    sd = O.leaf_state(s.state_dict())
+    ref = O.shell_net(sd, x, 2, 8)
+    ref_loss = O.dice_loss(ref, y)
+    ref_loss.backward()
+    seen = []
+    inner = engine.affine_sum
+
+    def counting(ctx, terms, out):
+        seen.append(len(terms))
+        return inner(ctx, terms, out)
+    monkeypatch.setattr(engine, "affine_sum", counting)
+    s = s.cuda()
+    pred = s(x.cuda())
+    loss = WeightedDiceLoss()(pred, y.cuda())
+    loss.backward()
+    assert max(seen) > engine.MAX_TERMS
+    assert O.max_rel(pred, ref) <= LOGIT_TOL and abs(loss.item() - ref_loss.item()) <= DICE_TOL
+    for k in ('alpha1_down', 'alpha1_up', 'alpha2_down', 'alpha2_up'):
         assert O.max_rel(getattr(s, k).grad, sd[k].grad) <= GRAD_TOL, k
     names = [k for k, _ in s.named_parameters() if k.startswith('kernel.')]
     flat_o = torch.cat([dict(s.named_parameters())[k].grad.reshape(-1) for k in names]).cpu()
