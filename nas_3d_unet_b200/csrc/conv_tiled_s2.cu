@@ -42,11 +42,14 @@ struct S2FwdShape {
   static constexpr int PD = 2 * TD + 1, PH = 2 * TH + 1, PWS = 2 * TW + 1, EVEN_N = TW + 1;
   static constexpr int PLANE = PD * PH * PWS;
   static constexpr int THREADS = 32 * HG * DG * C4O;
+  // register cap for two resident CTAs of the 384-thread 4->12 stem kernel: with one CTA per SM
+  // its staging and FMA phases never overlapped (tools/s2_micro.py: 289 -> 205 us); 0 = no cap
+  static constexpr int MINB = THREADS > 256 ? 2 : 0;
   static constexpr size_t SMEM = sizeof(float4) * PLANE * C4I + sizeof(float) * 27 * CIN * COUT;
 };
 
 template <int CIN, int COUT, int HG, int DG>
-__global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS)
+__global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS, S2FwdShape<CIN, COUT, HG, DG>::MINB)
     conv3_s2_sfb_kernel(const S2Args A) {
   using TS = S2FwdShape<CIN, COUT, HG, DG>;
   constexpr int C4I = TS::C4I, C4O = TS::C4O, PH = TS::PH, PWS = TS::PWS, EVEN_N = TS::EVEN_N;
@@ -162,11 +165,14 @@ struct S2BfsShape {
   static constexpr int SD = TDB / 2 + 1, SH = THB / 2 + 1, SW = TWB / 2 + 1;   // small tile
   static constexpr int PLANE = SD * SH * SW;
   static constexpr int THREADS = 32 * (THB / 4) * TDB * C4;
+  // C = 4: 512 threads at 80 registers left one CTA per SM; capped at 64 two are resident
+  // (tools/conv_micro.py stride 2, 8 x 128^3: dgrad 143.6 -> 110.7 us, profiles/r4j_minb_micro.txt)
+  static constexpr int MINB = C == 4 ? 2 : 0;
   static constexpr size_t SMEM = sizeof(float4) * PLANE * C4 + sizeof(float) * 27 * C * C;
 };
 
 template <int C>
-__global__ void __launch_bounds__(S2BfsShape<C>::THREADS) conv3_s2_bfs_kernel(const S2Args A) {
+__global__ void __launch_bounds__(S2BfsShape<C>::THREADS, S2BfsShape<C>::MINB) conv3_s2_bfs_kernel(const S2Args A) {
   using TS = S2BfsShape<C>;
   constexpr int C4 = TS::C4, SH = TS::SH, SW = TS::SW;
   extern __shared__ __align__(16) unsigned char smem_raw[];

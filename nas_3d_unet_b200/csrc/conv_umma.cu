@@ -322,6 +322,17 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   const int it0 = (int)((long long)blockIdx.y * nit / A.splits);
   const int it1 = (int)((long long)(blockIdx.y + 1) * nit / A.splits);
   gather(it0);
+  // B: packed weights of a stage (contiguous), asynchronous copy - issued ONE STAGE AHEAD so that its
+  // L2 latency overlaps the A stores / gather of the stage before (it used to be issued and
+  // awaited inside the same iteration: ~1 us of every 1.3 us iteration, 27 iterations per tile)
+  auto load_b = [&](int it, int s) {
+    unsigned char* b_sm = smem + s * US::STAGE_BYTES + 2 * US::A_BYTES;
+    const float* g = A.wp + (long long)(wbase + it) * (US::B_BYTES / 4);
+#pragma unroll
+    for (int i = tid; i < US::B_BYTES / 16; i += 128) cp_async16_u(b_sm + i * 16, g + i * 4);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  if (it0 < it1) load_b(it0, 0);
 
 #pragma unroll 1
   for (int it = it0; it < it1; ++it) {
@@ -331,15 +342,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
     unsigned char* a_hi = stage;
     unsigned char* a_lo = stage + US::A_BYTES;
     unsigned char* b_sm = stage + 2 * US::A_BYTES;
-    if (j >= 2) mbar_wait(&bars[s], (uint32_t)(((j >> 1) - 1) & 1));   // MMAs of stage j-2 drained
-
-    // ---- B: packed weights of this stage (contiguous), asynchronous copy ----
-    {
-      const float* g = A.wp + (long long)(wbase + it) * (US::B_BYTES / 4);
-#pragma unroll
-      for (int i = tid; i < US::B_BYTES / 16; i += 128) cp_async16_u(b_sm + i * 16, g + i * 4);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-    }
+    // (the MMAs of stage j-2 were awaited in iteration j-1, before B(j) was sent into this stage)
     // ---- A: split the gathered row into hi / lo and store in core-matrix layout ----
 #pragma unroll
     for (int tp = 0; tp < US::TPS; ++tp) {
@@ -358,8 +361,14 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
       }
     }
     // next stage's gather goes in flight now; it lands while this stage's MMAs are issued
-    if (it + 1 < it1) gather(it + 1);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (it + 1 < it1) {
+      gather(it + 1);
+      if (j >= 1) mbar_wait(&bars[s ^ 1], (uint32_t)(((j - 1) >> 1) & 1));   // MMAs of stage j-1 drained
+      load_b(it + 1, s ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");     // B(j) has landed, B(j+1) in flight
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -435,6 +444,276 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const UmmaArgs A) {
   }
 }
 
+// =========================================================================================
+// Warp-specialised variant (the default, option umma_ws): same operands, same MMA sequence, but
+// the three jobs no longer take turns.
+//   * warps 0..7 (256 threads) PRODUCE: two threads per voxel row, each gathers half of a
+//     stage's K slice into registers ONE STAGE AHEAD (the loads of stage j+1 are issued before
+//     the hi/lo split and shared-memory stores of stage j), writes its chunks of A_hi / A_lo
+//     and arrives on full[s]; thread 0 also sends the stage's packed weights with one
+//     cp.async.bulk onto the same barrier (expect_tx).
+//   * lane 0 of warp 8 ISSUES: waits full[s], issues the stage's tcgen05.mma chain and commits it
+//     to empty[s] (which the producers wait on before they reuse the stage).
+//   * all 8 producer warps run the EPILOGUE: warp w reads TMEM lanes 32*(w%4) and the column half
+//     w/4.
+// In the lock-step kernel above every tap cost one exposed L2 round trip plus a CTA barrier
+// (1.3 - 2.4 us per stage with the tensor pipe idle most of it).
+// =========================================================================================
+template <int CRED, int NPROD>
+struct UmmaWsShape : UmmaShape<CRED, NPROD> {
+  using US = UmmaShape<CRED, NPROD>;
+  static constexpr int NSTG = 2;
+  static constexpr int PROD = 256, THREADS = PROD + 32;
+  static constexpr int HCH = US::KCH / 2;                // 16-byte chunks per producer thread and stage
+  static constexpr size_t SMEM = NSTG * US::STAGE_BYTES + 128;
+};
+
+template <int CRED, int NPROD>
+__global__ void __launch_bounds__(UmmaWsShape<CRED, NPROD>::THREADS) umma_conv_ws_kernel(const UmmaArgs A) {
+  using US = UmmaShape<CRED, NPROD>;
+  using WS = UmmaWsShape<CRED, NPROD>;
+  constexpr int KS = US::KS, KCH = US::KCH, NIT = US::NIT, NSTG = WS::NSTG, HCH = WS::HCH;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTG * US::STAGE_BYTES);    // [NSTG]
+  uint64_t* empty = full + NSTG;                                                   // [NSTG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + NSTG);
+  __shared__ double sm_mom[2 * NPROD];
+  if (threadIdx.x < 2 * NPROD) sm_mom[threadIdx.x] = 0.0;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int b = 0; b < NSTG; ++b) {
+      mbar_init(&full[b], WS::PROD + 1);     // every producer + thread 0's expect_tx arrival
+      mbar_init(&empty[b], 1);               // one tcgen05.commit
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)US::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int cl = A.cls ? (int)blockIdx.z : 0;
+  const int nit = A.cls ? cls_stages<US::TPS>(cl) : NIT;
+  const int wbase = A.cls ? cls_stage_base<US::TPS>(cl) : 0;     // first packed stage of my class
+  const int it0 = (int)((long long)blockIdx.y * nit / A.splits);
+  const int it1 = (int)((long long)(blockIdx.y + 1) * nit / A.splits);
+  constexpr uint32_t IDESC1 = make_idesc_tf32(2 * NPROD);
+  constexpr uint32_t IDESC2 = make_idesc_tf32(NPROD);
+
+  if (warp == WS::PROD / 32) {
+    // ---- MMA issuer ---------------------------------------------------------------------------
+    if ((tid & 31) == 0) {
+#pragma unroll 1
+      for (int it = it0; it < it1; ++it) {
+        const int j = it - it0, s = j % NSTG;
+        mbar_wait(&full[s], (uint32_t)((j / NSTG) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        unsigned char* stage = smem + s * US::STAGE_BYTES;
+        const uint32_t a_hi_s = smem_u32(stage), a_lo_s = smem_u32(stage + US::A_BYTES),
+                       b_s = smem_u32(stage + 2 * US::A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < KS / 8; ++kk) {
+          const uint64_t da_hi = make_smem_desc(a_hi_s + kk * 256, 128, KCH * 128);
+          const uint64_t da_lo = make_smem_desc(a_lo_s + kk * 256, 128, KCH * 128);
+          const uint64_t db = make_smem_desc(b_s + kk * 256, 128, KCH * 128);
+          umma_tf32(tmem_base, da_hi, db, IDESC1, (j | kk) ? 1u : 0u);    // hi*[hi|lo] -> cols [0,2N)
+          umma_tf32(tmem_base, da_lo, db, IDESC2, 1u);                    // lo*hi      -> cols [0,N)
+        }
+        umma_commit(&empty[s]);
+      }
+    }
+  } else {
+    // ---- producers ----------------------------------------------------------------------------
+    const int row = tid & 127, half = tid >> 7;
+    long long o = (long long)blockIdx.x * 128 + row;
+    const bool row_valid = o < A.nvox;
+    int n = 0, od = 0, oh = 0, ow = 0;
+    if (row_valid) {
+      long long t = o;
+      if (A.cls) {
+        const int Wq = A.Wd >> 1, Hq = A.Hd >> 1, Dq = A.Dd >> 1;
+        ow = 2 * (int)(t % Wq) + (cl & 1); t /= Wq;
+        oh = 2 * (int)(t % Hq) + ((cl >> 1) & 1); t /= Hq;
+        od = 2 * (int)(t % Dq) + ((cl >> 2) & 1);
+        n = (int)(t / Dq);
+        o = (((long long)n * A.Dd + od) * A.Hd + oh) * A.Wd + ow;
+      } else {
+        ow = (int)(t % A.Wd); t /= A.Wd;
+        oh = (int)(t % A.Hd); t /= A.Hd;
+        od = (int)(t % A.Dd);
+        n = (int)(t / A.Dd);
+      }
+    }
+    const float* src_n = A.src + (long long)n * A.Dr * A.Hr * A.Wr * A.ldr;
+    const uint32_t row_off = (uint32_t)((row >> 3) * (KCH * 128) + (row & 7) * 16);   // bytes
+
+    // my half of a stage's K slice: chunks [half*HCH, (half+1)*HCH) = floats k0 .. k0 + 4*HCH of the
+    // stage; one tap (TPS = 1: half the channels of it; TPS = 2: tap `half`, all channels)
+    auto gather = [&](int it, float4 (&xv)[HCH]) {
+      const int tp = US::TPS == 2 ? half : 0;
+      const int c0 = US::TPS == 2 ? 0 : half * (CRED / 2);     // first channel of my chunks
+      const int tap = it * US::TPS + tp;
+      int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+      int id, ih, iw;
+      bool ok = row_valid && tap < 27;
+      if (A.cls) {
+        int o0, o1, o2;
+        ok = row_valid && tap < cls_taps(cl);
+        cls_tap(cl, ok ? tap : 0, &kd, &kh, &kw, &o0, &o1, &o2);
+        id = (od >> 1) + o0; ih = (oh >> 1) + o1; iw = (ow >> 1) + o2;
+      } else if (A.bfs) {
+        const int nd = od + A.pad - kd * A.dil, nh = oh + A.pad - kh * A.dil,
+                  nw = ow + A.pad - kw * A.dil;
+        ok = ok && nd >= 0 && nh >= 0 && nw >= 0 && (nd % A.stride) == 0 &&
+             (nh % A.stride) == 0 && (nw % A.stride) == 0;
+        id = nd / A.stride; ih = nh / A.stride; iw = nw / A.stride;
+      } else {
+        id = od * A.stride - A.pad + kd * A.dil;
+        ih = oh * A.stride - A.pad + kh * A.dil;
+        iw = ow * A.stride - A.pad + kw * A.dil;
+      }
+      ok = ok && id >= 0 && id < A.Dr && ih >= 0 && ih < A.Hr && iw >= 0 && iw < A.Wr;
+      const float* px = ok ? src_n + (((long long)id * A.Hr + ih) * A.Wr + iw) * A.ldr + c0 : A.src;
+#pragma unroll
+      for (int c = 0; c < HCH; ++c) xv[c] = ldg4_pred(px + c * 4, ok);
+    };
+    // stage j: wait for its smem, (thread 0) send B, split + store my chunks, arrive
+    auto produce = [&](int it, const float4 (&xv)[HCH]) {
+      const int j = it - it0, s = j % NSTG;
+      unsigned char* stage = smem + s * US::STAGE_BYTES;
+      if (j >= NSTG) mbar_wait(&empty[s], (uint32_t)(((j / NSTG) - 1) & 1));   // MMAs of stage j-NSTG drained
+      if (tid == 0) {
+        const uint32_t bar = smem_u32(&full[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                     "r"((uint32_t)US::B_BYTES)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                smem_u32(stage + 2 * US::A_BYTES)),
+            "l"(A.wp + (long long)(wbase + it) * (US::B_BYTES / 4)), "r"((uint32_t)US::B_BYTES), "r"(bar)
+            : "memory");
+      }
+#pragma unroll
+      for (int c = 0; c < HCH; ++c) {
+        const float4 x = xv[c];
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+        const uint32_t off = row_off + (uint32_t)(half * HCH + c) * 128u;
+        *reinterpret_cast<float4*>(stage + off) = hi;
+        *reinterpret_cast<float4*>(stage + US::A_BYTES + off) = lo;
+      }
+      // generic-proxy smem writes -> visible to the tensor core (async proxy), then hand over
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full[s])) : "memory");
+    };
+
+    float4 xa[HCH], xb[HCH];
+    if (it0 < it1) gather(it0, xa);
+#pragma unroll 1
+    for (int it = it0; it < it1; it += 2) {
+      if (it + 1 < it1) gather(it + 1, xb);
+      produce(it, xa);
+      if (it + 1 < it1) {
+        if (it + 2 < it1) gather(it + 2, xa);
+        produce(it + 1, xb);
+      }
+    }
+
+    // ---- epilogue: the last stage's commit covers every MMA before it -------------------------
+    const int jl = it1 - it0 - 1;
+    mbar_wait(&empty[jl % NSTG], (uint32_t)((jl / NSTG) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // warp w: TMEM lanes 32*(w%4) (row = 32*(w%4) + lane), column half w/4
+    const int erow = (warp & 3) * 32 + (tid & 31), ehalf = warp >> 2;
+    long long eo = (long long)blockIdx.x * 128 + erow;
+    const bool erow_valid = eo < A.nvox;
+    int en = 0;
+    if (erow_valid) {
+      long long t = eo;
+      if (A.cls) {
+        const int Wq = A.Wd >> 1, Hq = A.Hd >> 1, Dq = A.Dd >> 1;
+        const int w_ = 2 * (int)(t % Wq) + (cl & 1); t /= Wq;
+        const int h_ = 2 * (int)(t % Hq) + ((cl >> 1) & 1); t /= Hq;
+        const int d_ = 2 * (int)(t % Dq) + ((cl >> 2) & 1);
+        en = (int)(t / Dq);
+        eo = (((long long)en * A.Dd + d_) * A.Hd + h_) * A.Wd + w_;
+      } else {
+        en = (int)(t / ((long long)A.Dd * A.Hd * A.Wd));
+      }
+    }
+    n = en;
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float* pd = A.dst + eo * A.ldd;
+    constexpr int C8H = NPROD / 16;          // 8-column groups per half
+#pragma unroll 1
+    for (int c8 = ehalf * C8H; c8 < (ehalf + 1) * C8H; ++c8) {
+      float hi[8], lo[8];
+      tmem_ld8(trow + c8 * 8, hi);
+      tmem_ld8(trow + NPROD + c8 * 8, lo);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (erow_valid) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = hi[i] + lo[i];
+          if (A.bias && blockIdx.y == 0) v[i] += __ldg(A.bias + c8 * 8 + i);
+        }
+        if (A.splits > 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(pd + c8 * 8 + i, v[i]);
+        } else {
+          float4 v0 = make_float4(v[0], v[1], v[2], v[3]), v1 = make_float4(v[4], v[5], v[6], v[7]);
+          if (A.accumulate) {
+            const float4 o0 = *reinterpret_cast<const float4*>(pd + c8 * 8);
+            const float4 o1 = *reinterpret_cast<const float4*>(pd + c8 * 8 + 4);
+            v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+            v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
+          }
+          st4(pd + c8 * 8, v0);
+          st4(pd + c8 * 8 + 4, v1);
+          if (A.moments) {
+            const float s0[4] = {v0.x, v0.y, v0.z, v0.w}, s1[4] = {v1.x, v1.y, v1.z, v1.w};
+            const float q0[4] = {v0.x * v0.x, v0.y * v0.y, v0.z * v0.z, v0.w * v0.w};
+            const float q1[4] = {v1.x * v1.x, v1.y * v1.y, v1.z * v1.z, v1.w * v1.w};
+            warp_moments_add(sm_mom, c8 * 8, s0, q0);
+            warp_moments_add(sm_mom, c8 * 8 + 4, s1, q1);
+          }
+        }
+      } else if (A.moments && A.splits == 1) {
+        // keep the warp-collective reductions convergent (host guarantees full tiles with moments)
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        warp_moments_add(sm_mom, c8 * 8, z, z);
+        warp_moments_add(sm_mom, c8 * 8 + 4, z, z);
+      }
+    }
+    if (A.moments) {
+      // producers only (named barrier 1): the issuer warp has nothing to add
+      asm volatile("bar.sync 1, %0;\n" ::"n"(WS::PROD) : "memory");
+      for (int i = tid; i < 2 * NPROD; i += WS::PROD)
+        atomicAdd(&A.moments[(long long)n * NPROD * 2 + i], sm_mom[i]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
+                 "r"((uint32_t)US::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 template <int CRED, int NPROD>
 static int launch_umma(const UmmaArgs& A, cudaStream_t st) {
   using US = UmmaShape<CRED, NPROD>;
@@ -445,6 +724,17 @@ static int launch_umma(const UmmaArgs& A, cudaStream_t st) {
     attr_done = true;
   }
   const unsigned blocks = (unsigned)((A.nvox + 127) / 128);
+  if (g_opt.umma_ws) {
+    using WS = UmmaWsShape<CRED, NPROD>;
+    auto kws = umma_conv_ws_kernel<CRED, NPROD>;
+    static bool ws_attr_done = false;
+    if (!ws_attr_done) {
+      NAS3D_CUDA(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
+      ws_attr_done = true;
+    }
+    kws<<<dim3(blocks, (unsigned)A.splits, A.cls ? 8u : 1u), WS::THREADS, WS::SMEM, st>>>(A);
+    return launched("umma_conv_ws");
+  }
   kern<<<dim3(blocks, (unsigned)A.splits, A.cls ? 8u : 1u), 128, US::SMEM, st>>>(A);
   return launched("umma_conv");
 }

@@ -281,10 +281,12 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
     (yr * r).sum().backward()
     op = op.cuda()
     from nas_3d_unet_b200 import profiling
-    for mode in ("umma", "ffma"):
+    from nas_3d_unet_b200 import _lib
+    for mode in ("umma", "umma_lockstep", "ffma"):
         prof = profiling.enable()
+        before = _lib.launch_counts()
         try:
-            with variant(umma_min_c=16, umma=(mode == "umma")):
+            with variant(umma_min_c=16, umma=(mode != "ffma"), umma_ws=1 if mode == "umma" else 0):
                 op.zero_grad()
                 xg = x.cuda().requires_grad_(True)
                 y = op(xg)
@@ -292,7 +294,10 @@ def test_tcgen05_conv_matches_oracle(c, stride, dil, transposed):
             names = [rec[0] for rec in prof.records]
         finally:
             profiling.disable()
-        assert ("nas3d_umma_conv" in names) == (mode == "umma"), names
+        after = _lib.launch_counts()
+        ran = {k for k, v in after.items() if v > before.get(k, 0)}
+        assert ("nas3d_umma_conv" in names) == (mode != "ffma"), names
+        assert ("umma_conv_ws" in ran) == (mode == "umma") and ("umma_conv" in ran) == (mode == "umma_lockstep"), ran
         assert tuple(y.shape) == tuple(yr.shape)
         assert O.max_rel(y, yr) <= 2e-5, (mode, O.max_rel(y, yr))
         assert O.max_rel(xg.grad, xr.grad) <= 2e-5, (mode, O.max_rel(xg.grad, xr.grad))

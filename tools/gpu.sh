@@ -10,6 +10,7 @@
 #   configs         one line per BASELINE.json config (#1, #2, #3, #5; #4 is `bench`)
 #   refarm          bench.py --impl reference (CPU arm) with 2 steps
 #   launches        ncu launch list of one eager step (gpu__time_duration.sum)
+#   occ             ncu occupancy / issue / pipe metrics of every launch of one eager step, by kernel
 #   full:REGEX      ncu --set full capture of kernels matching REGEX (3 launches)
 #   py:"ARGS"       python ARGS   (micro-benchmarks under tools/)
 TAG=$1; shift
@@ -55,6 +56,10 @@ for cmd in "$@"; do
     launches) timeout 900 $NCU --metrics gpu__time_duration.sum -s 1200 -c 1900 --csv --log-file gpurun_out/${TAG}_launches.csv \
                  python bench.py --graph off --steps 1 --warmup 3 --no-cpu-baseline --no-roofline > /dev/null 2>&1
              python tools/launch_summary.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_ncu_launch_summary.csv; head -12 gpurun_out/${TAG}_ncu_launch_summary.csv ;;
+    occ)     timeout 900 $NCU --metrics gpu__time_duration.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__occupancy_limit_registers,launch__occupancy_limit_shared_mem,launch__occupancy_limit_warps,launch__registers_per_thread,launch__block_size,launch__grid_size,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed \
+                 -s 1200 -c 1900 --csv --page raw --log-file gpurun_out/${TAG}_occ.csv \
+                 python bench.py --graph off --steps 1 --warmup 3 --no-cpu-baseline --no-roofline > /dev/null 2>&1
+             python tools/occ_summary.py gpurun_out/${TAG}_occ.csv > gpurun_out/${TAG}_occ_summary.txt; head -50 gpurun_out/${TAG}_occ_summary.txt ;;
     full:*)  timeout 600 $NCU --set full --import-source on -k regex:$arg -s 0 -c 3 -o gpurun_out/${TAG}_full_$arg -f \
                  python bench.py --graph off --steps 1 --warmup 1 --no-cpu-baseline --no-roofline > /dev/null 2>&1
              ls -la gpurun_out/${TAG}_full_$arg.ncu-rep | awk '{print $5, $9}' ;;

@@ -50,6 +50,13 @@ def run(cb, cs, S, N=8):
     for name, v in (("wgrad_tma", 1), ("wgrad_cp", 0)):
         with _lib.option("s2_wgrad_tma", v):
             out[name] = timed(wg)
+    def fwd():
+        _lib.check(lib.nas3d_conv_small_from_big(C.byref(d), big.data_ptr(), w.data_ptr(), bias.data_ptr(), None, 0, 0, small.data_ptr(), 0, None, st), "fwd")
+    def dgrad():
+        _lib.check(lib.nas3d_conv_big_from_small(C.byref(d), small.data_ptr(), w.data_ptr(), None, None, 0, None, big.data_ptr(), 0, None, st), "dgrad")
+    out["fwd"] = timed(fwd)
+    if cb == cs:
+        out["dgrad"] = timed(dgrad)
     print("C%d->%d @%d^3 N%d  %.2f GFLOP   " % (cb, cs, S, N, gflop) +
           "   ".join("%s %.1f us (%.1f TF/s)" % (k, t, gflop / t * 1e3) for k, t in out.items()), flush=True)
 
