@@ -119,15 +119,17 @@ def _check_first_adam_step(before, after, grad, what, lr=1e-3, eps=1e-8):
     assert err <= 1e-6, (what, err)
 
 
-BIG_TENSOR_KERNELS = ["conv3_s1_tma_merged", "wgrad3_s1", "wgrad3_s2", "affine_sum_fwd_ring",
-                      "affine_sum_bwd_reduce_ring", "affine_sum_bwd_apply_ring", "pointwise_fwd_ring",
-                      "pw_bwd_fused", "umma_conv", "conv3_s2_sfb", "conv3_s2_bfs"]
+BIG_TENSOR_KERNELS = ["conv3_s1_tma_merged", "wgrad3_s1", "wgrad3_s2_tma", "wgrad3_s2_tma_cs8",
+                      "affine_sum_fwd_ring", "affine_sum_bwd_reduce_ring", "affine_sum_bwd_apply_ring",
+                      "pointwise_fwd_ring", "pw_bwd_fused", "umma_conv_ws", "umma_wgrad", "conv3_s2_sfb",
+                      "conv3_s2_bfs"]
 
 
 def test_searched_128_batch2_train_step_matches_fp32_and_fp64_oracle():
     """BASELINE.json config #4 per-GPU shape at batch 2: searched-G0, 4x128^3, train mode with the
     shared Dropout3d draw.  Ring-staged streaming kernels, merged-dimension TMA tiles, persistent
-    wgrad, tcgen05 convs and the fused 1x1 backward must all have run."""
+    and TMA-staged wgrads, the warp-specialised tcgen05 convs, the tcgen05 wgrad and the fused 1x1
+    backward must all have run."""
     _train_step_parity(2, 128, seed=41, fp64_twin=True, expect_engaged=BIG_TENSOR_KERNELS)
 
 
@@ -135,7 +137,7 @@ def test_searched_64_batch8_train_step_matches_oracle():
     """BASELINE.json config #2: searched-G0, 4x64^3, batch 8"""
     _train_step_parity(8, 64, seed=42, fp64_twin=False,
                        expect_engaged=["conv3_s1_tma_merged", "wgrad3_s1", "affine_sum_fwd_ring",
-                                       "pw_bwd_fused", "umma_conv"])
+                                       "pw_bwd_fused", "umma_conv_ws", "wgrad3_s2_tma"])
 
 
 def test_supernet_64_search_step_matches_oracle():
