@@ -469,7 +469,8 @@ struct UmmaWsShape : UmmaShape<CRED, NPROD> {
 };
 
 template <int CRED, int NPROD>
-__global__ void __launch_bounds__(UmmaWsShape<CRED, NPROD>::THREADS) umma_conv_ws_kernel(const UmmaArgs A) {
+__global__ void __launch_bounds__(UmmaWsShape<CRED, NPROD>::THREADS, CRED == 64 ? 1 : 2)   // 2 CTAs: <= 112 registers
+    umma_conv_ws_kernel(const UmmaArgs A) {
   using US = UmmaShape<CRED, NPROD>;
   using WS = UmmaWsShape<CRED, NPROD>;
   constexpr int KS = US::KS, KCH = US::KCH, NIT = US::NIT, NSTG = WS::NSTG, HCH = WS::HCH;
@@ -556,32 +557,35 @@ __global__ void __launch_bounds__(UmmaWsShape<CRED, NPROD>::THREADS) umma_conv_w
     const uint32_t row_off = (uint32_t)((row >> 3) * (KCH * 128) + (row & 7) * 16);   // bytes
 
     // my half of a stage's K slice: chunks [half*HCH, (half+1)*HCH) = floats k0 .. k0 + 4*HCH of the
-    // stage; one tap (TPS = 1: half the channels of it; TPS = 2: tap `half`, all channels)
+    // stage; one tap (TPS = 1: half the channels of it; TPS = 2: tap `half`, all channels).
+    // Everything that does not depend on the tap is computed once per thread: the input coordinate of
+    // tap k along an axis is (base + sgn * k * dil) >> sh, valid when non-negative, on the stride
+    // lattice and inside the tensor; offsets are 32-bit (host-checked).  ncu r4o: ~200 instructions
+    // per thread and stage, most of them this arithmetic in 64 bits with runtime divisions.
+    const int sgn = A.bfs ? -1 : 1, sh = A.bfs ? A.stride - 1 : 0, step = sgn * A.dil;
+    const int bd = A.bfs ? od + A.pad : od * A.stride - A.pad;
+    const int bh = A.bfs ? oh + A.pad : oh * A.stride - A.pad;
+    const int bw = A.bfs ? ow + A.pad : ow * A.stride - A.pad;
+    const int qd = od >> 1, qh = oh >> 1, qw = ow >> 1;        // parity-class mode
+    const int c0 = US::TPS == 2 ? 0 : half * (CRED / 2);        // first channel of my chunks
     auto gather = [&](int it, float4 (&xv)[HCH]) {
-      const int tp = US::TPS == 2 ? half : 0;
-      const int c0 = US::TPS == 2 ? 0 : half * (CRED / 2);     // first channel of my chunks
-      const int tap = it * US::TPS + tp;
-      int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+      const int tap = it * US::TPS + (US::TPS == 2 ? half : 0);
       int id, ih, iw;
-      bool ok = row_valid && tap < 27;
+      bool ok;
       if (A.cls) {
-        int o0, o1, o2;
+        int kd, kh, kw, o0, o1, o2;
         ok = row_valid && tap < cls_taps(cl);
         cls_tap(cl, ok ? tap : 0, &kd, &kh, &kw, &o0, &o1, &o2);
-        id = (od >> 1) + o0; ih = (oh >> 1) + o1; iw = (ow >> 1) + o2;
-      } else if (A.bfs) {
-        const int nd = od + A.pad - kd * A.dil, nh = oh + A.pad - kh * A.dil,
-                  nw = ow + A.pad - kw * A.dil;
-        ok = ok && nd >= 0 && nh >= 0 && nw >= 0 && (nd % A.stride) == 0 &&
-             (nh % A.stride) == 0 && (nw % A.stride) == 0;
-        id = nd / A.stride; ih = nh / A.stride; iw = nw / A.stride;
+        id = qd + o0; ih = qh + o1; iw = qw + o2;
       } else {
-        id = od * A.stride - A.pad + kd * A.dil;
-        ih = oh * A.stride - A.pad + kh * A.dil;
-        iw = ow * A.stride - A.pad + kw * A.dil;
+        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        const int nd = bd + kd * step, nh = bh + kh * step, nw = bw + kw * step;
+        ok = row_valid && tap < 27 && (nd | nh | nw) >= 0 && ((nd | nh | nw) & sh) == 0;
+        id = nd >> sh; ih = nh >> sh; iw = nw >> sh;
       }
       ok = ok && id >= 0 && id < A.Dr && ih >= 0 && ih < A.Hr && iw >= 0 && iw < A.Wr;
-      const float* px = ok ? src_n + (((long long)id * A.Hr + ih) * A.Wr + iw) * A.ldr + c0 : A.src;
+      const unsigned off = (unsigned)(((id * A.Hr + ih) * A.Wr + iw) * A.ldr + c0);
+      const float* px = ok ? src_n + off : A.src;
 #pragma unroll
       for (int c = 0; c < HCH; ++c) xv[c] = ldg4_pred(px + c * 4, ok);
     };
@@ -619,15 +623,23 @@ __global__ void __launch_bounds__(UmmaWsShape<CRED, NPROD>::THREADS) umma_conv_w
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full[s])) : "memory");
     };
 
-    float4 xa[HCH], xb[HCH];
+    // three register sets in rotation: the loads of stages j+1 and j+2 are in flight while stage j is
+    // split and stored (ncu r4o: 32-47 % of the producers' time was the gather's long scoreboard with
+    // one stage of look-ahead)
+    float4 xa[HCH], xb[HCH], xc[HCH];
     if (it0 < it1) gather(it0, xa);
+    if (it0 + 1 < it1) gather(it0 + 1, xb);
 #pragma unroll 1
-    for (int it = it0; it < it1; it += 2) {
-      if (it + 1 < it1) gather(it + 1, xb);
+    for (int it = it0; it < it1; it += 3) {
+      if (it + 2 < it1) gather(it + 2, xc);
       produce(it, xa);
       if (it + 1 < it1) {
-        if (it + 2 < it1) gather(it + 2, xa);
+        if (it + 3 < it1) gather(it + 3, xa);
         produce(it + 1, xb);
+      }
+      if (it + 2 < it1) {
+        if (it + 4 < it1) gather(it + 4, xb);
+        produce(it + 2, xc);
       }
     }
 
@@ -724,7 +736,11 @@ static int launch_umma(const UmmaArgs& A, cudaStream_t st) {
     attr_done = true;
   }
   const unsigned blocks = (unsigned)((A.nvox + 127) / 128);
-  if (g_opt.umma_ws) {
+  // (its gather shifts instead of dividing and keeps in-sample offsets in 32 bits)
+  // Measured (profiles/r4r_umma_direct.txt): faster or equal everywhere except the 16-channel parity-class
+  // dgrad (42 vs 33 us at 8 x 32^3), which keeps the lock-step kernel.
+  if (g_opt.umma_ws && (A.stride == 1 || A.stride == 2) && !(A.cls && CRED == 16) &&
+      (long long)A.Dr * A.Hr * A.Wr * A.ldr < (1ll << 31)) {
     using WS = UmmaWsShape<CRED, NPROD>;
     auto kws = umma_conv_ws_kernel<CRED, NPROD>;
     static bool ws_attr_done = false;
