@@ -87,6 +87,7 @@ int tiled_dw_s1(bool flip, const TiledArgs& A, int C, cudaStream_t st);
 int tiled_dw_s2_sfb(const S2Args& A, cudaStream_t st);
 int tiled_dw_s2_bfs(const S2Args& A, cudaStream_t st);
 int tiled_dw_wgrad(const S2Args& A, int stride, cudaStream_t st);
+int tiled_dw_s2_wgrad_tma(const S2Args& A, cudaStream_t st);   // conv_tiled_s2.cu (TMA tile ring)
 
 // tcgen05 weight gradient of the wide dense 3x3x3 convs (conv_umma_wgrad.cu)
 int umma_wgrad(const nas3d_conv_desc* d, const float* small, const float* big, float* dW,

@@ -476,7 +476,11 @@ int tiled_dw_wgrad(const S2Args& A, int stride, cudaStream_t st) {
     return NAS3D_ERR_UNSUPPORTED;
   if ((long long)A.Db * A.Hb * A.Wb * A.ld_big >= (1ll << 31)) return NAS3D_ERR_UNSUPPORTED;
   if (stride == 1 && A.Db == A.Ds && A.Hb == A.Hs && A.Wb == A.Ws) return launch_dw_wgrad<1>(A, st);
-  if (stride == 2 && dw_s2_ok(A)) return launch_dw_wgrad<2>(A, st);
+  if (stride == 2 && dw_s2_ok(A)) {
+    const int rc = tiled_dw_s2_wgrad_tma(A, st);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+    return launch_dw_wgrad<2>(A, st);
+  }
   return NAS3D_ERR_UNSUPPORTED;
 }
 

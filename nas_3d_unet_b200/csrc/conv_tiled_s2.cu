@@ -492,7 +492,10 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) 
 // Warp roles: warps 0..3 run the FMA loop, one lane of warp 4 issues the tensor copies.  full[s]
 // (1 arrival + the copies' bytes) hands a stage to the consumers, empty[s] (one arrival per
 // consumer warp) hands it back; no CTA-wide barrier inside the tile loop.
-template <int TWT, int CSV, bool BIAS>
+// DW = true: the depthwise weight gradient dW[c][tap] += sum_o small[o, c] * big[2o - 1 + tap, c] on
+// the same tiles (conv_tiled_dw.cu's stride-2 wgrad was the cp.async kernel's twin): blockIdx.y is
+// the 4-channel chunk of both tensors, 3 float4 accumulators per lane.
+template <int TWT, int CSV, bool BIAS, bool DW = false>
 __global__ void __launch_bounds__(WgS2TmaShape<TWT, CSV>::THREADS)
     wgrad3_s2_tma_kernel(const S2Args A, int ntiles, const __grid_constant__ CUtensorMap xmap,
                          const __grid_constant__ CUtensorMap ymap, int x_merged, int y_merged) {
@@ -502,14 +505,19 @@ __global__ void __launch_bounds__(WgS2TmaShape<TWT, CSV>::THREADS)
   __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST];
   float* red = reinterpret_cast<float*>(base);
 
-  const int C4S = A.Cs / (4 * CSV);
-  const int cic = blockIdx.y / C4S, coc = blockIdx.y % C4S;   // cic: 4 big channels, coc: 4*CSV small
+  static_assert(!DW || CSV == 1, "depthwise: one channel chunk");
+  const int C4S = DW ? 1 : A.Cs / (4 * CSV);
+  const int cic = DW ? (int)blockIdx.y : (int)blockIdx.y / C4S;   // cic: 4 big channels
+  const int coc = DW ? (int)blockIdx.y : (int)blockIdx.y % C4S;   // coc: 4*CSV small channels
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned code = kS2LaneTap[lane];
   const int kd = code & 3, kh = (code >> 2) & 3, j = (code >> 4) & 3, role = code >> 6;
   const bool tap_lane = role == 0, active = role < 2;
 
   float2 acc[CSV][3][4][2];   // [cs chunk][kw][cb][cs pair]: FFMA2 accumulators
+  float4 dacc[3];             // depthwise: [kw], one value per channel
+#pragma unroll
+  for (int t = 0; t < 3; ++t) dacc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 bsum[CSV];
 #pragma unroll
   for (int v = 0; v < CSV; ++v) {
@@ -600,7 +608,14 @@ __global__ void __launch_bounds__(WgS2TmaShape<TWT, CSV>::THREADS)
           for (int v = 0; v < CSV; ++v) {
             const float4 g = yr[w * CSV + v];
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) outer4(acc[v][kw], xv3[kw], g);
+            for (int kw = 0; kw < 3; ++kw) {
+              if constexpr (DW) {
+                dacc[kw].x = fmaf(xv3[kw].x, g.x, dacc[kw].x); dacc[kw].y = fmaf(xv3[kw].y, g.y, dacc[kw].y);
+                dacc[kw].z = fmaf(xv3[kw].z, g.z, dacc[kw].z); dacc[kw].w = fmaf(xv3[kw].w, g.w, dacc[kw].w);
+              } else {
+                outer4(acc[v][kw], xv3[kw], g);
+              }
+            }
             if (BIAS) { bsum[v].x += g.x; bsum[v].y += g.y; bsum[v].z += g.z; bsum[v].w += g.w; }
           }
           xa = xc;
@@ -620,6 +635,26 @@ __global__ void __launch_bounds__(WgS2TmaShape<TWT, CSV>::THREADS)
   for (int i = threadIdx.x; i < WS::NRED; i += WS::THREADS) red[i] = 0.f;
   __syncthreads();
   const int kdkh = kd * 3 + kh;
+  if constexpr (DW) {
+    // red[tap][4] -> dW[c][tap]
+    if (warp < WS::NWARP && tap_lane) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float* r = red + (kdkh * 3 + kw) * 4;
+        atomicAdd(r + 0, dacc[kw].x); atomicAdd(r + 1, dacc[kw].y);
+        atomicAdd(r + 2, dacc[kw].z); atomicAdd(r + 3, dacc[kw].w);
+      }
+    } else if (BIAS && warp < WS::NWARP && role == 1) {
+      atomicAdd(&red[27 * 4 + 0], bsum[0].x); atomicAdd(&red[27 * 4 + 1], bsum[0].y);
+      atomicAdd(&red[27 * 4 + 2], bsum[0].z); atomicAdd(&red[27 * 4 + 3], bsum[0].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 27 * 4; i += WS::THREADS)
+      atomicAdd(A.dW + (long long)(cic * 4 + i % 4) * 27 + i / 4, red[i]);
+    if (BIAS && A.dbias_small && threadIdx.x < 4)
+      atomicAdd(A.dbias_small + cic * 4 + threadIdx.x, red[27 * 4 + threadIdx.x]);
+    return;
+  }
   if (warp < WS::NWARP) {
     if (tap_lane) {
 #pragma unroll
@@ -734,7 +769,7 @@ static int launch_s2_wgrad(const S2Args& A, cudaStream_t st) {
   return A.dbias_small ? launch_s2_wgrad_b<TWT, true>(A, st) : launch_s2_wgrad_b<TWT, false>(A, st);
 }
 
-template <int TWT, int CSV, bool BIAS>
+template <int TWT, int CSV, bool BIAS, bool DW = false>
 static int launch_s2_wgrad_tma_b(S2Args A, cudaStream_t st) {
   using WS = WgS2TmaShape<TWT, CSV>;
   CUtensorMap xmap, ymap;
@@ -755,7 +790,7 @@ static int launch_s2_wgrad_tma_b(S2Args A, cudaStream_t st) {
   A.tiles_w = (A.Ws + WS::TW - 1) / WS::TW;
   A.tiles_h = (A.Hs + WS::TH - 1) / WS::TH;
   A.tiles_d = (A.Ds + WS::TD - 1) / WS::TD;
-  auto kern = wgrad3_s2_tma_kernel<TWT, CSV, BIAS>;
+  auto kern = wgrad3_s2_tma_kernel<TWT, CSV, BIAS, DW>;
   static int occ = 0;
   if (!occ) {
     NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
@@ -763,12 +798,12 @@ static int launch_s2_wgrad_tma_b(S2Args A, cudaStream_t st) {
     if (occ < 1) occ = 1;
   }
   const long long ntiles = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
-  const int pairs = (A.Cb / 4) * (A.Cs / (4 * CSV));
+  const int pairs = DW ? A.Cb / 4 : (A.Cb / 4) * (A.Cs / (4 * CSV));
   long long gx = (long long)kNumSMs * occ / pairs;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   kern<<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, (int)ntiles, xmap, ymap, x_merged, y_merged);
-  return launched(CSV == 2 ? "wgrad3_s2_tma_cs8" : "wgrad3_s2_tma");
+  return launched(DW ? "dw_wgrad3_s2_tma" : (CSV == 2 ? "wgrad3_s2_tma_cs8" : "wgrad3_s2_tma"));
 }
 
 template <int TWT>
@@ -776,6 +811,17 @@ static int launch_s2_wgrad_tma(const S2Args& A, cudaStream_t st) {
   if (A.Cs % 8 == 0)
     return A.dbias_small ? launch_s2_wgrad_tma_b<TWT, 2, true>(A, st) : launch_s2_wgrad_tma_b<TWT, 2, false>(A, st);
   return A.dbias_small ? launch_s2_wgrad_tma_b<TWT, 1, true>(A, st) : launch_s2_wgrad_tma_b<TWT, 1, false>(A, st);
+}
+
+// depthwise stride-2 weight gradient on the TMA tile ring; NAS3D_ERR_UNSUPPORTED = not taken
+int tiled_dw_s2_wgrad_tma(const S2Args& A, cudaStream_t st) {
+  const bool ok = g_opt.s2_wgrad_tma && A.Cb == A.Cs && A.Cb % 4 == 0 && A.ld_big % 4 == 0 &&
+                  A.ld_small % 4 == 0 && aligned16(A.big) && aligned16(A.small) && A.Db == 2 * A.Ds &&
+                  A.Hb == 2 * A.Hs && A.Wb == 2 * A.Ws && A.Ws >= 2;
+  if (!ok) return NAS3D_ERR_UNSUPPORTED;
+  if (A.Ws <= 8)
+    return A.dbias_small ? launch_s2_wgrad_tma_b<8, 1, true, true>(A, st) : launch_s2_wgrad_tma_b<8, 1, false, true>(A, st);
+  return A.dbias_small ? launch_s2_wgrad_tma_b<16, 1, true, true>(A, st) : launch_s2_wgrad_tma_b<16, 1, false, true>(A, st);
 }
 
 int tiled_s2_wgrad(const S2Args& A, cudaStream_t st) {

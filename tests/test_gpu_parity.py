@@ -502,12 +502,18 @@ def test_tiled_depthwise_kernels_match_oracle(c, stride, transposed):
     r = torch.randn(yr.shape, generator=g)
     (yr * r).sum().backward()
     op = op.cuda()
-    for mode in ("tiled", "generic"):
-        with variant(tiled=0 if mode == "generic" else 1):
+    from nas_3d_unet_b200 import _lib
+    for mode in ("tiled", "tiled_cp_async", "generic"):
+        before = _lib.launch_counts()
+        with variant(tiled=0 if mode == "generic" else 1, s2_wgrad_tma=1 if mode == "tiled" else 0):
             op.zero_grad()
             xg = x.cuda().requires_grad_(True)
             y = op(xg)
             (y * r.cuda()).sum().backward()
+        after = _lib.launch_counts()
+        ran = {k for k, v in after.items() if v > before.get(k, 0)}
+        if stride == 2 and mode != "generic":
+            assert ("dw_wgrad3_s2_tma" in ran) == (mode == "tiled"), ran
         assert O.max_rel(y, yr) <= 1e-5, mode
         assert O.max_rel(xg.grad, xr.grad) <= 1e-5, mode
         for k in ('depth_conv.weight', 'depth_conv.bias', 'point_conv.weight', 'point_conv.bias'):

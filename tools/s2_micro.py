@@ -61,6 +61,28 @@ def run(cb, cs, S, N=8):
           "   ".join("%s %.1f us (%.1f TF/s)" % (k, t, gflop / t * 1e3) for k, t in out.items()), flush=True)
 
 
+def run_dw(c, S, N=8):
+    d = desc(c, c, S, N)
+    d.depthwise = 1
+    so = S // 2
+    big = torch.randn(N, S, S, S, c, device="cuda"); small = torch.randn(N, so, so, so, c, device="cuda")
+    dW = torch.zeros(c, 27, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    mb = 4e-6 * (big.numel() + small.numel())
+    out = {}
+
+    def wg():
+        _lib.check(lib.nas3d_conv_wgrad_ws(C.byref(d), small.data_ptr(), big.data_ptr(), None, 0, dW.data_ptr(), None, None, None, 0, st), "dw wgrad")
+    for name, v in (("dw_wgrad_tma", 1), ("dw_wgrad_cp", 0)):
+        with _lib.option("s2_wgrad_tma", v):
+            out[name] = timed(wg)
+    print("depthwise C%d @%d^3 N%d  %.0f MB   " % (c, S, N, mb) +
+          "   ".join("%s %.1f us (%.0f GB/s)" % (k, t, mb / t * 1e3) for k, t in out.items()), flush=True)
+
+
 if __name__ == "__main__":
+    run_dw(4, 128)
+    run_dw(8, 64)
+    run_dw(16, 32)
     for cb, cs, S in ((4, 4, 128), (4, 12, 128), (8, 8, 64), (16, 16, 32)):
         run(cb, cs, S)
