@@ -36,6 +36,11 @@ struct GnScratch {
   double red[32];
 };
 
+// one channel per thread with every group a run of cg adjacent lanes inside one warp
+__device__ __forceinline__ bool gn_lane_groups(int C, int cg) {
+  return C <= (int)blockDim.x && cg <= 32 && (cg & (cg - 1)) == 0;
+}
+
 // block-wide sum; every thread of the block must call it
 __device__ __forceinline__ double gn_block_sum(double v, double* red) {
   v = warp_sum(v);
@@ -56,6 +61,40 @@ __device__ __forceinline__ void gn_coef_body(const GnFwdBatch& B, int k, int n, 
   float* sh_mean = reinterpret_cast<float*>(sc.dA);
   float* sh_rstd = reinterpret_cast<float*>(sc.dB);
   const double* Sn = B.S[k] + (long long)n * C * 2;
+  if (gn_lane_groups(C, cg)) {
+    // One channel per thread, a group = cg adjacent lanes: every input is loaded up front (ONE
+    // global round trip), the group sums are xor-shuffle trees - no shared memory, no barrier.
+    // These coefficient kernels sit between every conv and the affine pass that consumes it; the
+    // two-phase form below cost 6-7.5 us per launch (ncu r4i), most of it dependent load latency.
+    const int c = threadIdx.x;
+    const bool on = c < C;
+    double s = 0.0, q = 0.0;
+    float gam = 0.f, bet = 0.f;
+    if (on) {
+      const double2 v = *reinterpret_cast<const double2*>(Sn + 2 * c);
+      s = v.x; q = v.y;
+      gam = B.gamma[k][c]; bet = B.beta[k][c];
+    }
+    for (int o = cg >> 1; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (on) {
+      const double mean = s * inv_m;
+      double var = q * inv_m - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const int g = c / cg;
+      if ((c & (cg - 1)) == 0) {
+        B.mr[k][((long long)n * G + g) * 2 + 0] = (float)mean;
+        B.mr[k][((long long)n * G + g) * 2 + 1] = rstd;
+      }
+      const float av = rstd * gam;
+      B.a[k][(long long)n * C + c] = av;
+      B.b[k][(long long)n * C + c] = bet - (float)mean * av;
+    }
+    return;
+  }
   __syncthreads();   // scratch may still be read by the previous call
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double s = 0.0, q = 0.0;
@@ -91,6 +130,50 @@ __device__ __forceinline__ void gn_bwd_coef_body(const GnBwdBatch& B, int k, int
   double* shA = sc.dA;
   double* shB = sc.dB;
   const double* Rn = B.R[k] + (long long)n * C * 2;
+  if (gn_lane_groups(C, cg)) {
+    // lane-group form (see gn_coef_body): all loads first, group sums by xor shuffles
+    const int c = threadIdx.x;
+    const bool on = c < C;
+    const int g = on ? c / cg : 0;
+    double r1 = 0.0, r2 = 0.0, sx = 0.0, mu_f = 0.0, rho = 0.0, gam = 0.0, av = 0.0, bv = 0.0;
+    if (on) {
+      const double2 rv = *reinterpret_cast<const double2*>(Rn + 2 * c);
+      r1 = rv.x; r2 = rv.y;
+      if (B.S[k]) sx = B.S[k][((long long)n * C + c) * 2];
+      mu_f = mean_rstd[((long long)n * G + g) * 2 + 0];
+      rho = mean_rstd[((long long)n * G + g) * 2 + 1];
+      gam = gamma[c];
+      if (side) { av = B.a[k][(long long)n * C + c]; bv = B.b[k][(long long)n * C + c]; }
+    }
+    const double sx_c = sx;
+    for (int o = cg >> 1; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    const double mu = B.S[k] ? sx * inv_m : mu_f;       // fp64 group mean (see below)
+    double Ag = gam * r1, Bg = gam * rho * (r2 - mu * r1);
+    for (int o = cg >> 1; o > 0; o >>= 1) {
+      Ag += __shfl_xor_sync(0xffffffffu, Ag, o);
+      Bg += __shfl_xor_sync(0xffffffffu, Bg, o);
+    }
+    double dwp = 0.0;
+    if (on) {
+      const double qq = -rho * rho * Bg * inv_m;
+      const double pp = wv * rho * gam;
+      const double rr = wv * (-qq * mu - rho * Ag * inv_m);
+      B.p[k][(long long)n * C + c] = (float)pp;
+      B.q[k][(long long)n * C + c] = (float)(wv * qq);
+      B.r[k][(long long)n * C + c] = (float)rr;
+      if (side) {
+        atomicAdd(&B.dgamma[k][c], (float)(wv * rho * (r2 - mu * r1)));
+        atomicAdd(&B.dbeta[k][c], (float)(wv * r1));
+        if (B.dbias[k]) atomicAdd(&B.dbias[k][c], (float)(pp * r1 + wv * qq * sx_c + rr * V));
+        dwp = av * (r2 - mu * r1) + (bv + mu_f * av) * r1;
+      }
+    }
+    if (B.dw[k] && side) {   // `side` is uniform over the block
+      const double tot = gn_block_sum(dwp, sc.red);
+      if (threadIdx.x == 0) atomicAdd(B.dw[k], (float)tot);
+    }
+    return;
+  }
   __syncthreads();
   // The group mean enters every term as (R2 - mu*R1) = sum dout*(x - mu): with |mu| >> std the two
   // products cancel, and a mean rounded to fp32 leaves a COHERENT error eps*|mu*R1| (measured at
