@@ -55,7 +55,8 @@ int nas3d_launch_labels(char* buf, int cap);
  * (NAS3D_<UPPERCASE NAME>) when the library is loaded and changed afterwards only here; no launch
  * path reads the environment.  Names: tiled, tma, tma_merged, affine_ring, apply_ring,
  * reduce_ring, pw_fwd_ring, reduce_waves, ring_min_log2, pw_vpt_sfb, pw_vpt_bfs, pw_vpt_mom,
- * umma_split_k, umma_wgrad, umma_wgrad_min_c, umma_ws, s2_wgrad_tma.  set: 0 or NAS3D_ERR_ARG
+ * umma_split_k, umma_wgrad, umma_wgrad_min_c, umma_ws, s1_wgrad_tma,
+ * s2_wgrad_tma.  set: 0 or NAS3D_ERR_ARG
  * (unknown name / value out of range); get: the value (>= 0) or NAS3D_ERR_ARG. */
 /* Roofline probe: one launch of pure packed-fp32-FMA chains (no memory traffic) over all SMs;
  * returns the flops it executes (> 0) or a negative status.  bench.py times it with CUDA events

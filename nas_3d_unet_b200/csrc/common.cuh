@@ -30,6 +30,7 @@ struct Options {
   int umma_wgrad = 1;     // tcgen05 weight gradient of the wide dense 3x3x3 convs (conv_umma_wgrad.cu)
   int umma_wgrad_min_c = 32;   // ... always from this channel count up; 16 channels only for small K
   int umma_ws = 1;        // warp-specialised tcgen05 fwd / dgrad kernel (0: the lock-step kernel)
+  int s1_wgrad_tma = 1;   // TMA tile ring for the stride-1 weight gradient at C = 4 / 8 (0: cp.async kernel)
   int s2_wgrad_tma = 1;   // TMA-staged double-buffered stride-2 weight gradient (0: cp.async kernel)
 };
 extern Options g_opt;

@@ -573,6 +573,295 @@ int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t s
   return NAS3D_ERR_UNSUPPORTED;
 }
 
+// =========================================================================================
+// stride-1 weight gradient on a TMA tile ring (same structure as wgrad3_s2_tma_kernel,
+// conv_tiled_s2.cu): 16 FMA warps + 1 producer warp, the haloed x tile and the dy tile of a
+// 32 x 12 x 4 voxel block arrive as two tensor copies (OOB zero-fill = the conv padding) on
+// full[s], the FMA warps hand the stage back on empty[s]; no staging instructions and no CTA
+// barrier in the tile loop.  The TMA tile is dense, so its pitches are box extents: the box is one
+// row (dil 1: 15 x 34) / one column (dil 2: 16 x 37) larger than needed, and the lanes' (kd, kh,
+// row) assignment is permuted so that every quarter-warp of the x LDS.128 hits 8 distinct bank
+// groups or the same address (exhaustive search, as for the stride-2 kernel).
+// byte = kd | kh << 2 | j << 4 | role << 6   (role 0: tap lane, 1: bias lane, 2: idle)
+// =========================================================================================
+#define S1T(kd, kh, j) ((kd) | (kh) << 2 | (j) << 4)
+__constant__ unsigned char kS1LaneTapD1[32] = {
+    S1T(0, 1, 0), S1T(0, 1, 2), S1T(0, 2, 1), S1T(0, 1, 1), S1T(0, 0, 2), S1T(0, 2, 0), S1T(0, 2, 2), S1T(0, 0, 1),
+    S1T(1, 1, 2), S1T(0, 0, 0), S1T(2, 1, 2), S1T(2, 2, 1), S1T(1, 0, 0), S1T(1, 2, 1), S1T(0, 0, 0) | 64, S1T(2, 2, 1) | 64,
+    S1T(1, 0, 1), S1T(2, 1, 0), S1T(2, 0, 1), S1T(1, 0, 2), S1T(2, 2, 2), S1T(1, 2, 0), S1T(1, 1, 1), S1T(1, 1, 0),
+    S1T(1, 2, 2), S1T(2, 0, 0), S1T(2, 1, 1), S1T(2, 0, 2), S1T(2, 2, 0), S1T(1, 2, 2) | 64, 128, 128};
+__constant__ unsigned char kS1LaneTapD2[32] = {
+    S1T(0, 1, 0), S1T(0, 1, 2), S1T(2, 0, 1), S1T(0, 1, 1), S1T(0, 0, 2), S1T(0, 2, 0), S1T(0, 1, 0) | 64, S1T(2, 0, 1) | 64,
+    S1T(1, 1, 2), S1T(0, 0, 0), S1T(2, 2, 1), S1T(2, 1, 1), S1T(2, 2, 2), S1T(1, 2, 0), S1T(0, 0, 1), S1T(1, 1, 2) | 64,
+    S1T(1, 0, 1), S1T(0, 2, 1), S1T(2, 0, 0), S1T(1, 0, 2), S1T(0, 2, 2), S1T(1, 1, 1), S1T(1, 1, 0), 128,
+    S1T(1, 2, 2), S1T(2, 1, 0), S1T(2, 1, 2), S1T(2, 0, 2), S1T(1, 0, 0), S1T(1, 2, 1), S1T(2, 2, 0), 128};
+#undef S1T
+
+template <int DIL, int CSV>
+struct WgS1TmaShape {
+  // 8 output channels per lane need ~140 registers: half the warps (and a tile half as deep) then
+  static constexpr int TW = 32, TH = 12, TD = CSV == 2 ? 2 : 4, NWARP = TD * TH / 3;   // consumer warps; + 1 producer warp
+  static constexpr int THREADS = 32 * (NWARP + 1);
+  static constexpr int PD = TD + 2 * DIL;
+  static constexpr int PH = TH + 2 * DIL + (DIL == 1 ? 1 : 0);    // box rows (one spare for dil 1)
+  static constexpr int PW = TW + 2 * DIL + (DIL == 2 ? 1 : 0);    // box columns (one spare for dil 2)
+  static constexpr int XPLANE = PH * PW;
+  static constexpr int XBYTES = PD * XPLANE * 16;
+  static constexpr int YROW = TW * CSV;                            // float4 per dy row
+  static constexpr int YBYTES = TD * TH * YROW * 16;
+  static constexpr int XPAD = (XBYTES + 127) / 128 * 128, YPAD = (YBYTES + 127) / 128 * 128;
+  static constexpr int STAGE = XPAD + YPAD;
+  static constexpr int NST = 3 * STAGE <= 226 * 1024 ? 3 : 2;
+  static constexpr int RED_TAP = 48 * CSV + 1;
+  static constexpr int NRED = 9 * RED_TAP + 4 * CSV;               // aliases stage 0 after the last tile
+  static constexpr size_t SMEM = NST * STAGE;
+  static constexpr int WN = 2 * DIL + 1;
+  static_assert(TD * TH == 3 * NWARP, "one 3-row group per warp");
+  static_assert(NST * STAGE <= 227 * 1024, "tile ring fits shared memory");
+  static_assert(DIL == 1 ? (PW % 8 == 2 && XPLANE % 8 == 6) : (PW % 8 == 5 && XPLANE % 8 == 0),
+                "kS1LaneTap tables assume these bank-group pitches");
+};
+
+__device__ __forceinline__ void s1_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "S1_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra S1_DONE;\n\t"
+      "bra S1_WAIT;\n\t"
+      "S1_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+template <int DIL, int CSV, bool BIAS>
+__global__ void __launch_bounds__(WgS1TmaShape<DIL, CSV>::THREADS)
+    wgrad3_s1_tma_kernel(const WgradArgs A, int C, int ntiles, const __grid_constant__ CUtensorMap xmap,
+                         const __grid_constant__ CUtensorMap ymap, int x_merged, int y_merged) {
+  using WS = WgS1TmaShape<DIL, CSV>;
+  constexpr int TW = WS::TW, TH = WS::TH, PW = WS::PW, NST = WS::NST, WN = WS::WN;
+  extern __shared__ __align__(128) unsigned char base[];
+  __shared__ __align__(8) unsigned long long full_bar[NST], empty_bar[NST];
+  float* red = reinterpret_cast<float*>(base);
+
+  const int C4S = C / (4 * CSV);
+  const int cic = blockIdx.y / C4S, coc = blockIdx.y % C4S;   // cic: 4 input channels, coc: 4*CSV output
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned code = DIL == 1 ? kS1LaneTapD1[lane] : kS1LaneTapD2[lane];
+  const int kd = code & 3, kh = (code >> 2) & 3, j = (code >> 4) & 3, role = code >> 6;
+  const bool tap_lane = role == 0, active = role < 2;
+
+  float2 acc[CSV][3][4][2];   // [co chunk][kw][ci][co pair]: FFMA2 accumulators
+  float4 bsum[CSV];
+#pragma unroll
+  for (int v = 0; v < CSV; ++v) {
+    bsum[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) acc[v][t][a][c] = make_float2(0.f, 0.f);
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NST; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&empty_bar[b])),
+                   "r"(WS::NWARP));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == WS::NWARP) {
+    // ---- producer ---------------------------------------------------------------------------
+    if (lane == 0) {
+      int buf = 0, parity = 0;
+#pragma unroll 1
+      for (long long tile = blockIdx.x, k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+        if (k >= NST)
+          s1_mbar_wait((unsigned)__cvta_generic_to_shared(&empty_bar[buf]), (unsigned)(parity ^ 1));
+        unsigned b = (unsigned)tile;
+        const int tw = (int)(b % (unsigned)A.tiles_w); b /= (unsigned)A.tiles_w;
+        const int th = (int)(b % (unsigned)A.tiles_h); b /= (unsigned)A.tiles_h;
+        const int td = (int)(b % (unsigned)A.tiles_d);
+        const int n = (int)(b / (unsigned)A.tiles_d);
+        const int w0 = tw * TW, h0 = th * TH, d0 = td * WS::TD;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar[buf]);
+        const unsigned dx = (unsigned)__cvta_generic_to_shared(base + buf * WS::STAGE);
+        const unsigned dy = dx + WS::XPAD;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                     "r"((unsigned)(WS::XBYTES + WS::YBYTES))
+                     : "memory");
+        if (x_merged)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dx),
+              "l"(&xmap), "r"((w0 - DIL) * 4), "r"(h0 - DIL), "r"(d0 - DIL), "r"(n), "r"(bar)
+              : "memory");
+        else
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dx),
+              "l"(&xmap), "r"(cic * 4), "r"(w0 - DIL), "r"(h0 - DIL), "r"(d0 - DIL), "r"(n), "r"(bar)
+              : "memory");
+        if (y_merged)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dy),
+              "l"(&ymap), "r"(w0 * 4 * CSV), "r"(h0), "r"(d0), "r"(n), "r"(bar)
+              : "memory");
+        else
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dy),
+              "l"(&ymap), "r"(coc * 4 * CSV), "r"(w0), "r"(h0), "r"(d0), "r"(n), "r"(bar)
+              : "memory");
+        if (++buf == NST) { buf = 0; parity ^= 1; }
+      }
+    }
+  } else {
+    // ---- consumers --------------------------------------------------------------------------
+    const int row = warp * 3 + j;
+    const int pd = row / TH, ph = row % TH;
+    const int xoff = (pd + kd * DIL) * WS::XPLANE + (ph + kh * DIL) * PW, yoff = row * WS::YROW;
+    int buf = 0, parity = 0;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      s1_mbar_wait((unsigned)__cvta_generic_to_shared(&full_bar[buf]), (unsigned)parity);
+      if (active) {
+        const float4* xr = reinterpret_cast<const float4*>(base + buf * WS::STAGE) + xoff;
+        const float4* yr = reinterpret_cast<const float4*>(base + buf * WS::STAGE + WS::XPAD) + yoff;
+        // circular window: slot q holds xr[wb + q] at the top of every WN-step block
+        float4 win[WN];
+#pragma unroll
+        for (int q = 0; q < WN - 1; ++q) win[q] = xr[q];
+        constexpr int NFULL = TW / WN;
+#pragma unroll 2
+        for (int blk = 0; blk < NFULL; ++blk) {
+          const float4* xq = xr + blk * WN;
+          const float4* yq = yr + blk * WN * CSV;
+#pragma unroll
+          for (int u = 0; u < WN; ++u) {
+            win[(u + WN - 1) % WN] = xq[u + WN - 1];
+#pragma unroll
+            for (int v = 0; v < CSV; ++v) {
+              const float4 g = yq[u * CSV + v];
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) outer4(acc[v][kw], win[(u + kw * DIL) % WN], g);
+              if (BIAS) { bsum[v].x += g.x; bsum[v].y += g.y; bsum[v].z += g.z; bsum[v].w += g.w; }
+            }
+          }
+        }
+        {
+          const float4* xq = xr + NFULL * WN;
+          const float4* yq = yr + NFULL * WN * CSV;
+#pragma unroll
+          for (int u = 0; u < TW % WN; ++u) {
+            win[(u + WN - 1) % WN] = xq[u + WN - 1];
+#pragma unroll
+            for (int v = 0; v < CSV; ++v) {
+              const float4 g = yq[u * CSV + v];
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) outer4(acc[v][kw], win[(u + kw * DIL) % WN], g);
+              if (BIAS) { bsum[v].x += g.x; bsum[v].y += g.y; bsum[v].z += g.z; bsum[v].w += g.w; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(&empty_bar[buf]))
+                     : "memory");
+      if (++buf == NST) { buf = 0; parity ^= 1; }
+    }
+  }
+
+  // ---- flush once per CTA (the ring is idle: every issued tile has been consumed) ----------------
+  __syncthreads();
+  for (int i = threadIdx.x; i < WS::NRED; i += WS::THREADS) red[i] = 0.f;
+  __syncthreads();
+  const int kdkh = kd * 3 + kh;
+  if (warp < WS::NWARP) {
+    if (tap_lane) {
+#pragma unroll
+      for (int v = 0; v < CSV; ++v)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              atomicAdd(&red[kdkh * WS::RED_TAP + (kw * 4 + a) * (4 * CSV) + v * 4 + c],
+                        (c & 1) ? acc[v][kw][a][c >> 1].y : acc[v][kw][a][c >> 1].x);
+    } else if (BIAS && role == 1) {
+#pragma unroll
+      for (int v = 0; v < CSV; ++v) {
+        atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 0], bsum[v].x); atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 1], bsum[v].y);
+        atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 2], bsum[v].z); atomicAdd(&red[9 * WS::RED_TAP + v * 4 + 3], bsum[v].w);
+      }
+    }
+  }
+  __syncthreads();
+  // red[kd,kh][kw][ci][co] -> dW[co][ci][tap]
+  for (int i = threadIdx.x; i < 27 * 16 * CSV; i += WS::THREADS) {
+    const int co = coc * 4 * CSV + i % (4 * CSV), ci = cic * 4 + (i / (4 * CSV)) % 4, t = i / (16 * CSV);
+    atomicAdd(A.dW + ((long long)co * C + ci) * 27 + t, red[(t / 3) * WS::RED_TAP + i - (t / 3) * 48 * CSV]);
+  }
+  if (BIAS && A.dbias && cic == 0 && threadIdx.x < 4 * CSV)
+    atomicAdd(A.dbias + coc * 4 * CSV + threadIdx.x, red[9 * WS::RED_TAP + threadIdx.x]);
+}
+
+template <int DIL, int CSV, bool BIAS>
+static int launch_wgrad3_tma_b(WgradArgs A, int C, cudaStream_t st) {
+  using WS = WgS1TmaShape<DIL, CSV>;
+  CUtensorMap xmap, ymap;
+  memset(&xmap, 0, sizeof(xmap));
+  memset(&ymap, 0, sizeof(ymap));
+  int x_merged = 0, y_merged = 0;
+  if (C == 4 && A.ldx == 4 && make_ndhwc_merged_map(&xmap, A.x, 4, A.W, A.H, A.D, A.N, WS::PW, WS::PH, WS::PD))
+    x_merged = 1;
+  else if (!make_ndhwc_map(&xmap, A.x, C, A.W, A.H, A.D, A.N, A.ldx, WS::PW, WS::PH, WS::PD))
+    return NAS3D_ERR_UNSUPPORTED;
+  if (C == 4 * CSV && A.ldy == C &&
+      make_ndhwc_merged_map(&ymap, A.dy, C, A.W, A.H, A.D, A.N, WS::TW, WS::TH, WS::TD))
+    y_merged = 1;
+  else if (!make_ndhwc_map(&ymap, A.dy, C, A.W, A.H, A.D, A.N, A.ldy, WS::TW, WS::TH, WS::TD, 4 * CSV))
+    return NAS3D_ERR_UNSUPPORTED;
+  A.tiles_w = (A.W + WS::TW - 1) / WS::TW;
+  A.tiles_h = (A.H + WS::TH - 1) / WS::TH;
+  A.tiles_d = (A.D + WS::TD - 1) / WS::TD;
+  auto kern = wgrad3_s1_tma_kernel<DIL, CSV, BIAS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NAS3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS::SMEM));
+    attr_done = true;
+  }
+  const long long ntiles = (long long)A.N * A.tiles_w * A.tiles_h * A.tiles_d;
+  const int pairs = (C / 4) * (C / (4 * CSV));
+  long long gx = (long long)kNumSMs / pairs;           // one CTA per SM (the ring takes the shared memory)
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  kern<<<dim3((unsigned)gx, pairs), WS::THREADS, WS::SMEM, st>>>(A, C, (int)ntiles, xmap, ymap, x_merged, y_merged);
+  return launched(CSV == 2 ? "wgrad3_s1_tma_cs8" : "wgrad3_s1_tma");
+}
+
+// NAS3D_ERR_UNSUPPORTED = not taken (the cp.async kernel serves the shape)
+static int launch_wgrad3_tma(int C, int dil, const WgradArgs& A, cudaStream_t st) {
+  if (!g_opt.s1_wgrad_tma || A.xs != 1 || A.ys != 1 || A.W < 32) return NAS3D_ERR_UNSUPPORTED;
+  if (C == 4) {
+    if (dil == 1) return A.dbias ? launch_wgrad3_tma_b<1, 1, true>(A, C, st) : launch_wgrad3_tma_b<1, 1, false>(A, C, st);
+    if (dil == 2) return A.dbias ? launch_wgrad3_tma_b<2, 1, true>(A, C, st) : launch_wgrad3_tma_b<2, 1, false>(A, C, st);
+  }
+  if (C == 8 || C == 16) {
+    if (dil == 1) return A.dbias ? launch_wgrad3_tma_b<1, 2, true>(A, C, st) : launch_wgrad3_tma_b<1, 2, false>(A, C, st);
+    if (dil == 2) return A.dbias ? launch_wgrad3_tma_b<2, 2, true>(A, C, st) : launch_wgrad3_tma_b<2, 2, false>(A, C, st);
+  }
+  return NAS3D_ERR_UNSUPPORTED;
+}
+
 int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st) {
   if (A.W < 4 || A.ldx % 4 || A.ldy % 4 || !aligned16(A.x) || !aligned16(A.dy)) return NAS3D_ERR_UNSUPPORTED;
   if (C % 4 || C > 64) return NAS3D_ERR_UNSUPPORTED;
@@ -584,6 +873,10 @@ int tiled_wgrad3_s1(int C, int dil, const WgradArgs& A, cudaStream_t st) {
   auto padded = [&](int th, int td) {
     return (long long)((A.H + th - 1) / th * th) * ((A.D + td - 1) / td * td);
   };
+  {
+    const int rc = launch_wgrad3_tma(C, dil, A, st);
+    if (rc != NAS3D_ERR_UNSUPPORTED) return rc;
+  }
   const long long p12 = padded(12, 4), p68 = padded(6, 8), p64 = padded(6, 4);
   const int cfg = (p12 <= p68 && p12 <= p64) ? 0 : (p68 <= p64 ? 1 : 2);
 #define NAS3D_WG(TWT)                                                              \

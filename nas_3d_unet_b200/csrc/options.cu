@@ -28,6 +28,7 @@ static const OptEntry kOptions[] = {
     {"umma_wgrad", &Options::umma_wgrad, 0, 1},
     {"umma_wgrad_min_c", &Options::umma_wgrad_min_c, 16, 128},
     {"umma_ws", &Options::umma_ws, 0, 1},
+    {"s1_wgrad_tma", &Options::s1_wgrad_tma, 0, 1},
     {"s2_wgrad_tma", &Options::s2_wgrad_tma, 0, 1},
 };
 

@@ -246,14 +246,24 @@ def test_tiled_conv_kernels_match_oracle_on_ragged_volume(c, dil):
     (yr * r).sum().backward()
     op = op.cuda()
     outs = {}
-    for mode in ("tiled", "generic"):
-        with variant(tiled=0 if mode == "generic" else 1):
+    from nas_3d_unet_b200 import _lib
+    for mode in ("tiled", "tiled_cp_async", "generic"):
+        before = _lib.launch_counts()
+        with variant(tiled=0 if mode == "generic" else 1, s1_wgrad_tma=1 if mode == "tiled" else 0):
             op.zero_grad()
             xg = x.cuda().requires_grad_(True)
             y = op(xg)
             (y * r.cuda()).sum().backward()
             outs[mode] = (y.detach().cpu(), xg.grad.cpu(), op.conv.weight.grad.cpu().clone(),
                           op.conv.bias.grad.cpu().clone())
+        after = _lib.launch_counts()
+        ran = {k for k, v in after.items() if v > before.get(k, 0)}
+        tma_shape = c in (4, 8)       # launch_wgrad3_tma (conv_tiled.cu); 16 channels, small K: tcgen05
+        if mode == "tiled":
+            assert bool(ran & {"wgrad3_s1_tma", "wgrad3_s1_tma_cs8"}) == tma_shape, ran
+        elif mode == "tiled_cp_async":
+            assert not ran & {"wgrad3_s1_tma", "wgrad3_s1_tma_cs8"}, ran
+            assert "wgrad3_s1" in ran or c == 16, ran      # (16 channels, small K: tcgen05 wgrad)
     for mode, (y, dx, dw, db) in outs.items():
         assert O.max_rel(y, yr) <= 1e-5, mode
         assert O.max_rel(dx, xr.grad) <= 1e-5, mode
