@@ -607,7 +607,10 @@ struct WgS1TmaShape {
   static constexpr int PW = TW + 2 * DIL + (DIL == 2 ? 1 : 0);    // box columns (one spare for dil 2)
   static constexpr int XPLANE = PH * PW;
   static constexpr int XBYTES = PD * XPLANE * 16;
-  static constexpr int YROW = TW * CSV;                            // float4 per dy row
+  // dy box one column wider than the tile: with a row pitch of 32 float4 the 3 dy rows a warp reads
+  // share a bank group and every dy LDS.128 took 12 wavefronts instead of 4 (ncu r8c)
+  static constexpr int YW = TW + 1;
+  static constexpr int YROW = YW * CSV;                            // float4 per dy row
   static constexpr int YBYTES = TD * TH * YROW * 16;
   static constexpr int XPAD = (XBYTES + 127) / 128 * 128, YPAD = (YBYTES + 127) / 128 * 128;
   static constexpr int STAGE = XPAD + YPAD;
@@ -826,9 +829,9 @@ static int launch_wgrad3_tma_b(WgradArgs A, int C, cudaStream_t st) {
   else if (!make_ndhwc_map(&xmap, A.x, C, A.W, A.H, A.D, A.N, A.ldx, WS::PW, WS::PH, WS::PD))
     return NAS3D_ERR_UNSUPPORTED;
   if (C == 4 * CSV && A.ldy == C &&
-      make_ndhwc_merged_map(&ymap, A.dy, C, A.W, A.H, A.D, A.N, WS::TW, WS::TH, WS::TD))
+      make_ndhwc_merged_map(&ymap, A.dy, C, A.W, A.H, A.D, A.N, WS::YW, WS::TH, WS::TD))
     y_merged = 1;
-  else if (!make_ndhwc_map(&ymap, A.dy, C, A.W, A.H, A.D, A.N, A.ldy, WS::TW, WS::TH, WS::TD, 4 * CSV))
+  else if (!make_ndhwc_map(&ymap, A.dy, C, A.W, A.H, A.D, A.N, A.ldy, WS::YW, WS::TH, WS::TD, 4 * CSV))
     return NAS3D_ERR_UNSUPPORTED;
   A.tiles_w = (A.W + WS::TW - 1) / WS::TW;
   A.tiles_h = (A.H + WS::TH - 1) / WS::TH;

@@ -463,7 +463,7 @@ struct WgS2TmaShape {
   static constexpr int PD = 2 * TD + 1, PH = 2 * TH + 1, PW = 2 * TW + 1;
   static constexpr int XPLANE = PH * PW;
   static constexpr int XBYTES = PD * XPLANE * 16;
-  static constexpr int YW = TW;
+  static constexpr int YW = TW + 1;               // spare column: the warp's 3 dy rows start in different bank groups
   static constexpr int YROW = YW * CSV;           // float4 per dy row
   static constexpr int YBYTES = TD * TH * YROW * 16;
   static constexpr int XPAD = (XBYTES + 127) / 128 * 128, YPAD = (YBYTES + 127) / 128 * 128;
