@@ -563,11 +563,16 @@ int tiled_conv3_s1(int C, int dil, bool flip, const TiledArgs& A, cudaStream_t s
   if (C == CC && dil == DD)                                                      \
     return flip ? launch_conv3<CC, DD, HG, DG, MD, true>(A, st)                  \
                 : launch_conv3<CC, DD, HG, DG, MD, false>(A, st);
+  // (C, dil, HG, DG, MD): tile = 32 x 4*HG x MD*DG voxels.  Smaller tiles than round 1's where they
+  // let another CTA share the SM (measured, tools/conv_micro.py, 8 x 128^3 / 8 x 64^3, fwd / dgrad us):
+  // C4 dil 2 (4,2)->(2,2): 346 -> 315 / 312 -> 294; C8 dil 2 (2,2)->(1,2), one CTA per SM before:
+  // 245 -> 202 / 228 -> 185; C8 dil 1 (2,2)->(1,2): 174 -> 164 / 167 -> 156; C16 dil 1 (2,1)->(1,1) at
+  // 8 x 32^3: 100 -> 90 / 93 -> 83 (dil 2: slower, stays); C4 dil 1 stays (4,2).
   NAS3D_CASE(4, 1, 4, 2, 2)
-  NAS3D_CASE(4, 2, 4, 2, 2)
-  NAS3D_CASE(8, 1, 2, 2, 2)
-  NAS3D_CASE(8, 2, 2, 2, 2)
-  NAS3D_CASE(16, 1, 2, 1, 2)
+  NAS3D_CASE(4, 2, 2, 2, 2)
+  NAS3D_CASE(8, 1, 1, 2, 2)
+  NAS3D_CASE(8, 2, 1, 2, 2)
+  NAS3D_CASE(16, 1, 1, 1, 2)
   NAS3D_CASE(16, 2, 2, 1, 2)
 #undef NAS3D_CASE
   return NAS3D_ERR_UNSUPPORTED;
