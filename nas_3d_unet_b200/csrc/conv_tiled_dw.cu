@@ -198,7 +198,8 @@ constexpr int DB_TDB = 4, DB_THB = 16, DB_TWB = 64, DB_SD = 3, DB_SH = 9, DB_SW 
 constexpr int DB_THREADS = 512;
 constexpr size_t DB_SMEM = sizeof(float4) * (DB_SD * DB_SH * DB_SW + 32);
 
-__global__ void __launch_bounds__(DB_THREADS) dw3_s2_bfs_kernel(const S2Args A) {
+// register cap for two resident CTAs (78 registers x 512 threads left one): 130 -> 94 us at C4 8 x 64^3 -> 128^3
+__global__ void __launch_bounds__(DB_THREADS, 2) dw3_s2_bfs_kernel(const S2Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);
   float4* wsm = tile + DB_SD * DB_SH * DB_SW;

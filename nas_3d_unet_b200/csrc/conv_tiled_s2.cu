@@ -161,13 +161,14 @@ __global__ void __launch_bounds__(S2FwdShape<CIN, COUT, HG, DG>::THREADS, S2FwdS
 template <int C>
 struct S2BfsShape {
   static constexpr int C4 = C / 4;
-  static constexpr int TDB = 4, THB = 16, TWB = 64;               // big tile
+  // big tile; C = 8: 8 rows (512 threads, two CTAs per SM) - 58 -> 46 us at 8 x 64^3 -> 32^3
+  static constexpr int TDB = 4, THB = C == 8 ? 8 : 16, TWB = 64;
   static constexpr int SD = TDB / 2 + 1, SH = THB / 2 + 1, SW = TWB / 2 + 1;   // small tile
   static constexpr int PLANE = SD * SH * SW;
   static constexpr int THREADS = 32 * (THB / 4) * TDB * C4;
-  // C = 4: 512 threads at 80 registers left one CTA per SM; capped at 64 two are resident
+  // 512 threads at 80-84 registers left one CTA per SM; capped at 64 two are resident
   // (tools/conv_micro.py stride 2, 8 x 128^3: dgrad 143.6 -> 110.7 us, profiles/r4j_minb_micro.txt)
-  static constexpr int MINB = C == 4 ? 2 : 0;
+  static constexpr int MINB = 2;
   static constexpr size_t SMEM = sizeof(float4) * PLANE * C4 + sizeof(float) * 27 * C * C;
 };
 

@@ -76,6 +76,15 @@ def run_dw(c, S, N=8):
     for name, v in (("dw_wgrad_tma", 1), ("dw_wgrad_cp", 0)):
         with _lib.option("s2_wgrad_tma", v):
             out[name] = timed(wg)
+    w = torch.randn(c, 27, device="cuda")
+
+    def fwd():
+        _lib.check(lib.nas3d_conv_small_from_big(C.byref(d), big.data_ptr(), w.data_ptr(), None, None, 0, 0, small.data_ptr(), 0, None, st), "dw fwd")
+
+    def dgrad():
+        _lib.check(lib.nas3d_conv_big_from_small(C.byref(d), small.data_ptr(), w.data_ptr(), None, None, 0, None, big.data_ptr(), 0, None, st), "dw dgrad")
+    out["dw_fwd"] = timed(fwd)
+    out["dw_dgrad"] = timed(dgrad)
     print("depthwise C%d @%d^3 N%d  %.0f MB   " % (c, S, N, mb) +
           "   ".join("%s %.1f us (%.0f GB/s)" % (k, t, mb / t * 1e3) for k, t in out.items()), flush=True)
 
@@ -84,5 +93,7 @@ if __name__ == "__main__":
     run_dw(4, 128)
     run_dw(8, 64)
     run_dw(16, 32)
+    if "--dw-only" in sys.argv:
+        sys.exit(0)
     for cb, cs, S in ((4, 4, 128), (4, 12, 128), (8, 8, 64), (16, 16, 32)):
         run(cb, cs, S)
