@@ -23,6 +23,7 @@ import torch  # noqa: E402
 
 METRIC = "searched-net 128^3 train patches/s"
 UNIT = "patches/s"
+H2D_DELAY_MS_DEFAULT = -1.0     # < 0: GraphedStep.stream() paces the prefetch from its own measurements
 
 
 def parse():
@@ -61,6 +62,8 @@ def parse():
                          "modules, torch.optim.Adam, fp32 labels, loss.item() in the step) and add it to the "
                          "line as `drivers_loop`")
     ap.add_argument("--e2e-probe", action="store_true", help="print an e2e overhead breakdown to stderr")
+    ap.add_argument("--h2d-delay-ms", type=float, default=H2D_DELAY_MS_DEFAULT,
+                    help="e2e: issue the prefetch of batch i+1 this long after step i started (GraphedStep.stream); < 0 = measured")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel table (json) here")
@@ -477,7 +480,7 @@ def run_ours(args):
         if graphed is not None:
             # GraphedStep.stream: batch i+1 goes H2D straight into the idle static input set while
             # graph i runs; every step's loss comes back to the host (4 bytes), read one step late
-            for last in graphed.stream(host_batches(nsteps)):
+            for last in graphed.stream(host_batches(nsteps), h2d_delay_s=None if args.h2d_delay_ms < 0 else args.h2d_delay_ms * 1e-3):
                 pass
             return last
         for batch in DevicePrefetcher(host_batches(nsteps), dev):

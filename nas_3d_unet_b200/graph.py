@@ -77,12 +77,24 @@ class GraphedStep:
         self.load(*inputs)
         return self.replay()
 
-    def stream(self, host_batches, scalar=lambda out: out.reshape(-1)[-1]):
+    def stream(self, host_batches, scalar=lambda out: out.reshape(-1)[-1], h2d_delay_s=None):
         """run every batch of `host_batches` (tuples of pinned host tensors shaped like the example
         inputs) through the captured step; yields `scalar(step output)` of each step as a python
         float, in order, each value one step late (after the NEXT step has been enqueued).
         Per step the timeline holds: one H2D of the batch into the idle static input set (copy
-        stream, overlapping the running graph), one graph launch, one 4-byte D2H."""
+        stream, overlapping the running graph), one graph launch, one 4-byte D2H.
+
+        With two input sets the prefetch is PACED: the copy of batch i+1 is issued h2d_delay_s after
+        graph i started instead of together with it, so that the DMA writes land in the step's
+        FMA-/latency-bound middle and end rather than in its HBM-bound first third (measured on B200,
+        searched net 8 x 128^3: the copy engine's 285 MB slow the streaming kernels down
+        disproportionately - e2e 457.9 patches/s unpaced, 478.0 with 9 ms; profiles/r12_h2d_delay.txt).
+        h2d_delay_s = None (default) measures the graph and the copy with CUDA events and uses
+        graph - copy - 1 ms, i.e. the copy ends just before the next graph needs it; 0 when the
+        copy is the longer of the two (many GPUs behind one host).  0.0 = unpaced."""
+        import time
+        auto = h2d_delay_s is None or h2d_delay_s < 0
+        delay = 0.0 if auto else float(h2d_delay_s)
         dev = self.static_in[0].device
         main = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
@@ -93,15 +105,23 @@ class GraphedStep:
         consumed = [None] * nset          # main-stream event: graph k has read its inputs
         it = iter(host_batches)
 
+        copy_events = [None]              # (start, end) of the most recent H2D (auto pacing)
+
         def issue(k, batch):
             ins = self.sets[k][0]
             with torch.cuda.stream(cs):
                 if consumed[k] is not None:
                     cs.wait_event(consumed[k])
+                c0 = None
+                if auto:
+                    c0 = torch.cuda.Event(enable_timing=True)
+                    c0.record(cs)
                 for s, h in zip(ins, batch):
                     s.copy_(h, non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=auto)
                 ev.record(cs)
+                if auto:
+                    copy_events[0] = (c0, ev)
             return ev
 
         try:
@@ -110,12 +130,14 @@ class GraphedStep:
             return
         ready = issue(0, nxt)
         pending = None                    # (event, pinned slot) of the previous step's scalar
+        prev_graph_events = None
         i = 0
         while ready is not None:
             k = i % nset
             cur_ready = ready
             ready = None
-            if nset > 1:                  # prefetch batch i+1 into the other set while graph k runs
+            paced = nset > 1 and (auto or delay > 0)
+            if nset > 1 and not paced:    # prefetch batch i+1 into the other set while graph k runs
                 try:
                     ready = issue((i + 1) % nset, next(it))
                 except StopIteration:
@@ -123,10 +145,15 @@ class GraphedStep:
             main.wait_event(cur_ready)
             for o in self.optimizers:
                 o.sync()
+            g0 = None
+            if auto:
+                g0 = torch.cuda.Event(enable_timing=True)
+                g0.record(main)
             self.sets[k][1].replay()
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=auto)
             ev.record(main)
             consumed[k] = ev
+            graph_events = (g0, ev)
             slot = self._pinned[k]
             slot.copy_(scalar(self.sets[k][2]).detach().reshape(1), non_blocking=True)
             done = torch.cuda.Event()
@@ -136,9 +163,32 @@ class GraphedStep:
                     ready = issue(0, next(it))
                 except StopIteration:
                     pass
+            prev = None
             if pending is not None:
-                pending[0].synchronize()
-                yield float(pending[1])
+                pending[0].synchronize()          # step i-1 is done: graph i starts about now
+                prev = float(pending[1])
+                if auto and prev_graph_events is not None and copy_events[0] is not None:
+                    # graph i-1 has finished; the copy of batch i was issued during it
+                    c0, c1 = copy_events[0]
+                    if c1.query():
+                        g_ms = prev_graph_events[0].elapsed_time(prev_graph_events[1])
+                        c_ms = c0.elapsed_time(c1)
+                        delay = max(0.0, min(g_ms - c_ms - 1.0, 0.7 * g_ms)) * 1e-3
+                    else:
+                        delay = 0.0               # the graph is waiting for the copy: do not hold it back
+            if auto:
+                prev_graph_events = graph_events
+            if paced:
+                t0 = time.perf_counter()
+                try:
+                    nxt = next(it)
+                    while time.perf_counter() - t0 < delay:
+                        pass
+                    ready = issue((i + 1) % nset, nxt)
+                except StopIteration:
+                    pass
+            if prev is not None:
+                yield prev
             # the slot is overwritten nset steps from now; its value is read (above) before that
             pending = (done, slot) if nset > 1 else None
             if nset == 1:
